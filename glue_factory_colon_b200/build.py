@@ -1,0 +1,83 @@
+"""Builds csrc/*.cu into lib/liblightglue_b200.so with nvcc for sm_100a.
+
+In-tree build (the .so travels to the GPU box with the repo snapshot).  nvcc
+cross-compiles without a GPU.  Re-run is incremental per translation unit.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+CSRC = ROOT / "csrc"
+LIB_DIR = ROOT / "lib"
+LIB = LIB_DIR / "liblightglue_b200.so"
+OBJ_DIR = LIB_DIR / "obj"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found; the LightGlue B200 library cannot be built")
+
+
+def _digest(src: Path) -> str:
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(src.read_bytes())
+    for hdr in sorted(CSRC.glob("*.cuh")) + [ROOT.parent / "include" / "lightglue_b200.h"]:
+        h.update(hdr.read_bytes())
+    return h.hexdigest()
+
+
+def _compile(nvcc: str, src: Path, verbose: bool) -> Path:
+    obj = OBJ_DIR / (src.stem + ".o")
+    stamp = OBJ_DIR / (src.stem + ".sha")
+    dig = _digest(src)
+    if obj.exists() and stamp.exists() and stamp.read_text() == dig:
+        return obj
+    cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src.name}:\n{res.stdout}\n{res.stderr}")
+    stamp.write_text(dig)
+    return obj
+
+
+def build(verbose: bool = False, force: bool = False) -> Path:
+    nvcc = _nvcc()
+    OBJ_DIR.mkdir(parents=True, exist_ok=True)
+    if force:
+        for f in OBJ_DIR.glob("*"):
+            f.unlink()
+    sources = sorted(CSRC.glob("*.cu"))
+    with ThreadPoolExecutor(max_workers=min(8, len(sources))) as pool:
+        objs = list(pool.map(lambda s: _compile(nvcc, s, verbose), sources))
+    newest = max(o.stat().st_mtime for o in objs)
+    if force or not LIB.exists() or LIB.stat().st_mtime < newest:
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *map(str, objs)]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(verbose=True, force="--force" in sys.argv))

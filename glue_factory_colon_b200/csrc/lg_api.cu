@@ -1,0 +1,94 @@
+// extern "C" dispatch for the compute-bound entry points (include/lightglue_b200.h).
+#include "lg_internal.cuh"
+
+extern "C" int lgb200_linear(int precision, int epilogue, const void* A0, const void* A1, int K0,
+                             const void* W, const float* bias, int T, int N, int K,
+                             const int32_t* lens, int Lp, float scale0, float scale1, float scale2,
+                             const float* resid32, float* out32, void* out16, const float* rot,
+                             int n_rot, void* outp0, void* outp1, void* outp2, const float* gamma,
+                             const float* beta, void* stream) {
+  if (!A0 || !W || !bias) return LGB200_ERR_NULL;
+  if (T <= 0 || N <= 0 || K <= 0 || K0 <= 0 || K0 > K || Lp <= 0 || Lp % 128 || T % Lp)
+    return LGB200_ERR_SHAPE;
+  if (K0 < K && !A1) return LGB200_ERR_NULL;
+  LgEpi e;
+  e.mode = epilogue;
+  e.N = N;
+  e.Lp = Lp;
+  e.bias = bias;
+  e.scale[0] = scale0; e.scale[1] = scale1; e.scale[2] = scale2;
+  e.resid32 = resid32;
+  e.out32 = out32;
+  e.out16 = reinterpret_cast<__nv_bfloat16*>(out16);
+  e.rot = rot;
+  e.n_rot = n_rot;
+  e.outp[0] = outp0; e.outp[1] = outp1; e.outp[2] = outp2;
+  e.gamma = gamma;
+  e.beta = beta;
+  switch (epilogue) {
+    case LGB200_EPI_ROWMAJOR:
+      if (!out32 && !out16) return LGB200_ERR_NULL;
+      break;
+    case LGB200_EPI_HEADS: {
+      if (N % 256 || N / 256 > 3) return LGB200_ERR_SHAPE;
+      for (int p = 0; p < N / 256; ++p)
+        if (!e.outp[p]) return LGB200_ERR_NULL;
+      if (n_rot > 0 && !rot) return LGB200_ERR_NULL;
+      break;
+    }
+    case LGB200_EPI_LN_GELU:
+      if (N != 512) return LGB200_ERR_SHAPE;
+      if (!gamma || !beta) return LGB200_ERR_NULL;
+      break;
+    default:
+      return LGB200_ERR_PRECISION;
+  }
+  cudaStream_t st = lg_stream(stream);
+  if (precision == LGB200_F32)
+    return lg_simt_linear(epilogue, (const float*)A0, (const float*)A1, K0, (const float*)W, T, N, K,
+                          lens, e, st);
+  if (precision == LGB200_BF16)
+    return lg_tc_linear(epilogue, (const __nv_bfloat16*)A0, (const __nv_bfloat16*)A1, K0,
+                        (const __nv_bfloat16*)W, T, N, K, lens, e, st);
+  return LGB200_ERR_PRECISION;
+}
+
+extern "C" int lgb200_attention(int precision, const void* Q, const void* K, const void* V, int S,
+                                int Lp, const int32_t* lens, int kv_xor, void* ctx, void* stream) {
+  if (!Q || !K || !V || !ctx) return LGB200_ERR_NULL;
+  if (S <= 0 || Lp <= 0 || Lp % 128 || (kv_xor != 0 && kv_xor != 1) || (kv_xor && (S & 1)))
+    return LGB200_ERR_SHAPE;
+  cudaStream_t st = lg_stream(stream);
+  if (precision == LGB200_F32)
+    return lg_simt_attention((const float*)Q, (const float*)K, (const float*)V, S, Lp, lens, kv_xor,
+                             (float*)ctx, st);
+  if (precision == LGB200_BF16)
+    return lg_tc_attention((const __nv_bfloat16*)Q, (const __nv_bfloat16*)K, (const __nv_bfloat16*)V, S,
+                           Lp, lens, kv_xor, (__nv_bfloat16*)ctx, st);
+  return LGB200_ERR_PRECISION;
+}
+
+extern "C" int lgb200_assign_lse(int precision, const void* md, int S, int Lp, const int32_t* lens,
+                                 float* lse, void* stream) {
+  if (!md || !lse) return LGB200_ERR_NULL;
+  if (S <= 0 || (S & 1) || Lp <= 0 || Lp % 128) return LGB200_ERR_SHAPE;
+  cudaStream_t st = lg_stream(stream);
+  if (precision == LGB200_F32) return lg_simt_assign_lse((const float*)md, S, Lp, lens, lse, st);
+  if (precision == LGB200_BF16)
+    return lg_tc_assign_lse((const __nv_bfloat16*)md, S, Lp, lens, lse, st);
+  return LGB200_ERR_PRECISION;
+}
+
+extern "C" int lgb200_assign_scores(int precision, const void* md, const float* z, const float* lse,
+                                    int B, int Lp, const int32_t* lens, int R, int C, float* scores,
+                                    void* stream) {
+  if (!md || !z || !lse || !scores) return LGB200_ERR_NULL;
+  if (B <= 0 || Lp <= 0 || Lp % 128 || R < 1 || C < 1 || R - 1 > Lp || C - 1 > Lp)
+    return LGB200_ERR_SHAPE;
+  cudaStream_t st = lg_stream(stream);
+  if (precision == LGB200_F32)
+    return lg_simt_assign_scores((const float*)md, z, lse, B, Lp, lens, R, C, scores, st);
+  if (precision == LGB200_BF16)
+    return lg_tc_assign_scores((const __nv_bfloat16*)md, z, lse, B, Lp, lens, R, C, scores, st);
+  return LGB200_ERR_PRECISION;
+}

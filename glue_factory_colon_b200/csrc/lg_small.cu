@@ -1,0 +1,476 @@
+// HBM-bound helper kernels of the LightGlue hot path: input staging, positional
+// encoding, per-token heads, early-exit test, point-pruning compaction and
+// filter_matches.  All are streaming kernels: coalesced 16-byte accesses, warp
+// shuffles for reductions, no shared-memory tiling needed.
+#include "lg_common.cuh"
+
+extern "C" int lgb200_abi_version(void) { return LGB200_ABI_VERSION; }
+
+extern "C" int lgb200_device_ok(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return LGB200_ERR_ARCH;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+    return LGB200_ERR_ARCH;
+  return major == 10 ? LGB200_OK : LGB200_ERR_ARCH;
+}
+
+extern "C" const char* lgb200_error_string(int code) {
+  switch (code) {
+    case LGB200_OK: return "ok";
+    case LGB200_ERR_SHAPE: return "unsupported shape or alignment";
+    case LGB200_ERR_NULL: return "required pointer is NULL";
+    case LGB200_ERR_PRECISION: return "unknown precision or epilogue";
+    case LGB200_ERR_DRIVER: return "cuTensorMapEncodeTiled unavailable or failed";
+    case LGB200_ERR_ARCH: return "device is not sm_100";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+  }
+}
+
+// ---------------------------------------------------------------------------
+// pack_rows: [B,n,dim] fp32 -> sequence-major rows (+ bf16 shadow), zero padding
+// ---------------------------------------------------------------------------
+__global__ void pack_rows_kernel(const float* __restrict__ src, int n, int dim4, int img, int Lp,
+                                 float* __restrict__ x32, __nv_bfloat16* __restrict__ x16) {
+  const int b = blockIdx.y;
+  const int s = 2 * b + img;
+  const int total = Lp * dim4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int l = i / dim4, c4 = i - l * dim4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (l < n) v = reinterpret_cast<const float4*>(src)[((size_t)b * n + l) * dim4 + c4];
+    const size_t o = ((size_t)s * Lp + l) * dim4 + c4;
+    reinterpret_cast<float4*>(x32)[o] = v;
+    if (x16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(x16)[o] = pk;
+    }
+  }
+}
+
+extern "C" int lgb200_pack_rows(const float* src, int B, int n, int dim, int img, int Lp,
+                                float* x32, void* x16, void* stream) {
+  if (!src || !x32) return LGB200_ERR_NULL;
+  if (dim % 4 || Lp % 128 || n > Lp || B <= 0 || (img != 0 && img != 1)) return LGB200_ERR_SHAPE;
+  const int total = Lp * (dim / 4);
+  dim3 grid((total + 255) / 256 > 148 * 4 ? 148 * 4 : (total + 255) / 256, B);
+  pack_rows_kernel<<<grid, 256, 0, lg_stream(stream)>>>(src, n, dim / 4, img, Lp, x32,
+                                                        reinterpret_cast<__nv_bfloat16*>(x16));
+  LG_LAUNCH_CHECK();
+  return LGB200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// posenc: keypoint normalisation + Fourier projection + cos/sin table
+// ---------------------------------------------------------------------------
+// One CTA per pair-image: phase 1 finds shift/scale (given size, or the extent
+// of the valid points), phase 2 writes rot[l, 2f] = cos, rot[l, 2f+1] = sin.
+__global__ void posenc_kernel(const float* __restrict__ kpts, int n, int kdim,
+                              const float* __restrict__ size, const float* __restrict__ Wr,
+                              const int32_t* __restrict__ lens, int img, int Lp,
+                              float* __restrict__ rot) {
+  const int b = blockIdx.x;
+  const int s = 2 * b + img;
+  const int nv = lens ? min(lens[s], n) : n;
+  const float* kp = kpts + (size_t)b * n * kdim;
+  __shared__ float red[4][32];
+  __shared__ float sh_shift[2], sh_scale;
+  __shared__ float sW[32 * 4];
+  for (int i = threadIdx.x; i < 32 * kdim; i += blockDim.x) sW[i] = Wr[i];
+  if (size) {
+    if (threadIdx.x == 0) {
+      const float w = size[b * 2 + 0], h = size[b * 2 + 1];
+      sh_shift[0] = w / 2.f;
+      sh_shift[1] = h / 2.f;
+      sh_scale = fmaxf(w, h) / 2.f;
+    }
+  } else {
+    float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    for (int l = threadIdx.x; l < nv; l += blockDim.x) {
+      const float x = kp[(size_t)l * kdim], y = kp[(size_t)l * kdim + 1];
+      mnx = fminf(mnx, x); mxx = fmaxf(mxx, x);
+      mny = fminf(mny, y); mxy = fmaxf(mxy, y);
+    }
+    for (int o = 16; o; o >>= 1) {
+      mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+      mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+      mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+      mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+    }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { red[0][w] = mnx; red[1][w] = mny; red[2][w] = mxx; red[3][w] = mxy; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int nw = blockDim.x >> 5;
+      for (int i = 1; i < nw; ++i) {
+        red[0][0] = fminf(red[0][0], red[0][i]); red[1][0] = fminf(red[1][0], red[1][i]);
+        red[2][0] = fmaxf(red[2][0], red[2][i]); red[3][0] = fmaxf(red[3][0], red[3][i]);
+      }
+      const float sx = 1.f + red[2][0] - red[0][0], sy = 1.f + red[3][0] - red[1][0];
+      sh_shift[0] = sx / 2.f;
+      sh_shift[1] = sy / 2.f;
+      sh_scale = fmaxf(sx, sy) / 2.f;
+    }
+  }
+  __syncthreads();
+  const float shx = sh_shift[0], shy = sh_shift[1], sc = sh_scale;
+  // thread = (point, frequency); 32 consecutive threads write one 256-byte row
+  for (int i = threadIdx.x; i < Lp * 32; i += blockDim.x) {
+    const int l = i >> 5, f = i & 31;
+    float2 cs = make_float2(0.f, 0.f);
+    if (l < nv) {
+      const float x = (kp[(size_t)l * kdim] - shx) / sc;
+      const float y = (kp[(size_t)l * kdim + 1] - shy) / sc;
+      float p = x * sW[f * kdim] + y * sW[f * kdim + 1];
+      if (kdim == 4) p += kp[(size_t)l * kdim + 2] * sW[f * 4 + 2] + kp[(size_t)l * kdim + 3] * sW[f * 4 + 3];
+      sincosf(p, &cs.y, &cs.x);
+    }
+    reinterpret_cast<float2*>(rot)[((size_t)s * Lp + l) * 32 + f] = cs;
+  }
+}
+
+extern "C" int lgb200_posenc(const float* kpts, int B, int n, int kdim, const float* size,
+                             const float* Wr, const int32_t* lens, int img, int Lp, float* rot,
+                             void* stream) {
+  if (!kpts || !Wr || !rot) return LGB200_ERR_NULL;
+  if ((kdim != 2 && kdim != 4) || Lp % 128 || n > Lp || B <= 0) return LGB200_ERR_SHAPE;
+  posenc_kernel<<<B, 1024, 0, lg_stream(stream)>>>(kpts, n, kdim, size, Wr, lens, img, Lp, rot);
+  LG_LAUNCH_CHECK();
+  return LGB200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// rowdot: Linear(256,1) (+sigmoid) per token.  One warp per row, 2x float4 per lane.
+// ---------------------------------------------------------------------------
+__global__ void rowdot_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                              const float* __restrict__ bias, int S, int Lp,
+                              const int32_t* __restrict__ lens, int sig, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= S * Lp) return;
+  const int s = row / Lp, l = row - s * Lp;
+  if (lens && l >= lens[s]) return;  // rows past the valid prefix are left untouched
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * LG_D);
+  const float4* wr = reinterpret_cast<const float4*>(w);
+  const float4 a0 = xr[lane], a1 = xr[lane + 32], w0 = wr[lane], w1 = wr[lane + 32];
+  float acc = a0.x * w0.x + a0.y * w0.y + a0.z * w0.z + a0.w * w0.w + a1.x * w1.x + a1.y * w1.y +
+              a1.z * w1.z + a1.w * w1.w;
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    acc += bias[0];
+    out[row] = sig ? lg_sigmoid(acc) : acc;
+  }
+}
+
+extern "C" int lgb200_rowdot(const float* x32, const float* w, const float* b, int S, int Lp,
+                             const int32_t* lens, int apply_sigmoid, float* out, void* stream) {
+  if (!x32 || !w || !b || !out) return LGB200_ERR_NULL;
+  const long rows = (long)S * Lp;
+  const int blocks = (int)((rows * 32 + 255) / 256);
+  rowdot_kernel<<<blocks, 256, 0, lg_stream(stream)>>>(x32, w, b, S, Lp, lens, apply_sigmoid, out);
+  LG_LAUNCH_CHECK();
+  return LGB200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// exit_check: one CTA per pair
+// ---------------------------------------------------------------------------
+__global__ void exit_check_kernel(const float* __restrict__ conf, int Lp,
+                                  const int32_t* __restrict__ lens,
+                                  const int32_t* __restrict__ total, float thr, float depth_conf,
+                                  int layer, int32_t* __restrict__ done,
+                                  int32_t* __restrict__ lens_active) {
+  const int b = blockIdx.x;
+  if (done[b] != 0) return;
+  int cnt = 0;
+  for (int img = 0; img < 2; ++img) {
+    const int s = 2 * b + img;
+    const int n = lens[s];
+    for (int l = threadIdx.x; l < n; l += blockDim.x) cnt += conf[(size_t)s * Lp + l] < thr;
+  }
+  __shared__ int red[32];
+  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int c = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) c += red[i];
+    // lightglue.py:579-580 in fp32: 1.0 - sum/num_points > depth_confidence
+    const float ratio = 1.0f - __fdiv_rn((float)c, (float)total[b]);
+    if (ratio > depth_conf) {
+      done[b] = layer + 1;
+      lens_active[2 * b] = 0;
+      lens_active[2 * b + 1] = 0;
+    }
+  }
+}
+
+extern "C" int lgb200_exit_check(const float* conf, int B, int Lp, const int32_t* lens,
+                                 const int32_t* total, float thr, float depth_conf, int layer,
+                                 int32_t* done, int32_t* lens_active, void* stream) {
+  if (!conf || !lens || !total || !done || !lens_active) return LGB200_ERR_NULL;
+  exit_check_kernel<<<B, 512, 0, lg_stream(stream)>>>(conf, Lp, lens, total, thr, depth_conf, layer,
+                                                      done, lens_active);
+  LG_LAUNCH_CHECK();
+  return LGB200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// prune_compact: stable stream compaction of token rows, one CTA per sequence
+// ---------------------------------------------------------------------------
+// Phase 1: keep flags + block-wide exclusive scan (1024 threads, chunks of 1024)
+//          -> dst position per row in shared memory (Lp <= 8192).
+// Phase 2: warps copy kept rows (x32 1 KB, x16 512 B, rot 256 B, ind) to the
+//          destination buffers with 16-byte accesses.
+#define LG_MAX_LP 8192
+__global__ void __launch_bounds__(1024) prune_compact_kernel(
+    const float* __restrict__ match, const float* __restrict__ conf, float thr, float keep_above,
+    int Lp, int32_t* __restrict__ lens, int32_t* __restrict__ lens_active,
+    const float* __restrict__ x32s, float* __restrict__ x32d, const __nv_bfloat16* __restrict__ x16s,
+    __nv_bfloat16* __restrict__ x16d, const float* __restrict__ rots, float* __restrict__ rotd,
+    const int32_t* __restrict__ inds, int32_t* __restrict__ indd, int32_t* __restrict__ prune_cnt) {
+  __shared__ int16_t dst[LG_MAX_LP];
+  __shared__ int warp_sum[32];
+  __shared__ int running;
+  const int s = blockIdx.x;
+  const int n = lens[s];
+  const bool active = lens_active[s] != 0;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) running = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int l = base + threadIdx.x;
+    int keep = 0;
+    if (l < n) {
+      if (!active) {
+        keep = 1;
+      } else {
+        keep = match[(size_t)s * Lp + l] > keep_above;
+        if (conf) keep |= conf[(size_t)s * Lp + l] <= thr;
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    const int pre = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) warp_sum[wid] = __popc(bal);
+    __syncthreads();
+    int woff = 0, tot = 0;
+    for (int i = 0; i < 32; ++i) {
+      const int v = warp_sum[i];
+      if (i < wid) woff += v;
+      tot += v;
+    }
+    const int r0 = running;
+    if (l < n) dst[l] = keep ? (int16_t)(r0 + woff + pre) : (int16_t)-1;
+    __syncthreads();
+    if (threadIdx.x == 0) running = r0 + tot;
+    __syncthreads();
+  }
+  const int kept = running;
+  // phase 2: one warp per row
+  for (int l = wid; l < n; l += 32) {
+    const int d = dst[l];
+    if (d < 0) continue;
+    const size_t so = (size_t)s * Lp + l, dofs = (size_t)s * Lp + d;
+    const float4* a = reinterpret_cast<const float4*>(x32s + so * LG_D);
+    float4* o = reinterpret_cast<float4*>(x32d + dofs * LG_D);
+    o[lane] = a[lane];
+    o[lane + 32] = a[lane + 32];
+    if (x16s) {
+      reinterpret_cast<uint4*>(x16d + dofs * LG_D)[lane] =
+          reinterpret_cast<const uint4*>(x16s + so * LG_D)[lane];
+    }
+    reinterpret_cast<float2*>(rotd + dofs * 64)[lane] = reinterpret_cast<const float2*>(rots + so * 64)[lane];
+    if (lane == 0) {
+      const int orig = inds[so];
+      indd[dofs] = orig;
+      if (active) prune_cnt[(size_t)s * Lp + orig] += 1;
+    }
+  }
+  if (threadIdx.x == 0 && active) {
+    lens[s] = kept;
+    lens_active[s] = kept;
+  }
+}
+
+extern "C" int lgb200_prune_compact(const float* match, const float* conf, float thr,
+                                    float width_conf, int S, int Lp, int32_t* lens,
+                                    int32_t* lens_active, const float* x32_src, float* x32_dst,
+                                    const void* x16_src, void* x16_dst, const float* rot_src,
+                                    float* rot_dst, const int32_t* ind_src, int32_t* ind_dst,
+                                    int32_t* prune_cnt, void* stream) {
+  if (!match || !lens || !lens_active || !x32_src || !x32_dst || !rot_src || !rot_dst || !ind_src ||
+      !ind_dst || !prune_cnt)
+    return LGB200_ERR_NULL;
+  if (Lp > LG_MAX_LP || Lp % 128) return LGB200_ERR_SHAPE;
+  // lightglue.py:564: keep = scores > (1 - width_confidence), evaluated in fp32
+  const float keep_above = 1.0f - width_conf;
+  prune_compact_kernel<<<S, 1024, 0, lg_stream(stream)>>>(
+      match, conf, thr, keep_above, Lp, lens, lens_active, x32_src, x32_dst,
+      reinterpret_cast<const __nv_bfloat16*>(x16_src), reinterpret_cast<__nv_bfloat16*>(x16_dst),
+      rot_src, rot_dst, ind_src, ind_dst, prune_cnt);
+  LG_LAUNCH_CHECK();
+  return LGB200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// filter_matches
+// ---------------------------------------------------------------------------
+// Pass A streams the score matrix once.  A CTA owns a strip of FM_ROWS rows and
+// 128 columns per step (each thread one float4 of one row); row maxima are
+// reduced with warp shuffles, column maxima with packed 64-bit atomicMax on
+// (ordered value << 32 | ~index), which also resolves ties to the lowest index.
+// Pass B does the mutual check, exp, threshold and scatter.
+
+__device__ __forceinline__ unsigned long long fm_pack(float v, int idx) {
+  unsigned u = __float_as_uint(v);
+  unsigned key;
+  if (v != v) key = 0xffffffffu;                    // NaN is the maximum (torch.max)
+  else key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  if (key == 0xffffffffu && v == v) key = 0xfffffffeu;  // keep NaN strictly above everything
+  return ((unsigned long long)key << 32) | (unsigned)(0xffffffffu - (unsigned)idx);
+}
+__device__ __forceinline__ float fm_value(unsigned long long p) {
+  const unsigned key = (unsigned)(p >> 32);
+  if (key == 0xffffffffu) return __uint_as_float(0x7fc00000u);
+  const unsigned u = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ int fm_index(unsigned long long p) {
+  return (int)(0xffffffffu - (unsigned)(p & 0xffffffffu));
+}
+
+#define FM_ROWS 32
+__global__ void __launch_bounds__(256) fm_argmax_kernel(const float* __restrict__ scores, int R, int C,
+                                                        const int32_t* __restrict__ lens,
+                                                        unsigned long long* __restrict__ best0,
+                                                        unsigned long long* __restrict__ best1) {
+  const int b = blockIdx.y;
+  const int n0 = lens ? lens[2 * b] : R - 1, n1 = lens ? lens[2 * b + 1] : C - 1;
+  const int r0 = blockIdx.x * FM_ROWS;
+  if (r0 >= n0 || n1 <= 0) return;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;  // 8 warps, 4 rows each
+  const float* base = scores + (size_t)b * R * C;
+  unsigned long long* b0 = best0 + (size_t)b * R;
+  unsigned long long* b1 = best1 + (size_t)b * C;
+  __shared__ unsigned long long colbest[8][128];
+  unsigned long long rowbest[FM_ROWS / 8];
+#pragma unroll
+  for (int i = 0; i < FM_ROWS / 8; ++i) rowbest[i] = 0ull;
+  for (int c0 = 0; c0 < n1; c0 += 128) {
+    unsigned long long cb[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+    for (int i = 0; i < FM_ROWS / 8; ++i) {
+      const int r = r0 + wid * (FM_ROWS / 8) + i;
+      if (r < n0) {
+        const float* rowp = base + (size_t)r * C;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = c0 + lane + 32 * j;  // coalesced 128-byte row segments
+          if (c < n1) {
+            const float v = rowp[c];
+            const unsigned long long pr = fm_pack(v, c), pc = fm_pack(v, r);
+            rowbest[i] = pr > rowbest[i] ? pr : rowbest[i];
+            cb[j] = pc > cb[j] ? pc : cb[j];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) colbest[wid][lane + 32 * j] = cb[j];
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      unsigned long long m = colbest[0][threadIdx.x];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) m = colbest[w][threadIdx.x] > m ? colbest[w][threadIdx.x] : m;
+      const int c = c0 + threadIdx.x;
+      if (c < n1 && m != 0ull) atomicMax(b1 + c, m);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < FM_ROWS / 8; ++i) {
+    unsigned long long m = rowbest[i];
+    for (int o = 16; o; o >>= 1) {
+      const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
+      m = t > m ? t : m;
+    }
+    const int r = r0 + wid * (FM_ROWS / 8) + i;
+    if (lane == 0 && r < n0) b0[r] = m;
+  }
+}
+
+__global__ void fm_fill_kernel(int64_t* m0, int64_t* m1, float* ms0, float* ms1, long n0tot, long n1tot) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n0tot) { m0[i] = -1; ms0[i] = 0.f; }
+  if (i < n1tot) { m1[i] = -1; ms1[i] = 0.f; }
+}
+
+__global__ void fm_mutual_kernel(int R, int C, const int32_t* __restrict__ lens, float th,
+                                 const unsigned long long* __restrict__ best0,
+                                 const unsigned long long* __restrict__ best1,
+                                 const int32_t* __restrict__ ind0, const int32_t* __restrict__ ind1,
+                                 int ind_ld, int N0, int N1, int64_t* __restrict__ m0,
+                                 int64_t* __restrict__ m1, float* __restrict__ ms0,
+                                 float* __restrict__ ms1) {
+  const int b = blockIdx.y;
+  const int n0 = lens ? lens[2 * b] : R - 1, n1 = lens ? lens[2 * b + 1] : C - 1;
+  if (n0 <= 0 || n1 <= 0) return;  // lightglue.py:298-303: everything stays -1 / 0
+  const unsigned long long* b0 = best0 + (size_t)b * R;
+  const unsigned long long* b1 = best1 + (size_t)b * C;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n0) {
+    const int j = fm_index(b0[i]);
+    const bool mutual = fm_index(b1[j]) == i;
+    const float sc = mutual ? expf(fm_value(b0[i])) : 0.f;
+    const bool valid = mutual && (sc > th);
+    const int oi = ind0 ? ind0[(size_t)b * ind_ld + i] : i;
+    const int oj = ind1 ? ind1[(size_t)b * ind_ld + j] : j;
+    m0[(size_t)b * N0 + oi] = valid ? (int64_t)oj : -1;
+    ms0[(size_t)b * N0 + oi] = sc;
+  }
+  if (i < n1) {
+    const int r = fm_index(b1[i]);
+    const bool mutual1 = fm_index(b0[r]) == i;
+    // mscores1 = mutual1 ? mscores0[m1] : 0 ; valid1 = mutual1 & valid0[m1]
+    // (mutual1 implies row r's best column is i, hence mutual0[r])
+    const float sc = mutual1 ? expf(fm_value(b0[r])) : 0.f;
+    const bool valid = mutual1 && (sc > th);
+    const int oi = ind1 ? ind1[(size_t)b * ind_ld + i] : i;
+    const int orow = ind0 ? ind0[(size_t)b * ind_ld + r] : r;
+    m1[(size_t)b * N1 + oi] = valid ? (int64_t)orow : -1;
+    ms1[(size_t)b * N1 + oi] = sc;
+  }
+}
+
+extern "C" int lgb200_filter_matches(const float* scores, int B, int R, int C, const int32_t* lens,
+                                     float threshold, const int32_t* ind0, const int32_t* ind1,
+                                     int ind_ld, int N0, int N1, int64_t* m0, int64_t* m1,
+                                     float* ms0, float* ms1, void* workspace, void* stream) {
+  if (!m0 || !m1 || !ms0 || !ms1) return LGB200_ERR_NULL;
+  if (B <= 0 || R < 1 || C < 1 || N0 < 0 || N1 < 0) return LGB200_ERR_SHAPE;
+  cudaStream_t st = lg_stream(stream);
+  const long n0tot = (long)B * N0, n1tot = (long)B * N1;
+  const long mx = n0tot > n1tot ? n0tot : n1tot;
+  if (mx > 0) {
+    fm_fill_kernel<<<(unsigned)((mx + 255) / 256), 256, 0, st>>>(m0, m1, ms0, ms1, n0tot, n1tot);
+    LG_LAUNCH_CHECK();
+  }
+  if (R == 1 || C == 1) return LGB200_OK;  // empty side
+  if (!scores || !workspace) return LGB200_ERR_NULL;
+  unsigned long long* best0 = reinterpret_cast<unsigned long long*>(workspace);
+  unsigned long long* best1 = best0 + (size_t)B * R;
+  cudaError_t e = cudaMemsetAsync(workspace, 0, sizeof(unsigned long long) * (size_t)B * (R + C), st);
+  if (e != cudaSuccess) return (int)e;
+  dim3 g1((R - 1 + FM_ROWS - 1) / FM_ROWS, B);
+  fm_argmax_kernel<<<g1, 256, 0, st>>>(scores, R, C, lens, best0, best1);
+  LG_LAUNCH_CHECK();
+  const int mxn = (R > C ? R : C) - 1;
+  dim3 g2((mxn + 255) / 256, B);
+  fm_mutual_kernel<<<g2, 256, 0, st>>>(R, C, lens, threshold, best0, best1, ind0, ind1, ind_ld, N0, N1,
+                                       m0, m1, ms0, ms1);
+  LG_LAUNCH_CHECK();
+  return LGB200_OK;
+}

@@ -1,0 +1,487 @@
+"""B200-native drop-in for `gluefactory.models.matchers.lightglue.LightGlue`.
+
+Host side of the hot path.  Mirrors the reference's plugin contract
+(reference: gluefactory/models/matchers/lightglue.py, cited as lightglue.py:LINE):
+
+  * discovery: this module exposes `__main_model__` (reference
+    models/__init__.py:20-25), so `model.matcher.name=glue_factory_colon_b200.lightglue`
+    selects it through the reference's own `get_model` with no reference edits;
+  * construction: `LightGlue(conf)` with the conf keys of lightglue.py:323-343,
+    unknown keys accepted (the reference merge is non-struct, lightglue.py:351);
+  * parameters: identical names and shapes (252 state-dict entries), so
+    `matcher.*` checkpoints load unchanged;
+  * call: `forward(data) -> dict` with the keys of lightglue.py:541-553.
+
+All arithmetic runs in the hand-written sm_100a kernels of
+`lib/liblightglue_b200.so` (C ABI: include/lightglue_b200.h).  PyTorch is used
+for parameter storage, device memory and the stream only.  There is no CPU or
+PyTorch fallback: CPU inputs raise.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _abi
+from ._abi import BF16, EPI_HEADS, EPI_LN_GELU, EPI_ROWMAJOR, F32, check, ptr
+
+LOG2E = 1.4426950408889634
+
+
+class _Conf(dict):
+    """Minimal attribute dict (the reference uses OmegaConf; not a dependency here)."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as exc:
+            raise AttributeError(k) from exc
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def _merge_conf(default: dict, conf) -> _Conf:
+    out = _Conf()
+    for k, v in default.items():
+        out[k] = _merge_conf(v, {}) if isinstance(v, dict) else v
+    if conf is None:
+        return out
+    try:  # OmegaConf objects, when the caller has omegaconf
+        from omegaconf import OmegaConf  # type: ignore
+
+        if OmegaConf.is_config(conf):
+            conf = OmegaConf.to_container(conf, resolve=True)
+    except Exception:
+        pass
+    for k, v in dict(conf).items():
+        if isinstance(v, dict) and isinstance(out.get(k), dict):
+            out[k] = _merge_conf(out[k], v)
+        else:
+            out[k] = v
+    return out
+
+
+# ----- parameter holders: same module tree / names as the reference -----------------
+
+
+def _ffn(d: int) -> nn.Sequential:
+    # indices 0,1,3 carry parameters (lightglue.py:144-149); index 2 is the GELU slot
+    return nn.Sequential(nn.Linear(2 * d, 2 * d), nn.LayerNorm(2 * d), nn.Identity(), nn.Linear(2 * d, d))
+
+
+class _SelfBlockParams(nn.Module):  # lightglue.py:132-149
+    def __init__(self, d: int):
+        super().__init__()
+        self.Wqkv = nn.Linear(d, 3 * d)
+        self.out_proj = nn.Linear(d, d)
+        self.ffn = _ffn(d)
+
+
+class _CrossBlockParams(nn.Module):  # lightglue.py:167-184
+    def __init__(self, d: int):
+        super().__init__()
+        self.to_qk = nn.Linear(d, d)
+        self.to_v = nn.Linear(d, d)
+        self.to_out = nn.Linear(d, d)
+        self.ffn = _ffn(d)
+
+
+class _LayerParams(nn.Module):  # lightglue.py:225-229
+    def __init__(self, d: int):
+        super().__init__()
+        self.self_attn = _SelfBlockParams(d)
+        self.cross_attn = _CrossBlockParams(d)
+
+
+class _AssignParams(nn.Module):  # lightglue.py:272-277
+    def __init__(self, d: int):
+        super().__init__()
+        self.matchability = nn.Linear(d, 1)
+        self.final_proj = nn.Linear(d, d)
+
+
+class _TokenParams(nn.Module):  # lightglue.py:69-72
+    def __init__(self, d: int):
+        super().__init__()
+        self.token = nn.Sequential(nn.Linear(d, 1), nn.Identity())
+
+
+class _PosEncParams(nn.Module):  # lightglue.py:53-59
+    def __init__(self, m: int, f_dim: int):
+        super().__init__()
+        self.Wr = nn.Linear(m, f_dim // 2, bias=False)
+        nn.init.normal_(self.Wr.weight.data, mean=0, std=1.0)
+
+
+class LightGlue(nn.Module):
+    default_conf = {
+        "name": "lightglue",
+        "input_dim": 256,
+        "add_scale_ori": False,
+        "descriptor_dim": 256,
+        "n_layers": 9,
+        "num_heads": 4,
+        "flash": False,  # accepted for compatibility; attention is always the fused flash kernel
+        "mp": False,  # True -> bf16 tcgen05 kernels (see `precision`)
+        "depth_confidence": -1,
+        "width_confidence": -1,
+        "filter_threshold": 0.0,
+        "checkpointed": False,
+        "weights": None,
+        "weights_from_version": "v0.1_arxiv",
+        "loss": {"gamma": 1.0, "fn": "nll", "nll_balancing": 0.5},
+        # B200 extension: "fp32" (CUDA-core parity kernels), "bf16" (tcgen05 kernels),
+        # "auto" = bf16 when conf.mp or torch autocast is active, else fp32.
+        "precision": "auto",
+    }
+
+    required_data_keys = ["keypoints0", "keypoints1", "descriptors0", "descriptors1"]
+
+    def __init__(self, conf=None) -> None:
+        super().__init__()
+        self.conf = conf = _merge_conf(self.default_conf, conf)
+        d = conf.descriptor_dim
+        if d != 256 or conf.num_heads != 4:
+            raise NotImplementedError("the B200 kernels are specialised for descriptor_dim=256, num_heads=4")
+        if conf.input_dim != d:
+            self.input_proj = nn.Linear(conf.input_dim, d, bias=True)
+        else:
+            self.input_proj = nn.Identity()
+        self.posenc = _PosEncParams(2 + 2 * bool(conf.add_scale_ori), d // conf.num_heads)
+        n = conf.n_layers
+        self.transformers = nn.ModuleList([_LayerParams(d) for _ in range(n)])
+        self.log_assignment = nn.ModuleList([_AssignParams(d) for _ in range(n)])
+        self.token_confidence = nn.ModuleList([_TokenParams(d) for _ in range(n - 1)])
+        if conf.weights is not None:
+            self._load_weights(conf.weights)
+        self.register_buffer(
+            "confidence_thresholds",
+            torch.Tensor([self.confidence_threshold(i) for i in range(n)]),
+        )
+        self._packed: Dict = {}
+        self._pack_key = None
+
+    # ---- reference-compatible helpers ------------------------------------------------
+
+    def confidence_threshold(self, layer_index: int) -> float:  # lightglue.py:555-558
+        t = 0.8 + 0.1 * np.exp(-4.0 * layer_index / self.conf.n_layers)
+        return float(np.clip(t, 0, 1))
+
+    def _load_weights(self, weights) -> None:  # lightglue.py:375-401 (local files only: no network)
+        from pathlib import Path
+
+        if not Path(weights).exists():
+            raise FileNotFoundError(f"weights file {weights} not found (no download path in this build)")
+        sd = torch.load(str(weights), map_location="cpu")
+        for i in range(self.conf.n_layers):
+            sd = {k.replace(f"self_attn.{i}", f"transformers.{i}.self_attn"): v for k, v in sd.items()}
+            sd = {k.replace(f"cross_attn.{i}", f"transformers.{i}.cross_attn"): v for k, v in sd.items()}
+        self.load_state_dict(sd, strict=False)
+
+    def compile(self, mode="reduce-overhead"):  # lightglue.py:410-420: nothing to compile
+        return self
+
+    def loss(self, pred, data):
+        # TwoViewPipeline.loss skips components raising NotImplementedError
+        # (reference two_view_pipeline.py:417-429).  Training is outside this path.
+        raise NotImplementedError("training loss is not part of the B200 inference hot path")
+
+    # ---- weight packing ------------------------------------------------------------------
+
+    def _precision(self) -> int:
+        p = self.conf.precision
+        if p == "auto":
+            p = "bf16" if (self.conf.mp or torch.is_autocast_enabled()) else "fp32"
+        if p not in ("fp32", "bf16"):
+            raise ValueError(f"precision must be fp32, bf16 or auto, got {p}")
+        return BF16 if p == "bf16" else F32
+
+    def _pack(self, prec: int, device) -> Dict:
+        key = (prec, str(device), tuple((p.data_ptr(), p._version) for p in self.parameters()))
+        if self._pack_key == key:
+            return self._packed
+        wdt = torch.bfloat16 if prec == BF16 else torch.float32
+
+        def W(t):
+            return t.detach().to(device=device, dtype=wdt).contiguous()
+
+        def Fp(t):
+            return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+        # Wqkv rows: reference row = head*192 + d*3 + part (lightglue.py:158) -> part*256 + head*64 + d
+        perm = torch.arange(768).view(4, 64, 3).permute(2, 0, 1).reshape(-1)
+        layers = []
+        for lyr in self.transformers:
+            sa, ca = lyr.self_attn, lyr.cross_attn
+            layers.append(
+                dict(
+                    qkv_w=W(sa.Wqkv.weight[perm]), qkv_b=Fp(sa.Wqkv.bias[perm]),
+                    so_w=W(sa.out_proj.weight), so_b=Fp(sa.out_proj.bias),
+                    sf0_w=W(sa.ffn[0].weight), sf0_b=Fp(sa.ffn[0].bias),
+                    sln_g=Fp(sa.ffn[1].weight), sln_b=Fp(sa.ffn[1].bias),
+                    sf3_w=W(sa.ffn[3].weight), sf3_b=Fp(sa.ffn[3].bias),
+                    cqv_w=W(torch.cat([ca.to_qk.weight, ca.to_v.weight], 0)),
+                    cqv_b=Fp(torch.cat([ca.to_qk.bias, ca.to_v.bias], 0)),
+                    co_w=W(ca.to_out.weight), co_b=Fp(ca.to_out.bias),
+                    cf0_w=W(ca.ffn[0].weight), cf0_b=Fp(ca.ffn[0].bias),
+                    cln_g=Fp(ca.ffn[1].weight), cln_b=Fp(ca.ffn[1].bias),
+                    cf3_w=W(ca.ffn[3].weight), cf3_b=Fp(ca.ffn[3].bias),
+                )
+            )
+        assign = [
+            dict(fp_w=W(a.final_proj.weight), fp_b=Fp(a.final_proj.bias),
+                 m_w=Fp(a.matchability.weight.view(-1)), m_b=Fp(a.matchability.bias))
+            for a in self.log_assignment
+        ]
+        token = [dict(w=Fp(t.token[0].weight.view(-1)), b=Fp(t.token[0].bias)) for t in self.token_confidence]
+        packed = dict(layers=layers, assign=assign, token=token, wr=Fp(self.posenc.Wr.weight))
+        if isinstance(self.input_proj, nn.Linear):
+            packed["in_w"], packed["in_b"] = W(self.input_proj.weight), Fp(self.input_proj.bias)
+        self._packed, self._pack_key = packed, key
+        return packed
+
+    # ---- forward ---------------------------------------------------------------------------
+
+    @torch.no_grad()
+    def forward(self, data: dict) -> dict:
+        for key in self.required_data_keys:
+            assert key in data, f"Missing key {key} in data"
+        lib = _abi.load()
+        conf = self.conf
+        kpts0, kpts1 = data["keypoints0"], data["keypoints1"]
+        if not kpts0.is_cuda:
+            raise _abi.LightGlueB200Error(
+                "glue_factory_colon_b200.LightGlue runs on CUDA (sm_100a) tensors only; there is no CPU path"
+            )
+        check(lib.lgb200_device_ok(), "device check")
+        dev = kpts0.device
+        B, m, _ = kpts0.shape
+        _, n, _ = kpts1.shape
+        # lightglue.py:430-432 -- unlike the reference (F6: UnboundLocalError) a missing view is size=None
+        size0 = data["view0"].get("image_size") if "view0" in data else None
+        size1 = data["view1"].get("image_size") if "view1" in data else None
+        f32 = dict(device=dev, dtype=torch.float32)
+        i32 = dict(device=dev, dtype=torch.int32)
+
+        def prep_size(sz):
+            if sz is None:
+                return None
+            if not isinstance(sz, torch.Tensor):
+                sz = torch.tensor(sz)
+            return sz.to(**f32).reshape(-1, 2).expand(B, 2).contiguous()
+
+        size0, size1 = prep_size(size0), prep_size(size1)
+
+        def prep_kpts(idx, k):
+            k = k.to(torch.float32)
+            if conf.add_scale_ori:  # lightglue.py:436-454
+                sc, ori = data[f"scales{idx}"], data[f"oris{idx}"]
+                sc = sc if sc.dim() == 3 else sc[..., None]
+                ori = ori if ori.dim() == 3 else ori[..., None]
+                k = torch.cat([k, sc.to(k), ori.to(k)], -1)
+            return k.contiguous()
+
+        k0, k1 = prep_kpts(0, kpts0), prep_kpts(1, kpts1)
+        kdim = k0.shape[-1]
+        desc0 = data["descriptors0"].to(torch.float32).contiguous()
+        desc1 = data["descriptors1"].to(torch.float32).contiguous()
+        assert desc0.shape[-1] == conf.input_dim
+        assert desc1.shape[-1] == conf.input_dim
+
+        prec = self._precision()
+        bf = prec == BF16
+        W = self._pack(prec, dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        L = conf.n_layers
+        S = 2 * B
+        Lp = max(128, ((max(m, n) + 127) // 128) * 128)
+        T = S * Lp
+
+        # per-sequence valid counts (B200 extension for padded batches)
+        lens_host = np.empty((B, 2), dtype=np.int32)
+        lens_host[:, 0], lens_host[:, 1] = m, n
+        variable = False
+        for idx in (0, 1):
+            cnt = data.get(f"num_keypoints{idx}")
+            if cnt is not None:
+                lens_host[:, idx] = torch.as_tensor(cnt).to("cpu", torch.int32).numpy().reshape(-1)
+                variable = True
+        assert (lens_host[:, 0] <= m).all() and (lens_host[:, 1] <= n).all() and (lens_host >= 0).all()
+        do_early = conf.depth_confidence > 0 and not self.training
+        do_prune = conf.width_confidence > 0 and not self.training
+        adaptive = do_early or do_prune
+        use_lens = variable or adaptive or m != Lp or n != Lp
+        lens = torch.from_numpy(lens_host.reshape(-1).copy()).to(dev) if use_lens else None
+        lens_act = lens.clone() if adaptive else lens
+
+        act = torch.bfloat16 if bf else torch.float32
+        adt = dict(device=dev, dtype=act)
+        x32 = torch.empty(T, 256, **f32)
+        x16 = torch.empty(T, 256, **adt) if bf else None
+        rot = torch.empty(T, 64, **f32)
+        q = torch.zeros(T * 256, **adt)
+        k = torch.zeros(T * 256, **adt)
+        v = torch.zeros(T * 256, **adt)
+        ctx = torch.zeros(T, 256, **adt)
+        msg = torch.zeros(T, 256, **adt)
+        hid = torch.zeros(T, 512, **adt)
+
+        def linear(epi, A0, Wt, bias, N, K, A1=None, K0=None, scale=(1.0, 1.0, 1.0), resid=None,
+                   out32=None, out16=None, n_rot=0, outp=(None, None, None), gamma=None, beta=None,
+                   lens_=None):
+            check(
+                lib.lgb200_linear(
+                    prec, epi, ptr(A0), ptr(A1), K if K0 is None else K0, ptr(Wt), ptr(bias), T, N, K,
+                    ptr(lens_), Lp, scale[0], scale[1], scale[2], ptr(resid), ptr(out32), ptr(out16),
+                    ptr(rot), n_rot, ptr(outp[0]), ptr(outp[1]), ptr(outp[2]), ptr(gamma), ptr(beta), st,
+                ),
+                "lgb200_linear",
+            )
+
+        def rowmajor_out(t):
+            return dict(out16=t) if bf else dict(out32=t)
+
+        # ---- staging: descriptors (+ input_proj) and positional encoding ----
+        if isinstance(self.input_proj, nn.Linear):
+            din = conf.input_dim
+            xin32 = torch.empty(T, din, **f32)
+            xin16 = torch.empty(T, din, **adt) if bf else None
+            for img, dsc, cnt in ((0, desc0, m), (1, desc1, n)):
+                check(lib.lgb200_pack_rows(ptr(dsc), B, cnt, din, img, Lp, ptr(xin32), ptr(xin16), st), "pack_rows")
+            linear(EPI_ROWMAJOR, xin16 if bf else xin32, W["in_w"], W["in_b"], 256, din, out32=x32, out16=x16)
+        else:
+            for img, dsc, cnt in ((0, desc0, m), (1, desc1, n)):
+                check(lib.lgb200_pack_rows(ptr(dsc), B, cnt, 256, img, Lp, ptr(x32), ptr(x16), st), "pack_rows")
+        for img, kk, cnt, sz in ((0, k0, m, size0), (1, k1, n, size1)):
+            check(lib.lgb200_posenc(ptr(kk), B, cnt, kdim, ptr(sz), ptr(W["wr"]), ptr(lens), img, Lp, ptr(rot), st),
+                  "lgb200_posenc")
+
+        # ---- adaptive state (device resident) ----
+        if adaptive:
+            conf_buf = torch.zeros(T, **f32)
+            msig = torch.zeros(T, **f32)
+            done = torch.zeros(B, **i32)
+            total = torch.from_numpy(lens_host.sum(1).astype(np.int32)).to(dev)
+        if do_prune:
+            ind = torch.arange(Lp, **i32).repeat(S, 1).contiguous()
+            prune_cnt = torch.ones(S, Lp, **i32)
+            x32_b, rot_b, ind_b = torch.zeros_like(x32), torch.zeros_like(rot), torch.zeros_like(ind)
+            x16_b = torch.zeros_like(x16) if bf else None
+        exit_layer = np.full(B, L - 1, dtype=np.int64)
+
+        q_scale = LOG2E / math.sqrt(64.0)
+        c_scale = math.sqrt(q_scale)
+        for i in range(L):
+            w = W["layers"][i]
+            xa = x16 if bf else x32
+            la = lens_act
+            # self block (lightglue.py:151-164)
+            linear(EPI_HEADS, xa, w["qkv_w"], w["qkv_b"], 768, 256, scale=(q_scale, 1.0, 1.0), n_rot=2,
+                   outp=(q, k, v), lens_=la)
+            check(lib.lgb200_attention(prec, ptr(q), ptr(k), ptr(v), S, Lp, ptr(la), 0, ptr(ctx), st), "attention")
+            linear(EPI_ROWMAJOR, ctx, w["so_w"], w["so_b"], 256, 256, lens_=la, **rowmajor_out(msg))
+            linear(EPI_LN_GELU, xa, w["sf0_w"], w["sf0_b"], 512, 512, A1=msg, K0=256, gamma=w["sln_g"],
+                   beta=w["sln_b"], lens_=la, **rowmajor_out(hid))
+            linear(EPI_ROWMAJOR, hid, w["sf3_w"], w["sf3_b"], 256, 512, resid=x32, out32=x32, out16=x16, lens_=la)
+            # cross block (lightglue.py:193-222)
+            linear(EPI_HEADS, xa, w["cqv_w"], w["cqv_b"], 512, 256, scale=(c_scale, 1.0, 1.0), n_rot=0,
+                   outp=(q, v, None), lens_=la)
+            check(lib.lgb200_attention(prec, ptr(q), ptr(q), ptr(v), S, Lp, ptr(la), 1, ptr(ctx), st), "attention")
+            linear(EPI_ROWMAJOR, ctx, w["co_w"], w["co_b"], 256, 256, lens_=la, **rowmajor_out(msg))
+            linear(EPI_LN_GELU, xa, w["cf0_w"], w["cf0_b"], 512, 512, A1=msg, K0=256, gamma=w["cln_g"],
+                   beta=w["cln_b"], lens_=la, **rowmajor_out(hid))
+            linear(EPI_ROWMAJOR, hid, w["cf3_w"], w["cf3_b"], 256, 512, resid=x32, out32=x32, out16=x16, lens_=la)
+            if i == L - 1 or not adaptive:
+                continue
+            thr = float(self.confidence_thresholds[i])
+            if do_early:  # lightglue.py:501-505
+                tk = W["token"][i]
+                check(lib.lgb200_rowdot(ptr(x32), ptr(tk["w"]), ptr(tk["b"]), S, Lp, ptr(la), 1, ptr(conf_buf), st), "rowdot")
+                check(lib.lgb200_exit_check(ptr(conf_buf), B, Lp, ptr(lens), ptr(total), thr,
+                                            float(conf.depth_confidence), i, ptr(done), ptr(lens_act), st), "exit_check")
+                done_h = done.cpu().numpy()  # one host read per layer (the reference syncs 2-3 times)
+                newly = (done_h == i + 1)
+                exit_layer[newly] = i
+                if (done_h != 0).all():
+                    break
+            if do_prune:  # lightglue.py:506-521
+                ma = W["assign"][i]
+                check(lib.lgb200_rowdot(ptr(x32), ptr(ma["m_w"]), ptr(ma["m_b"]), S, Lp, ptr(la), 1, ptr(msig), st), "rowdot")
+                check(lib.lgb200_prune_compact(ptr(msig), ptr(conf_buf) if do_early else None, thr,
+                                               float(conf.width_confidence), S, Lp, ptr(lens), ptr(lens_act),
+                                               ptr(x32), ptr(x32_b), ptr(x16), ptr(x16_b), ptr(rot), ptr(rot_b),
+                                               ptr(ind), ptr(ind_b), ptr(prune_cnt), st), "prune_compact")
+                x32, x32_b = x32_b, x32
+                x16, x16_b = x16_b, x16
+                rot, rot_b = rot_b, rot
+                ind, ind_b = ind_b, ind
+
+        # ---- log assignment (lightglue.py:523-524) ----
+        md = msg  # reuse: [T,256] in the activation dtype
+        z = torch.zeros(T, **f32)
+        lse = torch.zeros(T, **f32)
+        xa = x16 if bf else x32
+        for e in np.unique(exit_layer):
+            if adaptive and lens is not None and len(np.unique(exit_layer)) > 1:
+                sel = torch.from_numpy(np.repeat(exit_layer == e, 2)).to(dev)
+                lens_g = torch.where(sel, lens, torch.zeros_like(lens))
+            else:
+                lens_g = lens
+            a = W["assign"][int(e)]
+            linear(EPI_ROWMAJOR, xa, a["fp_w"], a["fp_b"], 256, 256, scale=(0.25, 1.0, 1.0), lens_=lens_g,
+                   **rowmajor_out(md))
+            check(lib.lgb200_rowdot(ptr(x32), ptr(a["m_w"]), ptr(a["m_b"]), S, Lp, ptr(lens_g), 0, ptr(z), st), "rowdot")
+            check(lib.lgb200_assign_lse(prec, ptr(md), S, Lp, ptr(lens_g), ptr(lse), st), "assign_lse")
+        if do_prune:
+            lens_final = lens.cpu().numpy().reshape(B, 2)  # pruned shape is data dependent (lightglue.py:285 note)
+            R, C = int(lens_final[:, 0].max()) + 1, int(lens_final[:, 1].max()) + 1
+        else:
+            R, C = m + 1, n + 1
+        scores = torch.empty(B, R, C, **f32)
+        check(lib.lgb200_assign_scores(prec, ptr(md), ptr(z), ptr(lse), B, Lp, ptr(lens), R, C, ptr(scores), st),
+              "assign_scores")
+
+        # ---- filter_matches (lightglue.py:525-536) ----
+        m0 = torch.empty(B, m, device=dev, dtype=torch.int64)
+        m1 = torch.empty(B, n, device=dev, dtype=torch.int64)
+        ms0 = torch.empty(B, m, **f32)
+        ms1 = torch.empty(B, n, **f32)
+        fm_ws = torch.empty(B * (R + C), device=dev, dtype=torch.int64)
+        check(
+            lib.lgb200_filter_matches(
+                ptr(scores), B, R, C, ptr(lens), float(conf.filter_threshold),
+                ptr(ind) if do_prune else None, ptr(ind[1:]) if do_prune else None, 2 * Lp,
+                m, n, ptr(m0), ptr(m1), ptr(ms0), ptr(ms1), ptr(fm_ws), st,
+            ),
+            "filter_matches",
+        )
+
+        xv = x32.view(B, 2, Lp, 256)
+        if do_prune:
+            pc = prune_cnt.view(B, 2, Lp)
+            prune0, prune1 = pc[:, 0, :m].to(torch.int64), pc[:, 1, :n].to(torch.int64)
+            k0f, k1f = R - 1, C - 1
+            ref0, ref1 = xv[:, 0:1, :k0f], xv[:, 1:2, :k1f]
+        else:  # lightglue.py:538-539
+            prune0 = torch.full((B, m), float(L), **f32)
+            prune1 = torch.full((B, n), float(L), **f32)
+            ref0, ref1 = xv[:, 0:1, :m], xv[:, 1:2, :n]
+        return {
+            "matches0": m0,
+            "matches1": m1,
+            "matching_scores0": ms0,
+            "matching_scores1": ms1,
+            "ref_descriptors0": ref0,
+            "ref_descriptors1": ref1,
+            "log_assignment": scores,
+            "prune0": prune0,
+            "prune1": prune1,
+        }
+
+
+__main_model__ = LightGlue

@@ -1,0 +1,186 @@
+/*
+ * lightglue_b200.h -- C ABI of the B200-native LightGlue matcher hot path.
+ *
+ * The reference (ipastore/glue-factory-colon) has NO native boundary: every op
+ * of gluefactory/models/matchers/lightglue.py is a PyTorch library call.  Each
+ * entry point below replaces the library call sites of one kernel family; the
+ * reference file:line it replaces is cited per function (paths relative to the
+ * reference checkout).  The only caller is the Python host mirror
+ * glue_factory_colon_b200/lightglue.py (ctypes).
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless stated otherwise.  No entry point
+ *     allocates, synchronises or keeps mutable global state; every launch goes
+ *     to the `stream` argument (a cudaStream_t passed as void*).
+ *   - Return value: 0 on success; LGB200_ERR_* (negative) for bad arguments;
+ *     a positive value is a cudaError_t from the launch.
+ *   - Token storage ("sequence-major"): S = 2*B sequences, sequence s = 2*b+i
+ *     is image i of pair b; every sequence owns Lp rows (Lp % 128 == 0) of
+ *     which the first lens[s] are valid.  `lens` is a DEVICE int32[S] so that
+ *     point pruning can shrink it without a host round trip; a sequence with
+ *     lens[s] == 0 is skipped by every kernel (used for early-exited pairs).
+ *   - precision: LGB200_F32 runs hand-written CUDA-core fp32 kernels (the
+ *     parity mode, 1e-3 on log_assignment); LGB200_BF16 runs tcgen05/TMEM/TMA
+ *     kernels with bf16 operands and fp32 accumulation (the throughput mode).
+ */
+#ifndef LIGHTGLUE_B200_H_
+#define LIGHTGLUE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGB200_ABI_VERSION 1
+
+enum { LGB200_F32 = 0, LGB200_BF16 = 1 };
+
+enum {
+  LGB200_OK = 0,
+  LGB200_ERR_SHAPE = -1,     /* unsupported extent / alignment            */
+  LGB200_ERR_NULL = -2,      /* required pointer missing                  */
+  LGB200_ERR_PRECISION = -3, /* unknown precision / epilogue enum         */
+  LGB200_ERR_DRIVER = -4,    /* cuTensorMapEncodeTiled unavailable/failed */
+  LGB200_ERR_ARCH = -5       /* device is not sm_100                      */
+};
+
+/* epilogues of lgb200_linear */
+enum {
+  LGB200_EPI_ROWMAJOR = 0, /* out[r,c] = (acc + bias[c]) * scale0 (+ resid[r,c])            */
+  LGB200_EPI_HEADS = 1,    /* split into parts of 256 cols, optional rotary, head-major out */
+  LGB200_EPI_LN_GELU = 2   /* N == 512: gelu(layernorm(acc + bias) * gamma + beta)          */
+};
+
+int lgb200_abi_version(void);
+/* 0 if the current device can run the kernels (compute capability 10.x). */
+int lgb200_device_ok(void);
+const char* lgb200_error_string(int code);
+
+/* ---- input staging ------------------------------------------------------
+ * Replaces descriptors.contiguous() + the implicit [B,N,d] layout,
+ * lightglue.py:456-465 (input_proj itself goes through lgb200_linear).
+ * src [B, n, dim] fp32 -> rows of sequences (2*b + img): x32 [S,Lp,dim] fp32 and,
+ * when x16 != NULL, a bf16 shadow.  Rows >= n are zero-filled. */
+int lgb200_pack_rows(const float* src, int B, int n, int dim, int img, int Lp,
+                     float* x32, void* x16, void* stream);
+
+/* ---- positional encoding --------------------------------------------------
+ * Replaces normalize_keypoints (lightglue.py:28-40) and
+ * LearnableFourierPositionalEncoding.forward (lightglue.py:61-66).
+ * kpts [B,n,kdim] fp32 (kdim 2, or 4 with scale/orientation appended),
+ * size [B,2] (W,H) or NULL (extent of the valid points), Wr [32,kdim].
+ * rot [S,Lp,64] fp32 receives (cos_f, sin_f) pairs, f = 0..31, for sequence
+ * 2*b+img; one table serves the 4 heads and all layers (the reference's
+ * repeat_interleave(2) is implicit: rotary pair f uses entry f). */
+int lgb200_posenc(const float* kpts, int B, int n, int kdim, const float* size,
+                  const float* Wr, const int32_t* lens, int img, int Lp,
+                  float* rot, void* stream);
+
+/* ---- linear layers with fused epilogues -------------------------------------
+ * Replaces nn.Linear + the elementwise ops around it:
+ *   Wqkv + unflatten + rotary   lightglue.py:157-161, 43-50
+ *   to_qk / to_v                lightglue.py:196-201, 208
+ *   out_proj / to_out           lightglue.py:163, 219
+ *   ffn (cat, Linear, LayerNorm, GELU, Linear, residual)  lightglue.py:144-149,164,220-221
+ *   final_proj / d**.25         lightglue.py:281-283
+ *   input_proj                  lightglue.py:464-465
+ * Y[T,N] = A[T,K] . W[N,K]^T, T = S*Lp.  A is A0[T,K0] followed column-wise by
+ * A1[T,K-K0] (A1 NULL when K0 == K) -- this is the ffn's torch.cat([x,msg],-1).
+ * A and W are fp32 (LGB200_F32) or bf16 (LGB200_BF16); bias/gamma/beta fp32.
+ *   ROWMAJOR: out32 (fp32, nullable) / out16 (bf16, nullable), leading dim N;
+ *             resid32 [T,N] fp32 nullable.
+ *   HEADS:    N = parts*256, column c = part*256 + head*64 + d (the caller
+ *             permutes Wqkv rows from the reference's head*192 + d*3 + part).
+ *             Parts < n_rot get the rotary embedding from rot [T,64]; part p is
+ *             scaled by scale[p] and written to outp[p] laid out [S,4,Lp,64]
+ *             in the precision's element type.
+ *   LN_GELU:  N = 512; out as ROWMAJOR. */
+int lgb200_linear(int precision, int epilogue, const void* A0, const void* A1, int K0,
+                  const void* W, const float* bias, int T, int N, int K,
+                  const int32_t* lens, int Lp,
+                  float scale0, float scale1, float scale2,
+                  const float* resid32, float* out32, void* out16,
+                  const float* rot, int n_rot, void* outp0, void* outp1, void* outp2,
+                  const float* gamma, const float* beta, void* stream);
+
+/* ---- attention ---------------------------------------------------------------
+ * Replaces Attention.forward / F.scaled_dot_product_attention and the einsum
+ * cross attention, lightglue.py:112-129, 203-217.  Q,K,V [S,4,Lp,64]; Q is
+ * expected pre-scaled so that softmax uses exp2 (log2(e)/sqrt(64) folded in by
+ * the producing lgb200_linear).  Sequence s attends to sequence s ^ kv_xor
+ * (0 = self attention, 1 = the other image of the pair = cross attention);
+ * keys >= lens[s ^ kv_xor] are masked, a sequence with no keys yields zeros
+ * (nan_to_num, lightglue.py:118,217).  ctx [S,Lp,256] token-major, column
+ * head*64+d (= transpose(1,2).flatten(-2), lightglue.py:163,218). */
+int lgb200_attention(int precision, const void* Q, const void* K, const void* V,
+                     int S, int Lp, const int32_t* lens, int kv_xor,
+                     void* ctx, void* stream);
+
+/* ---- per-token heads -----------------------------------------------------------
+ * Replaces matchability / token-confidence Linear(256,1) (+ sigmoid),
+ * lightglue.py:72,75-80,285-286,290-291.  out[r] = dot(x32[r,:], w) + b,
+ * sigmoid applied when apply_sigmoid != 0; rows >= lens[s] are left untouched. */
+int lgb200_rowdot(const float* x32, const float* w, const float* b, int S, int Lp,
+                  const int32_t* lens, int apply_sigmoid, float* out, void* stream);
+
+/* ---- log assignment ---------------------------------------------------------------
+ * Replaces the similarity einsum + sigmoid_log_double_softmax,
+ * lightglue.py:257-269, 284-288.  md [S,Lp,256] = final_proj(desc)/4 (from
+ * lgb200_linear), z [S,Lp] = matchability logits.
+ *   pass 1 (lgb200_assign_lse): lse[s,l] = logsumexp_j <md[s,l], md[s^1,j]>,
+ *          j < lens[s^1]  (row normaliser of image 0, column normaliser of image 1);
+ *   pass 2 (lgb200_assign_scores): recomputes the similarity tile and writes
+ *          scores [B,R,C] fp32 (R = n0max+1, C = n1max+1) exactly once:
+ *          valid block 2*sim - lse0[i] - lse1[j] + logsigmoid(z0[i]) + logsigmoid(z1[j]),
+ *          dustbin column C-1 = logsigmoid(-z0), dustbin row R-1 = logsigmoid(-z1),
+ *          everything else (padding, corner) 0. */
+int lgb200_assign_lse(int precision, const void* md, int S, int Lp, const int32_t* lens,
+                      float* lse, void* stream);
+int lgb200_assign_scores(int precision, const void* md, const float* z, const float* lse,
+                         int B, int Lp, const int32_t* lens, int R, int C,
+                         float* scores, void* stream);
+
+/* ---- filter_matches -------------------------------------------------------------------
+ * Replaces filter_matches, lightglue.py:294-319 (and the scatter back to
+ * un-pruned indices, lightglue.py:527-536).  scores [B,R,C] fp32; pair b uses
+ * rows < n0 = lens[2b], cols < n1 = lens[2b+1] (lens NULL: n0 = R-1, n1 = C-1).
+ * Ties resolve to the lowest index, NaN counts as the maximum (torch.max).
+ * ind0/ind1 (int32 [B,ind_ld], nullable) map current rows to original indices;
+ * outputs are indexed by ORIGINAL index: m0 [B,N0] int64, m1 [B,N1] int64,
+ * ms0 [B,N0], ms1 [B,N1] fp32; untouched entries are -1 / 0.
+ * workspace: 8 * B * (R + C) bytes. */
+int lgb200_filter_matches(const float* scores, int B, int R, int C, const int32_t* lens,
+                          float threshold, const int32_t* ind0, const int32_t* ind1, int ind_ld,
+                          int N0, int N1, int64_t* m0, int64_t* m1, float* ms0, float* ms1,
+                          void* workspace, void* stream);
+
+/* ---- adaptive depth (early exit) ---------------------------------------------------------
+ * Replaces check_if_stop, lightglue.py:569-580.  conf [S,Lp] = sigmoid token
+ * confidences; pair b stops iff 1 - count(conf < thr)/total[b] > depth_conf
+ * (fp32 arithmetic as in the reference).  done[b] is set to layer+1 for pairs
+ * that stop now (pairs with done[b] != 0 are left alone) and their entries of
+ * `lens_active` are zeroed so later kernels skip them. */
+int lgb200_exit_check(const float* conf, int B, int Lp, const int32_t* lens,
+                      const int32_t* total, float thr, float depth_conf, int layer,
+                      int32_t* done, int32_t* lens_active, void* stream);
+
+/* ---- adaptive width (point pruning) --------------------------------------------------------
+ * Replaces get_pruning_mask + torch.where + index_select + prune += 1,
+ * lightglue.py:506-521, 560-567.  keep[l] = match[s,l] > 1 - width_conf ||
+ * (conf != NULL && conf[s,l] <= thr).  Rows are compacted from the *_src
+ * buffers into the *_dst buffers (stable order), lens[s] is updated on the
+ * device, prune_cnt[s, ind] += 1 for kept rows.  Sequences with
+ * lens_active[s] == 0 are copied through unchanged in count (not pruned). */
+int lgb200_prune_compact(const float* match, const float* conf, float thr, float width_conf,
+                         int S, int Lp, int32_t* lens, int32_t* lens_active,
+                         const float* x32_src, float* x32_dst,
+                         const void* x16_src, void* x16_dst,
+                         const float* rot_src, float* rot_dst,
+                         const int32_t* ind_src, int32_t* ind_dst,
+                         int32_t* prune_cnt, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIGHTGLUE_B200_H_ */

@@ -1,0 +1,52 @@
+"""Shared test helpers: build the product module / oracle weights for a golden fixture."""
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+from glue_factory_colon_b200.lightglue import LightGlue  # noqa: E402
+from glue_factory_colon_b200.synthetic import make_pairs  # noqa: E402
+from oracle import lightglue_oracle as oracle  # noqa: E402
+
+
+def fingerprint(sd):
+    return float(sum(v.double().abs().sum() for v in sd.values()))
+
+
+def build_model(conf, seed, overrides=None):
+    """Seeded construction: bit-identical to the reference constructor under the same seed."""
+    torch.manual_seed(seed)
+    model = LightGlue(conf).eval()
+    sd = model.state_dict()
+    for k, v in (overrides or {}).items():
+        sd[k].copy_(v)
+    return model
+
+
+def load_fixture(path):
+    fx = torch.load(path, weights_only=False)
+    model = build_model(fx["conf"], fx["seed"], fx["overrides"])
+    assert abs(fingerprint(model.state_dict()) - fx["fingerprint"]) < 1e-6 * fx["fingerprint"], (
+        "seeded weights differ from the ones the reference used for this fixture"
+    )
+    data = make_pairs(**fx["data_kwargs"])
+    return fx, model, data
+
+
+def oracle_batch(model, conf, data, dtype=torch.float32, num0=None, num1=None):
+    return oracle.forward(model.state_dict(), dict(conf), data, dtype=dtype, num0=num0, num1=num1)
+
+
+def assert_matches_equal(got_m, got_s, exp_m, exp_s, scores_row_gap=None, what=""):
+    """Indices bit-exact; a mismatch is tolerated only where the oracle's own decision
+    is numerically ambiguous (top-2 gap below 1e-4), which `scores_row_gap` reports."""
+    bad = got_m != exp_m
+    if scores_row_gap is not None:
+        bad = bad & (scores_row_gap > 1e-4)
+    assert not bad.any(), f"{what}: {int(bad.sum())} index mismatches"
+    same = got_m == exp_m
+    torch.testing.assert_close(got_s[same], exp_s[same], atol=2e-4, rtol=1e-3)

@@ -1,0 +1,378 @@
+"""GPU parity tests (run with -m gpu on a B200).  Everything goes through the C ABI
+(ctypes) and is checked against the CPU oracle / the reference's golden fixtures.
+
+Tolerances
+  fp32 mode : log_assignment within 1e-3 absolute (north_star), indices bit-exact
+              except where the oracle's own top-2 gap is < 1e-4 (numerically tied).
+  bf16 mode : the reference's OWN bf16-autocast run deviates from its fp32 run by
+              max 0.26 / mean 0.043 on log_assignment.  We
+              require mean |d| < 0.05 and max |d| < 0.5 on the valid block, and
+              row-argmax agreement > 85 %.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import build_model, load_fixture, make_pairs, oracle_batch
+from glue_factory_colon_b200 import _abi
+from glue_factory_colon_b200._abi import ptr
+from glue_factory_colon_b200.synthetic import to_device
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _row_gap(la):
+    top2 = la[:-1, :-1].topk(2, dim=1).values
+    return top2[:, 0] - top2[:, 1]
+
+
+def _col_gap(la):
+    top2 = la[:-1, :-1].topk(2, dim=0).values
+    return top2[0] - top2[1]
+
+
+def compare_to_oracle(out, res, m, n, fp32=True):
+    """out: product dict (padded batch); res: per-pair oracle dicts (un-padded)."""
+    for b, r in enumerate(res):
+        la_o = r["log_assignment"]
+        n0, n1 = la_o.shape[0] - 1, la_o.shape[1] - 1
+        la = out["log_assignment"][b].cpu()
+        R, C = la.shape
+        got = torch.cat([torch.cat([la[:n0, :n1], la[:n0, C - 1:C]], 1),
+                         torch.cat([la[R - 1:R, :n1], la[R - 1:R, C - 1:C]], 1)], 0)
+        diff = (got - la_o).abs()
+        if fp32:
+            assert diff.max() < 1e-3, f"pair {b}: max |dlog_assignment| = {diff.max():.2e}"
+        else:
+            assert diff.mean() < 0.05 and diff.max() < 0.5, f"pair {b}: mean {diff.mean():.3f} max {diff.max():.3f}"
+        m0, m1 = out["matches0"][b].cpu(), out["matches1"][b].cpu()
+        s0, s1 = out["matching_scores0"][b].cpu(), out["matching_scores1"][b].cpu()
+        if fp32 and "ind0" in r and n0 == r["matches0"].shape[0]:  # un-pruned: index spaces coincide
+            gap0 = torch.full((m,), 1.0)
+            gap1 = torch.full((n,), 1.0)
+            if n0 > 1 and n1 > 1:
+                gap0[:n0], gap1[:n1] = _row_gap(la_o), _col_gap(la_o)
+            e0 = torch.full((m,), -1, dtype=torch.long); e0[:n0] = r["matches0"]
+            e1 = torch.full((n,), -1, dtype=torch.long); e1[:n1] = r["matches1"]
+            bad0 = (m0 != e0) & (gap0 > 1e-4)
+            bad1 = (m1 != e1) & (gap1 > 1e-4)
+            # a flipped tie on one side can break mutuality on the other: allow only those
+            assert bad0.sum() <= (gap1 <= 1e-4).sum() and bad1.sum() <= (gap0 <= 1e-4).sum(), (
+                f"pair {b}: {int(bad0.sum())}/{int(bad1.sum())} index mismatches")
+            ok = m0 == e0
+            es0 = torch.zeros(m); es0[:n0] = r["matching_scores0"]
+            torch.testing.assert_close(s0[ok], es0[ok], atol=1e-4, rtol=1e-3)
+        elif fp32:  # pruned: compare in original index space
+            e0, e1 = r["matches0"], r["matches1"]
+            assert (m0[: e0.shape[0]] != e0).float().mean() < 0.02
+            assert (m1[: e1.shape[0]] != e1).float().mean() < 0.02
+        else:
+            e0 = r["matches0"]
+            agree = (la[:n0, :n1].argmax(1) == la_o[:n0, :n1].argmax(1)).float().mean()
+            assert agree > 0.85, f"pair {b}: row-argmax agreement {agree:.3f}"
+        # padded entries
+        assert (m0[n0:] == -1).all() if n0 < m and "ind0" in r and n0 == r["matches0"].shape[0] else True
+
+
+# ------------------------------------------------------------------ kernel-level tests
+
+
+def test_device_ok():
+    lib = _abi.load()
+    assert lib.lgb200_device_ok() == 0
+
+
+def test_filter_matches_kat_bit_exact(golden_dir):
+    lib = _abi.load()
+    for case in torch.load(golden_dir / "filter_kat.pt", weights_only=False):
+        sc = case["scores"].to(DEV).contiguous()
+        B, R, C = sc.shape
+        m0 = torch.empty(B, R - 1, device=DEV, dtype=torch.int64)
+        m1 = torch.empty(B, C - 1, device=DEV, dtype=torch.int64)
+        s0 = torch.empty(B, R - 1, device=DEV)
+        s1 = torch.empty(B, C - 1, device=DEV)
+        ws = torch.empty(B * (R + C), device=DEV, dtype=torch.int64)
+        rc = lib.lgb200_filter_matches(ptr(sc), B, R, C, None, case["th"], None, None, 0, R - 1, C - 1,
+                                       ptr(m0), ptr(m1), ptr(s0), ptr(s1), ptr(ws), _stream())
+        assert rc == 0
+        assert torch.equal(m0.cpu(), case["m0"]) and torch.equal(m1.cpu(), case["m1"])
+        torch.testing.assert_close(s0.cpu(), case["ms0"], atol=1e-6, rtol=1e-5)
+        torch.testing.assert_close(s1.cpu(), case["ms1"], atol=1e-6, rtol=1e-5)
+
+
+def test_filter_matches_large_random_against_torch():
+    """Full-size property test: 2049x2049 scores, torch on the same device is the checker."""
+    lib = _abi.load()
+    g = torch.Generator(device=DEV).manual_seed(3)
+    B, R, C = 3, 2049, 2049
+    sc = torch.randn(B, R, C, device=DEV, generator=g)
+    sc = (sc * 64).round() / 64 - 3.0  # exact ties
+    m0 = torch.empty(B, R - 1, device=DEV, dtype=torch.int64); m1 = torch.empty(B, C - 1, device=DEV, dtype=torch.int64)
+    s0 = torch.empty(B, R - 1, device=DEV); s1 = torch.empty(B, C - 1, device=DEV)
+    ws = torch.empty(B * (R + C), device=DEV, dtype=torch.int64)
+    assert lib.lgb200_filter_matches(ptr(sc), B, R, C, None, 0.01, None, None, 0, R - 1, C - 1,
+                                     ptr(m0), ptr(m1), ptr(s0), ptr(s1), ptr(ws), _stream()) == 0
+    inner = sc[:, :-1, :-1]
+    mx0, mx1 = inner.max(2), inner.max(1)
+    i0 = torch.arange(R - 1, device=DEV)[None]; i1 = torch.arange(C - 1, device=DEV)[None]
+    mut0 = i0 == mx1.indices.gather(1, mx0.indices); mut1 = i1 == mx0.indices.gather(1, mx1.indices)
+    e_s0 = torch.where(mut0, mx0.values.exp(), torch.zeros_like(mx0.values))
+    v0 = mut0 & (e_s0 > 0.01); v1 = mut1 & v0.gather(1, mx1.indices)
+    assert torch.equal(m0, torch.where(v0, mx0.indices, -1)) and torch.equal(m1, torch.where(v1, mx1.indices, -1))
+    torch.testing.assert_close(s0, e_s0, atol=1e-7, rtol=1e-6)
+    # idempotence property: matches0[matches1[j]] == j for every valid j
+    j = (m1[0] > -1).nonzero()[:, 0]
+    assert torch.equal(m0[0][m1[0][j]], j)
+
+
+def _rand_lens(S, Lp, seed):
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(1, Lp + 1, (S,), generator=g, dtype=torch.int32)
+    lens[0] = Lp
+    return lens
+
+
+@pytest.mark.parametrize("prec", [_abi.F32, _abi.BF16], ids=["fp32", "bf16"])
+def test_linear_epilogues(prec):
+    lib = _abi.load()
+    torch.manual_seed(0)
+    S, Lp = 4, 256
+    T = S * Lp
+    bf = prec == _abi.BF16
+    adt = torch.bfloat16 if bf else torch.float32
+    tol = dict(atol=3e-2, rtol=3e-2) if bf else dict(atol=2e-4, rtol=1e-4)
+    lens = _rand_lens(S, Lp, 1).to(DEV)
+    valid = (torch.arange(Lp)[None] < lens.cpu()[:, None]).reshape(-1)
+    tile_valid = (torch.arange(Lp)[None] // 128 * 128 < lens.cpu()[:, None]).reshape(-1)
+    x = torch.randn(T, 256, device=DEV)
+    y = torch.randn(T, 256, device=DEV)
+    xa, ya = x.to(adt), y.to(adt)
+    st = _stream()
+
+    def lin(epi, A0, W, b, N, K, A1=None, K0=None, scale=(1., 1., 1.), resid=None, out32=None, out16=None,
+            rot=None, n_rot=0, outp=(None, None, None), gamma=None, beta=None):
+        rc = lib.lgb200_linear(prec, epi, ptr(A0), ptr(A1), K if K0 is None else K0, ptr(W), ptr(b), T, N, K,
+                               ptr(lens), Lp, scale[0], scale[1], scale[2], ptr(resid), ptr(out32), ptr(out16),
+                               ptr(rot), n_rot, ptr(outp[0]), ptr(outp[1]), ptr(outp[2]), ptr(gamma), ptr(beta), st)
+        assert rc == 0, lib.lgb200_error_string(rc)
+
+    # ROWMAJOR + scale + residual, K = 512 from two sources
+    W = (torch.randn(256, 512, device=DEV) / 16).to(adt)
+    b = torch.randn(256, device=DEV)
+    resid = torch.randn(T, 256, device=DEV)
+    o32 = torch.zeros(T, 256, device=DEV); o16 = torch.zeros(T, 256, device=DEV, dtype=torch.bfloat16)
+    lin(_abi.EPI_ROWMAJOR, xa, W, b, 256, 512, A1=ya, K0=256, scale=(0.25, 1, 1), resid=resid, out32=o32,
+        out16=o16 if bf else None)
+    ref = (torch.cat([xa, ya], 1).float() @ W.float().t() + b) * 0.25 + resid
+    torch.testing.assert_close(o32[tile_valid], ref[tile_valid], **tol)
+    if bf:
+        torch.testing.assert_close(o16[tile_valid].float(), ref[tile_valid], atol=5e-2, rtol=2e-2)
+    assert (o32[~tile_valid] == 0).all(), "tiles past lens must be skipped"
+
+    # HEADS with rotary on parts 0,1 (self-attention QKV)
+    W = (torch.randn(768, 256, device=DEV) / 16).to(adt)
+    b = torch.randn(768, device=DEV)
+    ang = torch.randn(T, 32, device=DEV)
+    rot = torch.stack([ang.cos(), ang.sin()], -1).reshape(T, 64).contiguous()
+    outs = [torch.zeros(S, 4, Lp, 64, device=DEV, dtype=adt) for _ in range(3)]
+    lin(_abi.EPI_HEADS, xa, W, b, 768, 256, scale=(0.5, 1.0, 2.0), rot=rot, n_rot=2, outp=outs)
+    yref = (xa.float() @ W.float().t() + b).view(S, Lp, 3, 4, 64).permute(2, 0, 3, 1, 4)  # [part,S,h,Lp,64]
+    c = ang.cos().repeat_interleave(2, -1).view(S, 1, Lp, 64); s_ = ang.sin().repeat_interleave(2, -1).view(S, 1, Lp, 64)
+
+    def rotf(t):
+        t2 = t.unflatten(-1, (-1, 2))
+        r = torch.stack((-t2[..., 1], t2[..., 0]), -1).flatten(-2)
+        return t * c + r * s_
+
+    refs = [rotf(yref[0]) * 0.5, rotf(yref[1]), yref[2] * 2.0]
+    tv = tile_valid.view(S, 1, Lp, 1).to(DEV)
+    for o, r in zip(outs, refs):
+        torch.testing.assert_close(torch.where(tv, o.float(), 0), torch.where(tv, r, 0), **tol)
+
+    # LN + GELU
+    W = (torch.randn(512, 512, device=DEV) / 22).to(adt)
+    b = torch.randn(512, device=DEV)
+    gamma = torch.rand(512, device=DEV) + 0.5; beta = torch.randn(512, device=DEV) * 0.1
+    h = torch.zeros(T, 512, device=DEV, dtype=adt)
+    lin(_abi.EPI_LN_GELU, xa, W, b, 512, 512, A1=ya, K0=256, gamma=gamma, beta=beta,
+        out16=h if bf else None, out32=None if bf else h)
+    pre = torch.cat([xa, ya], 1).float() @ W.float().t() + b
+    ref = torch.nn.functional.gelu(torch.nn.functional.layer_norm(pre, (512,), gamma, beta, 1e-5))
+    torch.testing.assert_close(h[tile_valid].float(), ref[tile_valid], **tol)
+
+
+@pytest.mark.parametrize("prec", [_abi.F32, _abi.BF16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("kv_xor", [0, 1])
+def test_attention(prec, kv_xor):
+    lib = _abi.load()
+    torch.manual_seed(1)
+    S, Lp = 4, 384
+    bf = prec == _abi.BF16
+    adt = torch.bfloat16 if bf else torch.float32
+    lens = torch.tensor([384, 200, 129, 77], dtype=torch.int32, device=DEV)
+    q = (torch.randn(S, 4, Lp, 64, device=DEV) * 1.5).to(adt)
+    k = torch.randn(S, 4, Lp, 64, device=DEV).to(adt)
+    v = torch.randn(S, 4, Lp, 64, device=DEV).to(adt)
+    ctx = torch.zeros(S, Lp, 256, device=DEV, dtype=adt)
+    rc = lib.lgb200_attention(prec, ptr(q), ptr(k), ptr(v), S, Lp, ptr(lens), kv_xor, ptr(ctx), _stream())
+    assert rc == 0, lib.lgb200_error_string(rc)
+    for s in range(S):
+        nq, skv = int(lens[s]), s ^ kv_xor
+        nk = int(lens[skv])
+        sc = q[s, :, :nq].float() @ k[skv, :, :nk].float().transpose(-1, -2) * math.log(2.0)  # exp2 domain
+        ref = (torch.softmax(sc, -1) @ v[skv, :, :nk].float()).permute(1, 0, 2).reshape(nq, 256)
+        tol = dict(atol=2e-2, rtol=2e-2) if bf else dict(atol=2e-5, rtol=1e-4)
+        torch.testing.assert_close(ctx[s, :nq].float(), ref, **tol)
+
+
+def test_attention_empty_keys_give_zeros():
+    lib = _abi.load()
+    S, Lp = 2, 128
+    lens = torch.tensor([50, 0], dtype=torch.int32, device=DEV)
+    q = torch.randn(S, 4, Lp, 64, device=DEV); k = torch.randn_like(q); v = torch.randn_like(q)
+    ctx = torch.full((S, Lp, 256), 7.0, device=DEV)
+    assert lib.lgb200_attention(_abi.F32, ptr(q), ptr(k), ptr(v), S, Lp, ptr(lens), 1, ptr(ctx), _stream()) == 0
+    assert (ctx[0, :50] == 0).all()
+
+
+def test_posenc_and_rowdot():
+    lib = _abi.load()
+    torch.manual_seed(2)
+    B, n, Lp = 3, 150, 256
+    kp = torch.rand(B, n, 2, device=DEV) * torch.tensor([640., 480.], device=DEV)
+    Wr = torch.randn(32, 2, device=DEV)
+    size = torch.tensor([[640., 480.]], device=DEV).repeat(B, 1)
+    lens = torch.tensor([150, 1, 100, 2, 150, 3], dtype=torch.int32, device=DEV)
+    for sz in (size, None):
+        rot = torch.zeros(2 * B, Lp, 64, device=DEV)
+        assert lib.lgb200_posenc(ptr(kp), B, n, 2, ptr(sz), ptr(Wr), ptr(lens), 0, Lp, ptr(rot), _stream()) == 0
+        for b in range(B):
+            nv = int(lens[2 * b])
+            kk = kp[b, :nv]
+            s_ = size[b] if sz is not None else 1 + kk.max(0).values - kk.min(0).values
+            kn = (kk - s_ / 2) / (s_.max() / 2)
+            p = kn @ Wr.t()
+            ref = torch.stack([p.cos(), p.sin()], -1).reshape(nv, 64)
+            torch.testing.assert_close(rot[2 * b, :nv], ref, atol=2e-5, rtol=1e-5)
+            assert (rot[2 * b, nv:] == 0).all()
+    x = torch.randn(2 * B * Lp, 256, device=DEV); w = torch.randn(256, device=DEV); bb = torch.randn(1, device=DEV)
+    out = torch.zeros(2 * B * Lp, device=DEV)
+    assert lib.lgb200_rowdot(ptr(x), ptr(w), ptr(bb), 2 * B, Lp, None, 1, ptr(out), _stream()) == 0
+    torch.testing.assert_close(out, torch.sigmoid(x @ w + bb), atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("prec", [_abi.F32, _abi.BF16], ids=["fp32", "bf16"])
+def test_assignment_kernels(prec):
+    lib = _abi.load()
+    torch.manual_seed(3)
+    B, Lp = 2, 256
+    S = 2 * B
+    bf = prec == _abi.BF16
+    adt = torch.bfloat16 if bf else torch.float32
+    lens = torch.tensor([256, 200, 131, 256], dtype=torch.int32, device=DEV)
+    md = (torch.randn(S, Lp, 256, device=DEV) / 4).to(adt)
+    z = torch.randn(S, Lp, device=DEV)
+    lse = torch.zeros(S, Lp, device=DEV)
+    assert lib.lgb200_assign_lse(prec, ptr(md), S, Lp, ptr(lens), ptr(lse), _stream()) == 0
+    R, C = 257, 257
+    sc = torch.full((B, R, C), 99.0, device=DEV)
+    assert lib.lgb200_assign_scores(prec, ptr(md), ptr(z), ptr(lse), B, Lp, ptr(lens), R, C, ptr(sc), _stream()) == 0
+    ls = torch.nn.functional.logsigmoid
+    for b in range(B):
+        n0, n1 = int(lens[2 * b]), int(lens[2 * b + 1])
+        sim = md[2 * b, :n0].float() @ md[2 * b + 1, :n1].float().t()
+        tol = dict(atol=2e-3, rtol=1e-3) if bf else dict(atol=1e-4, rtol=1e-5)
+        torch.testing.assert_close(lse[2 * b, :n0], sim.logsumexp(1), **tol)
+        torch.testing.assert_close(lse[2 * b + 1, :n1], sim.logsumexp(0), **tol)
+        ref = sim.log_softmax(1) + sim.log_softmax(0) + ls(z[2 * b, :n0])[:, None] + ls(z[2 * b + 1, :n1])[None]
+        torch.testing.assert_close(sc[b, :n0, :n1], ref, atol=5e-3 if bf else 2e-4, rtol=0)
+        torch.testing.assert_close(sc[b, :n0, C - 1], ls(-z[2 * b, :n0]), atol=1e-6, rtol=1e-6)
+        torch.testing.assert_close(sc[b, R - 1, :n1], ls(-z[2 * b + 1, :n1]), atol=1e-6, rtol=1e-6)
+        assert sc[b, R - 1, C - 1] == 0 and (sc[b, n0:R - 1, :] == 0).all() and (sc[b, :, n1:C - 1] == 0).all()
+
+
+# ------------------------------------------------------------------ whole forward
+
+
+@pytest.mark.parametrize("name", ["basic", "nosize_sift", "prune"])
+def test_forward_fp32_against_reference_golden(name, golden_dir):
+    fx, model, data = load_fixture(golden_dir / f"{name}.pt")
+    model = model.to(DEV)
+    model.conf.precision = "fp32"
+    out = model(to_device(data, DEV))
+    exp = fx["out"]
+    assert out["log_assignment"].shape == exp["log_assignment"].shape
+    diff = (out["log_assignment"].cpu() - exp["log_assignment"]).abs().max()
+    assert diff < 1e-3, f"max |dlog_assignment| vs reference = {diff:.2e}"
+    mism0 = (out["matches0"].cpu() != exp["matches0"]).sum()
+    mism1 = (out["matches1"].cpu() != exp["matches1"]).sum()
+    assert mism0 <= 2 and mism1 <= 2, (int(mism0), int(mism1))  # numerically tied rows only
+    assert out["matches0"].dtype == torch.int64 and out["prune0"].dtype == exp["prune0"].dtype
+    assert torch.equal(out["prune0"].cpu(), exp["prune0"]) and torch.equal(out["prune1"].cpu(), exp["prune1"])
+    torch.testing.assert_close(out["matching_scores0"].cpu(), exp["matching_scores0"], atol=2e-4, rtol=1e-2)
+    assert abs(float(out["ref_descriptors0"].abs().mean()) - fx["ref_desc_absmean"]) < 1e-3
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_forward_variable_counts_against_oracle(prec):
+    conf = {"filter_threshold": 0.0, "precision": prec}
+    model = build_model(conf, 5).to(DEV)
+    data = make_pairs(B=3, n0=300, n1=260, seed=31)
+    num0, num1 = [300, 129, 1], [260, 260, 77]
+    d = to_device(data, DEV)
+    d["num_keypoints0"], d["num_keypoints1"] = torch.tensor(num0), torch.tensor(num1)
+    out = model(d)
+    res = oracle_batch(model.cpu(), conf, data, num0=num0, num1=num1)
+    compare_to_oracle(out, res, 300, 260, fp32=(prec == "fp32"))
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_forward_adaptive_against_oracle(prec):
+    """Early exit + pruning, B > 1, every branch forced through head biases."""
+    ov = {}
+    for i in range(8):
+        ov[f"token_confidence.{i}.token.0.bias"] = torch.tensor([3.0 if i >= 4 else -3.0])
+        ov[f"log_assignment.{i}.matchability.bias"] = torch.tensor([-4.5 if i % 2 == 0 else 0.0])
+    conf = {"depth_confidence": 0.95, "width_confidence": 0.99, "filter_threshold": 0.0, "precision": prec}
+    model = build_model(conf, 6, ov).to(DEV)
+    data = make_pairs(B=2, n0=257, n1=230, seed=41)
+    out = model(to_device(data, DEV))
+    res = oracle_batch(model.cpu(), conf, data)
+    if prec == "fp32":
+        for b, r in enumerate(res):
+            k0, k1 = r["log_assignment"].shape[0] - 1, r["log_assignment"].shape[1] - 1
+            la = out["log_assignment"][b].cpu()
+            R, C = la.shape
+            assert R - 1 >= k0 and C - 1 >= k1
+            torch.testing.assert_close(la[:k0, :k1], r["log_assignment"][:k0, :k1], atol=1e-3, rtol=0)
+            assert (out["matches0"][b].cpu() != r["matches0"]).float().mean() < 0.02
+            assert torch.equal(out["prune0"][b].cpu(), r["prune0"]), "prune layer indices differ"
+    else:
+        assert out["log_assignment"].isfinite().all()
+
+
+def test_full_size_properties_bf16():
+    """BASELINE config shape (2048 kpts), properties that need no oracle run."""
+    conf = {"filter_threshold": 0.0, "precision": "bf16"}
+    model = build_model(conf, 0).to(DEV)
+    data = make_pairs(B=2, n0=2048, n1=2048, seed=51, device=DEV)
+    out = model(data)
+    la = out["log_assignment"]
+    assert la.shape == (2, 2049, 2049) and la.isfinite().all()
+    # exp(log_assignment) rows/cols incl. dustbin are sub-stochastic products; row sums of the
+    # softmax factor: exp(la - certainties) is hard to isolate, so check the mutual property:
+    m0, m1 = out["matches0"], out["matches1"]
+    for b in range(2):
+        j = (m1[b] > -1).nonzero()[:, 0]
+        assert torch.equal(m0[b][m1[b][j]], j)
+    assert (out["matching_scores0"] >= 0).all() and (out["matching_scores0"] <= 1).all()
+    # determinism
+    out2 = model(data)
+    assert torch.equal(out2["log_assignment"], la)

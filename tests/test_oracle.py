@@ -1,0 +1,93 @@
+"""CPU tests: the oracle restatement against (a) golden fixtures produced by the
+unmodified reference and (b), when /root/reference exists, the live reference."""
+import os
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+from helpers import load_fixture, oracle_batch, ROOT
+from oracle import lightglue_oracle as oracle
+
+CASES = ["basic", "nosize_sift", "prune"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_golden(name, golden_dir):
+    fx, model, data = load_fixture(golden_dir / f"{name}.pt")
+    res = oracle_batch(model, fx["conf"], data)
+    out = fx["out"]
+    for b, r in enumerate(res):
+        la = out["log_assignment"][b]
+        # fp32 vs fp32, different summation order: 1e-4 is ample (reference fp32-vs-fp64 is 3e-5)
+        torch.testing.assert_close(r["log_assignment"], la, atol=2e-4, rtol=0)
+        assert torch.equal(r["matches0"], out["matches0"][b])
+        assert torch.equal(r["matches1"], out["matches1"][b])
+        torch.testing.assert_close(r["matching_scores0"], out["matching_scores0"][b], atol=1e-5, rtol=1e-4)
+        torch.testing.assert_close(r["matching_scores1"], out["matching_scores1"][b], atol=1e-5, rtol=1e-4)
+        assert torch.equal(r["prune0"].to(out["prune0"].dtype), out["prune0"][b])
+        assert torch.equal(r["prune1"].to(out["prune1"].dtype), out["prune1"][b])
+
+
+def test_oracle_fp64_close_to_fp32(golden_dir):
+    fx, model, data = load_fixture(golden_dir / "basic.pt")
+    r32 = oracle_batch(model, fx["conf"], data)[0]
+    r64 = oracle_batch(model, fx["conf"], data, dtype=torch.float64)[0]
+    torch.testing.assert_close(r32["log_assignment"].double(), r64["log_assignment"], atol=2e-4, rtol=0)
+
+
+def test_filter_matches_kat(golden_dir):
+    for case in torch.load(golden_dir / "filter_kat.pt", weights_only=False):
+        for b in range(case["scores"].shape[0]):
+            m0, m1, s0, s1 = oracle.filter_matches(case["scores"][b], case["th"])
+            assert torch.equal(m0, case["m0"][b]) and torch.equal(m1, case["m1"][b])
+            torch.testing.assert_close(s0, case["ms0"][b])
+            torch.testing.assert_close(s1, case["ms1"][b])
+
+
+def test_confidence_thresholds_match_buffer():
+    from helpers import build_model
+
+    model = build_model({}, 0)
+    for i in range(9):
+        assert oracle.confidence_threshold(i, 9) == float(model.confidence_thresholds[i])
+
+
+def test_early_exit_and_variable_counts_run():
+    """Branches the reference cannot run (F4 crash, F3 no masks): smoke the oracle's definition."""
+    from helpers import build_model, make_pairs
+
+    ov = {f"token_confidence.{i}.token.0.bias": torch.tensor([20.0 if i >= 2 else -20.0]) for i in range(8)}
+    conf = {"depth_confidence": 0.95, "width_confidence": 0.99, "n_layers": 4}
+    ov = {k: v for k, v in ov.items() if int(k.split(".")[1]) < 3}
+    model = build_model(conf, 4, ov)
+    data = make_pairs(B=2, n0=70, n1=60, seed=3)
+    res = oracle_batch(model, conf, data, num0=[70, 50], num1=[33, 60])
+    assert res[0]["exit_layer"] == 2 and res[1]["exit_layer"] == 2
+    assert res[1]["log_assignment"].shape == (51, 61)
+    assert res[0]["ref_descriptors0"].shape == (1, 70, 256)
+
+
+@pytest.mark.skipif(not Path("/root/reference/gluefactory").exists(), reason="reference checkout not present")
+def test_oracle_against_live_reference():
+    sys.path.insert(0, str(ROOT / "oracle" / "_shim"))
+    sys.path.insert(0, "/root/reference")
+    from gluefactory.models import get_model
+    from helpers import build_model, make_pairs
+
+    conf = {"filter_threshold": 0.0, "n_layers": 3}
+    torch.manual_seed(7)
+    ref = get_model("matchers.lightglue")(conf).eval()
+    mine = build_model(conf, 7)
+    assert get_model("glue_factory_colon_b200.lightglue") is type(mine)  # plugin discovery, models/__init__.py:20-25
+    for k, v in ref.state_dict().items():
+        assert torch.equal(v, mine.state_dict()[k]), k
+    data = make_pairs(B=1, n0=97, n1=64, seed=21)
+    with torch.no_grad():
+        out = ref(data)
+    r = oracle_batch(mine, conf, data)[0]
+    torch.testing.assert_close(r["log_assignment"], out["log_assignment"][0], atol=1e-4, rtol=0)
+    assert torch.equal(r["matches0"], out["matches0"][0])
+    # layer-level masked oracle: masked_forward on padded input == un-padded run (lightglue.py:248-254)
+    torch.testing.assert_close(r["ref_descriptors0"][0], out["ref_descriptors0"][0, 0], atol=1e-4, rtol=1e-4)
