@@ -449,8 +449,8 @@ extern "C" int lgb200_filter_matches(const float* scores, int B, int R, int C, c
                                      float threshold, const int32_t* ind0, const int32_t* ind1,
                                      int ind_ld, int N0, int N1, int64_t* m0, int64_t* m1,
                                      float* ms0, float* ms1, void* workspace, void* stream) {
-  if (!m0 || !m1 || !ms0 || !ms1) return LGB200_ERR_NULL;
   if (B <= 0 || R < 1 || C < 1 || N0 < 0 || N1 < 0) return LGB200_ERR_SHAPE;
+  if ((N0 > 0 && (!m0 || !ms0)) || (N1 > 0 && (!m1 || !ms1))) return LGB200_ERR_NULL;
   cudaStream_t st = lg_stream(stream);
   const long n0tot = (long)B * N0, n1tot = (long)B * N1;
   const long mx = n0tot > n1tot ? n0tot : n1tot;
