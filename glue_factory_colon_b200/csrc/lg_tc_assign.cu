@@ -1,0 +1,242 @@
+// MatchAssignment on tcgen05 (sm_100a): similarity GEMM fused with the dual log-softmax.
+//
+// Both passes run the same strip kernel: a CTA owns 128 rows of md[s] (resident in smem, K = 256)
+// and sweeps the 128-row tiles of the other image md[s^1] (TMA, 2-stage ring); each 128x128
+// similarity tile is produced by 16 tcgen05.mma into one of two TMEM accumulators so the MMAs
+// of tile j+1 overlap the epilogue of tile j.
+//   pass 1 (SCORES = false): epilogue keeps an online (max, sum-exp) per row -> lse[s, row].
+//          Run for every sequence: rows of image 0 give the row normaliser, rows of image 1 the
+//          column normaliser.  Nothing N x M is written.
+//   pass 2 (SCORES = true):  epilogue forms 2*sim - lse0[i] - lse1[j] + logsigmoid(z0[i]) +
+//          logsigmoid(z1[j]) and writes the fp32 score tile ONCE; tiles are transposed through
+//          shared memory so that every warp store is a contiguous 128-byte row segment.
+// The N x M matrix is therefore never materialised before its final form and never re-read.
+#include "lg_internal.cuh"
+#include "lg_tc_common.cuh"
+
+namespace {
+
+constexpr int AS_TILE = 128 * 64 * 2;        // one 128-row x 64-col bf16 box (16 KB)
+constexpr int AS_OPER = 4 * AS_TILE;         // 128 rows x K=256 (64 KB)
+constexpr int AS_STAGE_OFF = AS_OPER;        // B stages follow A
+constexpr int AS_BAR_OFF = 3 * AS_OPER;
+constexpr int AS_XPOSE_OFF = AS_BAR_OFF + 128;
+constexpr int AS_SMEM = AS_XPOSE_OFF + 4 * 32 * 33 * 4 + 1024;
+
+__device__ __forceinline__ float ex2a(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool SCORES>
+__global__ void __launch_bounds__(192, 1)
+tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t* __restrict__ lens,
+                 const float* __restrict__ z, const float* __restrict__ lse_in, float* __restrict__ lse_out,
+                 int R, int C, float* __restrict__ scores) {
+  // SCORES: blockIdx.y = pair b, rows from sequence 2b.  LSE: blockIdx.y = sequence s.
+  const int s = SCORES ? 2 * blockIdx.y : blockIdx.y;
+  const int so = s ^ 1;
+  const int m0 = blockIdx.x * 128;
+  const int nq = lens ? lens[s] : (SCORES ? R - 1 : Lp);
+  const int nk = lens ? lens[so] : (SCORES ? C - 1 : Lp);
+  if (m0 >= nq) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (nk + 127) / 128;
+  if (n_tiles == 0) {
+    if (!SCORES && warp >= 2) {
+      const int r = (warp & 3) * 32 + lane;
+      if (m0 + r < nq) lse_out[(size_t)s * Lp + m0 + r] = 0.f;
+    }
+    return;
+  }
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + AS_STAGE_OFF;  // 2 stages of AS_OPER
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AS_BAR_OFF);
+  uint64_t* a_full = bars;
+  uint64_t* b_full = bars + 1;   // [2]
+  uint64_t* b_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;   // [2]
+  uint64_t* s_empty = bars + 7;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  float* xpose = reinterpret_cast<float*>(smem + AS_XPOSE_OFF);
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmMd);
+    tc::mbar_init(a_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&b_full[i], 1);
+      tc::mbar_init(&b_empty[i], 1);
+      tc::mbar_init(&s_full[i], 1);
+      tc::mbar_init(&s_empty[i], 4);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 256);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tc::mbar_arrive_expect_tx(a_full, AS_OPER);
+      for (int kb = 0; kb < 4; ++kb) tc::tma_load_2d(sA + kb * AS_TILE, &tmMd, a_full, kb * 64, s * Lp + m0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        tc::mbar_wait(&b_empty[st], ((j >> 1) & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(&b_full[st], AS_OPER);
+        for (int kb = 0; kb < 4; ++kb)
+          tc::tma_load_2d(sB + st * AS_OPER + kb * AS_TILE, &tmMd, &b_full[st], kb * 64, so * Lp + j * 128);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::idesc_bf16(128, 128, 0);
+      const uint32_t aA = tc::smem_u32(sA);
+      tc::mbar_wait(a_full, 0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        tc::mbar_wait(&b_full[st], ph);
+        tc::mbar_wait(&s_empty[st], ph ^ 1);
+        tc::fence_after_sync();
+        const uint32_t aB = tc::smem_u32(sB + st * AS_OPER);
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc::umma_ss(tmem + st * 128, tc::smem_desc_sw128(aA + kb * AS_TILE + k * 32, 0, 1024),
+                        tc::smem_desc_sw128(aB + kb * AS_TILE + k * 32, 0, 1024), idesc, (kb | k) != 0);
+        tc::umma_commit(&s_full[st]);
+        tc::umma_commit(&b_empty[st]);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int row = m0 + r;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f;
+    float rowconst = 0.f;
+    if (SCORES && row < nq) rowconst = lg_logsigmoid(z[(size_t)s * Lp + row]) - lse_in[(size_t)s * Lp + row];
+    float* xp = xpose + (warp - 2) * 32 * 33;
+    for (int j = 0; j < n_tiles; ++j) {
+      const int st = j & 1;
+      tc::mbar_wait(&s_full[st], (j >> 1) & 1);
+      tc::fence_after_sync();
+      const int valid = nk - j * 128;
+      if constexpr (!SCORES) {
+        uint32_t sv[128];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tc::tmem_ld32(tmem + lane_base + st * 128 + c * 32, sv + c * 32);
+        tc::tmem_ld_wait();
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&s_empty[st]);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 128; ++i) {
+          if (i >= valid) sv[i] = 0xff800000u;
+          mx = fmaxf(mx, __uint_as_float(sv[i]));
+        }
+        const float m_new = fmaxf(m_run, mx);
+        const float ml2 = m_new * 1.4426950408889634f;
+        float rs = 0.f;
+#pragma unroll
+        for (int i = 0; i < 128; ++i) rs += ex2a(fmaf(__uint_as_float(sv[i]), 1.4426950408889634f, -ml2));
+        l_run = l_run * ex2a((m_run - m_new) * 1.4426950408889634f) + rs;
+        m_run = m_new;
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tc::tmem_ld32(tmem + lane_base + st * 128 + c * 32, v);
+          tc::tmem_ld_wait();
+          if (c == 3) {
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&s_empty[st]);
+          }
+          const int col = j * 128 + c * 32 + lane;  // this lane's column in the transposed phase
+          float colconst = 0.f;
+          if (col < nk) colconst = lg_logsigmoid(z[(size_t)so * Lp + col]) - lse_in[(size_t)so * Lp + col];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) xp[lane * 33 + i] = fmaf(2.f, __uint_as_float(v[i]), rowconst);
+          __syncwarp();
+          float* out = scores + ((size_t)blockIdx.y * R + m0 + quarter * 32) * C + col;
+          const int rows_here = min(32, nq - (m0 + quarter * 32));
+          if (col < nk) {
+            for (int rr = 0; rr < rows_here; ++rr) out[(size_t)rr * C] = xp[rr * 33 + lane] + colconst;
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (!SCORES && row < nq) lse_out[(size_t)s * Lp + row] = m_run + logf(l_run);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem, 256);
+  }
+}
+
+// Dustbin row / column and zero padding of scores [B,R,C]; one CTA per (row, pair).
+__global__ void assign_border_kernel(const float* __restrict__ z, int Lp, const int32_t* __restrict__ lens,
+                                     int R, int C, float* __restrict__ scores) {
+  const int b = blockIdx.y, r = blockIdx.x;
+  const int n0 = lens ? lens[2 * b] : R - 1, n1 = lens ? lens[2 * b + 1] : C - 1;
+  float* out = scores + ((size_t)b * R + r) * C;
+  if (r < n0) {
+    for (int c = n1 + threadIdx.x; c < C - 1; c += blockDim.x) out[c] = 0.f;
+    if (threadIdx.x == 0) out[C - 1] = lg_logsigmoid(-z[(size_t)(2 * b) * Lp + r]);
+  } else if (r == R - 1) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+      out[c] = c < n1 ? lg_logsigmoid(-z[(size_t)(2 * b + 1) * Lp + c]) : 0.f;
+  } else {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) out[c] = 0.f;
+  }
+}
+
+int make_md_map(CUtensorMap* tm, const __nv_bfloat16* md, int S, int Lp) {
+  const uint64_t d[2] = {256, (uint64_t)S * Lp}, sb[1] = {512};
+  const uint32_t box[2] = {64, 128};
+  return lg_make_tmap_bf16(tm, md, 2, d, sb, box);
+}
+
+}  // namespace
+
+int lg_tc_assign_lse(const __nv_bfloat16* md, int S, int Lp, const int32_t* lens, float* lse,
+                     cudaStream_t st) {
+  CUtensorMap tm;
+  int rc = make_md_map(&tm, md, S, Lp);
+  if (rc) return rc;
+  cudaError_t e = cudaFuncSetAttribute(tc_assign_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AS_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid(Lp / 128, S);
+  tc_assign_kernel<false><<<grid, 192, AS_SMEM, st>>>(tm, Lp, lens, nullptr, nullptr, lse, 0, 0, nullptr);
+  LG_LAUNCH_CHECK();
+  return LGB200_OK;
+}
+
+int lg_tc_assign_scores(const __nv_bfloat16* md, const float* z, const float* lse, int B, int Lp,
+                        const int32_t* lens, int R, int C, float* scores, cudaStream_t st) {
+  CUtensorMap tm;
+  int rc = make_md_map(&tm, md, 2 * B, Lp);
+  if (rc) return rc;
+  cudaError_t e = cudaFuncSetAttribute(tc_assign_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AS_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  assign_border_kernel<<<dim3(R, B), 128, 0, st>>>(z, Lp, lens, R, C, scores);
+  LG_LAUNCH_CHECK();
+  if (R > 1 && C > 1) {
+    dim3 grid((R - 1 + 127) / 128, B);
+    tc_assign_kernel<true><<<grid, 192, AS_SMEM, st>>>(tm, Lp, lens, z, lse, nullptr, R, C, scores);
+    LG_LAUNCH_CHECK();
+  }
+  return LGB200_OK;
+}
