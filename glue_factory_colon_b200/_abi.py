@@ -56,6 +56,8 @@ def load(path: Path = LIB_PATH):
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
         fn.restype = C.c_int
+    lib.lgb200_launch_count.argtypes = []
+    lib.lgb200_launch_count.restype = C.c_ulonglong
     lib.lgb200_error_string.argtypes = [C.c_int]
     lib.lgb200_error_string.restype = C.c_char_p
     if lib.lgb200_abi_version() != ABI_VERSION:

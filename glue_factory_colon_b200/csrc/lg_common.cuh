@@ -11,10 +11,14 @@
 #define LG_DH 64
 #define LG_D 256
 
+// Every kernel launch is followed by this macro: it surfaces launch errors and bumps the
+// process-wide launch counter that bench.py reports as "gpu_launches" (statistics only).
+extern unsigned long long lg_launch_counter;
 #define LG_LAUNCH_CHECK()                       \
   do {                                          \
     cudaError_t e__ = cudaGetLastError();       \
     if (e__ != cudaSuccess) return (int)e__;    \
+    ++lg_launch_counter;                        \
   } while (0)
 
 static inline cudaStream_t lg_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

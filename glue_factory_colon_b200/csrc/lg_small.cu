@@ -4,7 +4,10 @@
 // shuffles for reductions, no shared-memory tiling needed.
 #include "lg_common.cuh"
 
+unsigned long long lg_launch_counter = 0;
+
 extern "C" int lgb200_abi_version(void) { return LGB200_ABI_VERSION; }
+extern "C" unsigned long long lgb200_launch_count(void) { return lg_launch_counter; }
 
 extern "C" int lgb200_device_ok(void) {
   int dev = 0;

@@ -56,6 +56,8 @@ int lgb200_abi_version(void);
 /* 0 if the current device can run the kernels (compute capability 10.x). */
 int lgb200_device_ok(void);
 const char* lgb200_error_string(int code);
+/* Number of kernels this library has launched in the process so far (statistics for bench.py). */
+unsigned long long lgb200_launch_count(void);
 
 /* ---- input staging ------------------------------------------------------
  * Replaces descriptors.contiguous() + the implicit [B,N,d] layout,
