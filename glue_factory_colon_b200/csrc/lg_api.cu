@@ -1,5 +1,6 @@
 // extern "C" dispatch for the compute-bound entry points (include/lightglue_b200.h).
 #include "lg_internal.cuh"
+#include <stdlib.h>
 
 extern "C" int lgb200_linear(int precision, int epilogue, const void* A0, const void* A1, int K0,
                              const void* W, const float* bias, int T, int N, int K,
@@ -47,9 +48,16 @@ extern "C" int lgb200_linear(int precision, int epilogue, const void* A0, const 
   if (precision == LGB200_F32)
     return lg_simt_linear(epilogue, (const float*)A0, (const float*)A1, K0, (const float*)W, T, N, K,
                           lens, e, st);
-  if (precision == LGB200_BF16)
+  if (precision == LGB200_BF16) {
+    // v2 = weight-stationary / cluster-multicast kernel (lg_tc_gemm2.cu); LGB200_GEMM_V1=1 selects the
+    // first-generation streaming kernel (lg_tc_gemm.cu) for A/B measurements.
+    static const bool use_v1 = getenv("LGB200_GEMM_V1") != nullptr;
+    if (!use_v1)
+      return lg_tc_linear_v2(epilogue, (const __nv_bfloat16*)A0, (const __nv_bfloat16*)A1, K0,
+                             (const __nv_bfloat16*)W, T, N, K, lens, e, st);
     return lg_tc_linear(epilogue, (const __nv_bfloat16*)A0, (const __nv_bfloat16*)A1, K0,
                         (const __nv_bfloat16*)W, T, N, K, lens, e, st);
+  }
   return LGB200_ERR_PRECISION;
 }
 
