@@ -12,7 +12,7 @@ LIB_PATH = Path(__file__).resolve().parent / "lib" / "liblightglue_b200.so"
 
 F32, BF16 = 0, 1
 EPI_ROWMAJOR, EPI_HEADS, EPI_LN_GELU = 0, 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _p, _i, _f = C.c_void_p, C.c_int, C.c_float
 
@@ -21,16 +21,16 @@ SIGNATURES = {
     "lgb200_abi_version": [],
     "lgb200_device_ok": [],
     "lgb200_pack_rows": [_p, _i, _i, _i, _i, _i, _p, _p, _p],
-    "lgb200_posenc": [_p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p],
-    "lgb200_linear": [_i, _i, _p, _p, _i, _p, _p, _i, _i, _i, _p, _i, _f, _f, _f, _p, _p, _p, _p, _i,
+    "lgb200_posenc": [_p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p, _p],
+    "lgb200_linear": [_i, _i, _p, _p, _i, _p, _p, _i, _i, _i, _p, _i, _f, _f, _f, _p, _p, _p, _p, _p, _p, _i,
                       _p, _p, _p, _p, _p, _p],
     "lgb200_attention": [_i, _p, _p, _p, _i, _i, _p, _i, _p, _p],
-    "lgb200_rowdot": [_p, _p, _p, _i, _i, _p, _i, _p, _p],
+    "lgb200_rowdot": [_i, _p, _p, _p, _i, _i, _p, _i, _p, _p],
     "lgb200_assign_lse": [_i, _p, _i, _i, _p, _p, _p],
     "lgb200_assign_scores": [_i, _p, _p, _p, _i, _i, _p, _i, _i, _p, _p],
     "lgb200_filter_matches": [_p, _i, _i, _i, _p, _f, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p],
     "lgb200_exit_check": [_p, _i, _i, _p, _p, _f, _f, _i, _p, _p, _p],
-    "lgb200_prune_compact": [_p, _p, _f, _f, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "lgb200_prune_compact": [_p, _p, _f, _f, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
 }
 
 

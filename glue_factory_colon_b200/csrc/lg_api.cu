@@ -5,13 +5,15 @@
 extern "C" int lgb200_linear(int precision, int epilogue, const void* A0, const void* A1, int K0,
                              const void* W, const float* bias, int T, int N, int K,
                              const int32_t* lens, int Lp, float scale0, float scale1, float scale2,
-                             const float* resid32, float* out32, void* out16, const float* rot,
-                             int n_rot, void* outp0, void* outp1, void* outp2, const float* gamma,
-                             const float* beta, void* stream) {
+                             const float* resid32, const void* resid16, float* out32, void* out16,
+                             const float* rot, const void* rot16, int n_rot, void* outp0, void* outp1,
+                             void* outp2, const float* gamma, const float* beta, void* stream) {
   if (!A0 || !W || !bias) return LGB200_ERR_NULL;
   if (T <= 0 || N <= 0 || K <= 0 || K0 <= 0 || K0 > K || Lp <= 0 || Lp % 128 || T % Lp)
     return LGB200_ERR_SHAPE;
   if (K0 < K && !A1) return LGB200_ERR_NULL;
+  if (resid32 && resid16) return LGB200_ERR_SHAPE;
+  if (precision == LGB200_F32 && (resid16 || (rot16 && !rot))) return LGB200_ERR_PRECISION;
   LgEpi e;
   e.mode = epilogue;
   e.N = N;
@@ -34,7 +36,7 @@ extern "C" int lgb200_linear(int precision, int epilogue, const void* A0, const 
       if (N % 256 || N / 256 > 3) return LGB200_ERR_SHAPE;
       for (int p = 0; p < N / 256; ++p)
         if (!e.outp[p]) return LGB200_ERR_NULL;
-      if (n_rot > 0 && !rot) return LGB200_ERR_NULL;
+      if (n_rot > 0 && !rot && !rot16) return LGB200_ERR_NULL;
       break;
     }
     case LGB200_EPI_LN_GELU:
@@ -52,9 +54,13 @@ extern "C" int lgb200_linear(int precision, int epilogue, const void* A0, const 
     // v2 = weight-stationary / cluster-multicast kernel (lg_tc_gemm2.cu); LGB200_GEMM_V1=1 selects the
     // first-generation streaming kernel (lg_tc_gemm.cu) for A/B measurements.
     static const bool use_v1 = getenv("LGB200_GEMM_V1") != nullptr;
-    if (!use_v1)
-      return lg_tc_linear_v2(epilogue, (const __nv_bfloat16*)A0, (const __nv_bfloat16*)A1, K0,
-                             (const __nv_bfloat16*)W, T, N, K, lens, e, st);
+    if (!use_v1) {
+      const int rc = lg_tc_linear_v2(epilogue, (const __nv_bfloat16*)A0, (const __nv_bfloat16*)A1, K0,
+                                     (const __nv_bfloat16*)W, T, N, K, lens, e, rot16,
+                                     (const __nv_bfloat16*)resid16, st);
+      if (rc != LGB200_ERR_SHAPE) return rc;  // v2 covers bf16-in/bf16-out shapes; the rest goes to v1
+    }
+    if (resid16 || (n_rot > 0 && !rot)) return LGB200_ERR_SHAPE;  // v1 takes fp32 side inputs only
     return lg_tc_linear(epilogue, (const __nv_bfloat16*)A0, (const __nv_bfloat16*)A1, K0,
                         (const __nv_bfloat16*)W, T, N, K, lens, e, st);
   }

@@ -3,6 +3,7 @@
 // filter_matches.  All are streaming kernels: coalesced 16-byte accesses, warp
 // shuffles for reductions, no shared-memory tiling needed.
 #include "lg_common.cuh"
+#include <cuda_fp16.h>
 
 unsigned long long lg_launch_counter = 0;
 
@@ -43,7 +44,7 @@ __global__ void pack_rows_kernel(const float* __restrict__ src, int n, int dim4,
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (l < n) v = reinterpret_cast<const float4*>(src)[((size_t)b * n + l) * dim4 + c4];
     const size_t o = ((size_t)s * Lp + l) * dim4 + c4;
-    reinterpret_cast<float4*>(x32)[o] = v;
+    if (x32) reinterpret_cast<float4*>(x32)[o] = v;
     if (x16) {
       __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
       uint2 pk;
@@ -56,7 +57,7 @@ __global__ void pack_rows_kernel(const float* __restrict__ src, int n, int dim4,
 
 extern "C" int lgb200_pack_rows(const float* src, int B, int n, int dim, int img, int Lp,
                                 float* x32, void* x16, void* stream) {
-  if (!src || !x32) return LGB200_ERR_NULL;
+  if (!src || (!x32 && !x16)) return LGB200_ERR_NULL;
   if (dim % 4 || Lp % 128 || n > Lp || B <= 0 || (img != 0 && img != 1)) return LGB200_ERR_SHAPE;
   const int total = Lp * (dim / 4);
   dim3 grid((total + 255) / 256 > 148 * 4 ? 148 * 4 : (total + 255) / 256, B);
@@ -74,7 +75,7 @@ extern "C" int lgb200_pack_rows(const float* src, int B, int n, int dim, int img
 __global__ void posenc_kernel(const float* __restrict__ kpts, int n, int kdim,
                               const float* __restrict__ size, const float* __restrict__ Wr,
                               const int32_t* __restrict__ lens, int img, int Lp,
-                              float* __restrict__ rot) {
+                              float* __restrict__ rot, __half2* __restrict__ rot16) {
   const int b = blockIdx.x;
   const int s = 2 * b + img;
   const int nv = lens ? min(lens[s], n) : n;
@@ -131,16 +132,18 @@ __global__ void posenc_kernel(const float* __restrict__ kpts, int n, int kdim,
       if (kdim == 4) p += kp[(size_t)l * kdim + 2] * sW[f * 4 + 2] + kp[(size_t)l * kdim + 3] * sW[f * 4 + 3];
       sincosf(p, &cs.y, &cs.x);
     }
-    reinterpret_cast<float2*>(rot)[((size_t)s * Lp + l) * 32 + f] = cs;
+    if (rot) reinterpret_cast<float2*>(rot)[((size_t)s * Lp + l) * 32 + f] = cs;
+    if (rot16) rot16[((size_t)s * Lp + l) * 32 + f] = __floats2half2_rn(cs.x, cs.y);
   }
 }
 
 extern "C" int lgb200_posenc(const float* kpts, int B, int n, int kdim, const float* size,
                              const float* Wr, const int32_t* lens, int img, int Lp, float* rot,
-                             void* stream) {
-  if (!kpts || !Wr || !rot) return LGB200_ERR_NULL;
+                             void* rot16, void* stream) {
+  if (!kpts || !Wr || (!rot && !rot16)) return LGB200_ERR_NULL;
   if ((kdim != 2 && kdim != 4) || Lp % 128 || n > Lp || B <= 0) return LGB200_ERR_SHAPE;
-  posenc_kernel<<<B, 1024, 0, lg_stream(stream)>>>(kpts, n, kdim, size, Wr, lens, img, Lp, rot);
+  posenc_kernel<<<B, 1024, 0, lg_stream(stream)>>>(kpts, n, kdim, size, Wr, lens, img, Lp, rot,
+                                                   reinterpret_cast<__half2*>(rot16));
   LG_LAUNCH_CHECK();
   return LGB200_OK;
 }
@@ -148,7 +151,8 @@ extern "C" int lgb200_posenc(const float* kpts, int B, int n, int kdim, const fl
 // ---------------------------------------------------------------------------
 // rowdot: Linear(256,1) (+sigmoid) per token.  One warp per row, 2x float4 per lane.
 // ---------------------------------------------------------------------------
-__global__ void rowdot_kernel(const float* __restrict__ x, const float* __restrict__ w,
+template <bool BF>
+__global__ void rowdot_kernel(const void* __restrict__ xv, const float* __restrict__ w,
                               const float* __restrict__ bias, int S, int Lp,
                               const int32_t* __restrict__ lens, int sig, float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
@@ -156,11 +160,20 @@ __global__ void rowdot_kernel(const float* __restrict__ x, const float* __restri
   if (row >= S * Lp) return;
   const int s = row / Lp, l = row - s * Lp;
   if (lens && l >= lens[s]) return;  // rows past the valid prefix are left untouched
-  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * LG_D);
   const float4* wr = reinterpret_cast<const float4*>(w);
-  const float4 a0 = xr[lane], a1 = xr[lane + 32], w0 = wr[lane], w1 = wr[lane + 32];
-  float acc = a0.x * w0.x + a0.y * w0.y + a0.z * w0.z + a0.w * w0.w + a1.x * w1.x + a1.y * w1.y +
-              a1.z * w1.z + a1.w * w1.w;
+  float acc;
+  if (BF) {  // 8 consecutive bf16 per lane (one 16-byte load)
+    const uint4 raw = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(xv) + (size_t)row * LG_D)[lane];
+    const float4 w0 = wr[2 * lane], w1 = wr[2 * lane + 1];
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    acc = __low2float(h[0]) * w0.x + __high2float(h[0]) * w0.y + __low2float(h[1]) * w0.z + __high2float(h[1]) * w0.w +
+          __low2float(h[2]) * w1.x + __high2float(h[2]) * w1.y + __low2float(h[3]) * w1.z + __high2float(h[3]) * w1.w;
+  } else {
+    const float4* xr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(xv) + (size_t)row * LG_D);
+    const float4 a0 = xr[lane], a1 = xr[lane + 32], w0 = wr[lane], w1 = wr[lane + 32];
+    acc = a0.x * w0.x + a0.y * w0.y + a0.z * w0.z + a0.w * w0.w + a1.x * w1.x + a1.y * w1.y +
+          a1.z * w1.z + a1.w * w1.w;
+  }
   for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) {
     acc += bias[0];
@@ -168,12 +181,16 @@ __global__ void rowdot_kernel(const float* __restrict__ x, const float* __restri
   }
 }
 
-extern "C" int lgb200_rowdot(const float* x32, const float* w, const float* b, int S, int Lp,
+extern "C" int lgb200_rowdot(int precision, const void* x, const float* w, const float* b, int S, int Lp,
                              const int32_t* lens, int apply_sigmoid, float* out, void* stream) {
-  if (!x32 || !w || !b || !out) return LGB200_ERR_NULL;
+  if (!x || !w || !b || !out) return LGB200_ERR_NULL;
+  if (precision != LGB200_F32 && precision != LGB200_BF16) return LGB200_ERR_PRECISION;
   const long rows = (long)S * Lp;
   const int blocks = (int)((rows * 32 + 255) / 256);
-  rowdot_kernel<<<blocks, 256, 0, lg_stream(stream)>>>(x32, w, b, S, Lp, lens, apply_sigmoid, out);
+  if (precision == LGB200_BF16)
+    rowdot_kernel<true><<<blocks, 256, 0, lg_stream(stream)>>>(x, w, b, S, Lp, lens, apply_sigmoid, out);
+  else
+    rowdot_kernel<false><<<blocks, 256, 0, lg_stream(stream)>>>(x, w, b, S, Lp, lens, apply_sigmoid, out);
   LG_LAUNCH_CHECK();
   return LGB200_OK;
 }
@@ -234,7 +251,7 @@ __global__ void __launch_bounds__(1024) prune_compact_kernel(
     int Lp, int32_t* __restrict__ lens, int32_t* __restrict__ lens_active,
     const float* __restrict__ x32s, float* __restrict__ x32d, const __nv_bfloat16* __restrict__ x16s,
     __nv_bfloat16* __restrict__ x16d, const float* __restrict__ rots, float* __restrict__ rotd,
-    const int32_t* __restrict__ inds, int32_t* __restrict__ indd, int32_t* __restrict__ prune_cnt) {
+    const uint32_t* __restrict__ rot16s, uint32_t* __restrict__ rot16d, const int32_t* __restrict__ inds, int32_t* __restrict__ indd, int32_t* __restrict__ prune_cnt) {
   __shared__ int16_t dst[LG_MAX_LP];
   __shared__ int warp_sum[32];
   __shared__ int running;
@@ -277,15 +294,18 @@ __global__ void __launch_bounds__(1024) prune_compact_kernel(
     const int d = dst[l];
     if (d < 0) continue;
     const size_t so = (size_t)s * Lp + l, dofs = (size_t)s * Lp + d;
-    const float4* a = reinterpret_cast<const float4*>(x32s + so * LG_D);
-    float4* o = reinterpret_cast<float4*>(x32d + dofs * LG_D);
-    o[lane] = a[lane];
-    o[lane + 32] = a[lane + 32];
+    if (x32s) {
+      const float4* a = reinterpret_cast<const float4*>(x32s + so * LG_D);
+      float4* o = reinterpret_cast<float4*>(x32d + dofs * LG_D);
+      o[lane] = a[lane];
+      o[lane + 32] = a[lane + 32];
+    }
     if (x16s) {
       reinterpret_cast<uint4*>(x16d + dofs * LG_D)[lane] =
           reinterpret_cast<const uint4*>(x16s + so * LG_D)[lane];
     }
-    reinterpret_cast<float2*>(rotd + dofs * 64)[lane] = reinterpret_cast<const float2*>(rots + so * 64)[lane];
+    if (rots) reinterpret_cast<float2*>(rotd + dofs * 64)[lane] = reinterpret_cast<const float2*>(rots + so * 64)[lane];
+    if (rot16s) rot16d[dofs * 32 + lane] = rot16s[so * 32 + lane];
     if (lane == 0) {
       const int orig = inds[so];
       indd[dofs] = orig;
@@ -302,10 +322,12 @@ extern "C" int lgb200_prune_compact(const float* match, const float* conf, float
                                     float width_conf, int S, int Lp, int32_t* lens,
                                     int32_t* lens_active, const float* x32_src, float* x32_dst,
                                     const void* x16_src, void* x16_dst, const float* rot_src,
-                                    float* rot_dst, const int32_t* ind_src, int32_t* ind_dst,
-                                    int32_t* prune_cnt, void* stream) {
-  if (!match || !lens || !lens_active || !x32_src || !x32_dst || !rot_src || !rot_dst || !ind_src ||
-      !ind_dst || !prune_cnt)
+                                    float* rot_dst, const void* rot16_src, void* rot16_dst,
+                                    const int32_t* ind_src, int32_t* ind_dst, int32_t* prune_cnt,
+                                    void* stream) {
+  if (!match || !lens || !lens_active || !ind_src || !ind_dst || !prune_cnt) return LGB200_ERR_NULL;
+  if ((x32_src && !x32_dst) || (x16_src && !x16_dst) || (rot_src && !rot_dst) || (rot16_src && !rot16_dst) ||
+      (!x32_src && !x16_src))
     return LGB200_ERR_NULL;
   if (Lp > LG_MAX_LP || Lp % 128) return LGB200_ERR_SHAPE;
   // lightglue.py:564: keep = scores > (1 - width_confidence), evaluated in fp32
@@ -313,7 +335,8 @@ extern "C" int lgb200_prune_compact(const float* match, const float* conf, float
   prune_compact_kernel<<<S, 1024, 0, lg_stream(stream)>>>(
       match, conf, thr, keep_above, Lp, lens, lens_active, x32_src, x32_dst,
       reinterpret_cast<const __nv_bfloat16*>(x16_src), reinterpret_cast<__nv_bfloat16*>(x16_dst),
-      rot_src, rot_dst, ind_src, ind_dst, prune_cnt);
+      rot_src, rot_dst, reinterpret_cast<const uint32_t*>(rot16_src), reinterpret_cast<uint32_t*>(rot16_dst),
+      ind_src, ind_dst, prune_cnt);
   LG_LAUNCH_CHECK();
   return LGB200_OK;
 }

@@ -321,9 +321,11 @@ class LightGlue(nn.Module):
 
         act = torch.bfloat16 if bf else torch.float32
         adt = dict(device=dev, dtype=act)
-        x32 = torch.empty(T, 256, **f32)
-        x16 = torch.empty(T, 256, **adt) if bf else None
-        rot = torch.empty(T, 64, **f32)
+        # Residual stream x [T,256] in the activation dtype (bf16 mode keeps it in bf16 only: measured
+        # against the fp32 oracle this is still 2x closer than the reference's own autocast run).
+        x = torch.empty(T, 256, **adt)
+        rot = None if bf else torch.empty(T, 64, **f32)           # (cos, sin) fp32 pairs
+        rot16 = torch.empty(T, 32, **i32) if bf else None          # packed fp16 (cos, sin)
         q = torch.zeros(T * 256, **adt)
         k = torch.zeros(T * 256, **adt)
         v = torch.zeros(T * 256, **adt)
@@ -332,34 +334,40 @@ class LightGlue(nn.Module):
         hid = torch.zeros(T, 512, **adt)
 
         def linear(epi, A0, Wt, bias, N, K, A1=None, K0=None, scale=(1.0, 1.0, 1.0), resid=None,
-                   out32=None, out16=None, n_rot=0, outp=(None, None, None), gamma=None, beta=None,
-                   lens_=None):
+                   out=None, n_rot=0, outp=(None, None, None), gamma=None, beta=None, lens_=None):
+            r32, r16 = (None, resid) if bf else (resid, None)
+            o32, o16 = (None, out) if bf else (out, None)
             check(
                 lib.lgb200_linear(
                     prec, epi, ptr(A0), ptr(A1), K if K0 is None else K0, ptr(Wt), ptr(bias), T, N, K,
-                    ptr(lens_), Lp, scale[0], scale[1], scale[2], ptr(resid), ptr(out32), ptr(out16),
-                    ptr(rot), n_rot, ptr(outp[0]), ptr(outp[1]), ptr(outp[2]), ptr(gamma), ptr(beta), st,
+                    ptr(lens_), Lp, scale[0], scale[1], scale[2], ptr(r32), ptr(r16), ptr(o32), ptr(o16),
+                    ptr(rot), ptr(rot16), n_rot, ptr(outp[0]), ptr(outp[1]), ptr(outp[2]), ptr(gamma),
+                    ptr(beta), st,
                 ),
                 "lgb200_linear",
             )
 
-        def rowmajor_out(t):
-            return dict(out16=t) if bf else dict(out32=t)
+        def pack(dsc, cnt, dim, img, dst):
+            x32_, x16_ = (None, dst) if bf else (dst, None)
+            check(lib.lgb200_pack_rows(ptr(dsc), B, cnt, dim, img, Lp, ptr(x32_), ptr(x16_), st), "pack_rows")
+
+        def rowdot(xt, wb, lens_, sigmoid, out):
+            check(lib.lgb200_rowdot(prec, ptr(xt), ptr(wb[0]), ptr(wb[1]), S, Lp, ptr(lens_), sigmoid, ptr(out), st),
+                  "lgb200_rowdot")
 
         # ---- staging: descriptors (+ input_proj) and positional encoding ----
         if isinstance(self.input_proj, nn.Linear):
             din = conf.input_dim
-            xin32 = torch.empty(T, din, **f32)
-            xin16 = torch.empty(T, din, **adt) if bf else None
+            xin = torch.empty(T, din, **adt)
             for img, dsc, cnt in ((0, desc0, m), (1, desc1, n)):
-                check(lib.lgb200_pack_rows(ptr(dsc), B, cnt, din, img, Lp, ptr(xin32), ptr(xin16), st), "pack_rows")
-            linear(EPI_ROWMAJOR, xin16 if bf else xin32, W["in_w"], W["in_b"], 256, din, out32=x32, out16=x16)
+                pack(dsc, cnt, din, img, xin)
+            linear(EPI_ROWMAJOR, xin, W["in_w"], W["in_b"], 256, din, out=x)
         else:
             for img, dsc, cnt in ((0, desc0, m), (1, desc1, n)):
-                check(lib.lgb200_pack_rows(ptr(dsc), B, cnt, 256, img, Lp, ptr(x32), ptr(x16), st), "pack_rows")
+                pack(dsc, cnt, 256, img, x)
         for img, kk, cnt, sz in ((0, k0, m, size0), (1, k1, n, size1)):
-            check(lib.lgb200_posenc(ptr(kk), B, cnt, kdim, ptr(sz), ptr(W["wr"]), ptr(lens), img, Lp, ptr(rot), st),
-                  "lgb200_posenc")
+            check(lib.lgb200_posenc(ptr(kk), B, cnt, kdim, ptr(sz), ptr(W["wr"]), ptr(lens), img, Lp, ptr(rot),
+                                    ptr(rot16), st), "lgb200_posenc")
 
         # ---- adaptive state (device resident) ----
         if adaptive:
@@ -370,38 +378,39 @@ class LightGlue(nn.Module):
         if do_prune:
             ind = torch.arange(Lp, **i32).repeat(S, 1).contiguous()
             prune_cnt = torch.ones(S, Lp, **i32)
-            x32_b, rot_b, ind_b = torch.zeros_like(x32), torch.zeros_like(rot), torch.zeros_like(ind)
-            x16_b = torch.zeros_like(x16) if bf else None
+            x_b, ind_b = torch.zeros_like(x), torch.zeros_like(ind)
+            rot_b = None if bf else torch.zeros_like(rot)
+            rot16_b = torch.zeros_like(rot16) if bf else None
         exit_layer = np.full(B, L - 1, dtype=np.int64)
+        thresholds = [self.confidence_threshold(i) for i in range(L)]
 
         q_scale = LOG2E / math.sqrt(64.0)
         c_scale = math.sqrt(q_scale)
         for i in range(L):
             w = W["layers"][i]
-            xa = x16 if bf else x32
             la = lens_act
             # self block (lightglue.py:151-164)
-            linear(EPI_HEADS, xa, w["qkv_w"], w["qkv_b"], 768, 256, scale=(q_scale, 1.0, 1.0), n_rot=2,
+            linear(EPI_HEADS, x, w["qkv_w"], w["qkv_b"], 768, 256, scale=(q_scale, 1.0, 1.0), n_rot=2,
                    outp=(q, k, v), lens_=la)
             check(lib.lgb200_attention(prec, ptr(q), ptr(k), ptr(v), S, Lp, ptr(la), 0, ptr(ctx), st), "attention")
-            linear(EPI_ROWMAJOR, ctx, w["so_w"], w["so_b"], 256, 256, lens_=la, **rowmajor_out(msg))
-            linear(EPI_LN_GELU, xa, w["sf0_w"], w["sf0_b"], 512, 512, A1=msg, K0=256, gamma=w["sln_g"],
-                   beta=w["sln_b"], lens_=la, **rowmajor_out(hid))
-            linear(EPI_ROWMAJOR, hid, w["sf3_w"], w["sf3_b"], 256, 512, resid=x32, out32=x32, out16=x16, lens_=la)
+            linear(EPI_ROWMAJOR, ctx, w["so_w"], w["so_b"], 256, 256, out=msg, lens_=la)
+            linear(EPI_LN_GELU, x, w["sf0_w"], w["sf0_b"], 512, 512, A1=msg, K0=256, gamma=w["sln_g"],
+                   beta=w["sln_b"], out=hid, lens_=la)
+            linear(EPI_ROWMAJOR, hid, w["sf3_w"], w["sf3_b"], 256, 512, resid=x, out=x, lens_=la)
             # cross block (lightglue.py:193-222)
-            linear(EPI_HEADS, xa, w["cqv_w"], w["cqv_b"], 512, 256, scale=(c_scale, 1.0, 1.0), n_rot=0,
+            linear(EPI_HEADS, x, w["cqv_w"], w["cqv_b"], 512, 256, scale=(c_scale, 1.0, 1.0), n_rot=0,
                    outp=(q, v, None), lens_=la)
             check(lib.lgb200_attention(prec, ptr(q), ptr(q), ptr(v), S, Lp, ptr(la), 1, ptr(ctx), st), "attention")
-            linear(EPI_ROWMAJOR, ctx, w["co_w"], w["co_b"], 256, 256, lens_=la, **rowmajor_out(msg))
-            linear(EPI_LN_GELU, xa, w["cf0_w"], w["cf0_b"], 512, 512, A1=msg, K0=256, gamma=w["cln_g"],
-                   beta=w["cln_b"], lens_=la, **rowmajor_out(hid))
-            linear(EPI_ROWMAJOR, hid, w["cf3_w"], w["cf3_b"], 256, 512, resid=x32, out32=x32, out16=x16, lens_=la)
+            linear(EPI_ROWMAJOR, ctx, w["co_w"], w["co_b"], 256, 256, out=msg, lens_=la)
+            linear(EPI_LN_GELU, x, w["cf0_w"], w["cf0_b"], 512, 512, A1=msg, K0=256, gamma=w["cln_g"],
+                   beta=w["cln_b"], out=hid, lens_=la)
+            linear(EPI_ROWMAJOR, hid, w["cf3_w"], w["cf3_b"], 256, 512, resid=x, out=x, lens_=la)
             if i == L - 1 or not adaptive:
                 continue
-            thr = float(self.confidence_thresholds[i])
+            thr = thresholds[i]
             if do_early:  # lightglue.py:501-505
                 tk = W["token"][i]
-                check(lib.lgb200_rowdot(ptr(x32), ptr(tk["w"]), ptr(tk["b"]), S, Lp, ptr(la), 1, ptr(conf_buf), st), "rowdot")
+                rowdot(x, (tk["w"], tk["b"]), la, 1, conf_buf)
                 check(lib.lgb200_exit_check(ptr(conf_buf), B, Lp, ptr(lens), ptr(total), thr,
                                             float(conf.depth_confidence), i, ptr(done), ptr(lens_act), st), "exit_check")
                 done_h = done.cpu().numpy()  # one host read per layer (the reference syncs 2-3 times)
@@ -411,21 +420,23 @@ class LightGlue(nn.Module):
                     break
             if do_prune:  # lightglue.py:506-521
                 ma = W["assign"][i]
-                check(lib.lgb200_rowdot(ptr(x32), ptr(ma["m_w"]), ptr(ma["m_b"]), S, Lp, ptr(la), 1, ptr(msig), st), "rowdot")
+                rowdot(x, (ma["m_w"], ma["m_b"]), la, 1, msig)
+                x32s, x16s = (None, x) if bf else (x, None)
+                x32d, x16d = (None, x_b) if bf else (x_b, None)
                 check(lib.lgb200_prune_compact(ptr(msig), ptr(conf_buf) if do_early else None, thr,
                                                float(conf.width_confidence), S, Lp, ptr(lens), ptr(lens_act),
-                                               ptr(x32), ptr(x32_b), ptr(x16), ptr(x16_b), ptr(rot), ptr(rot_b),
-                                               ptr(ind), ptr(ind_b), ptr(prune_cnt), st), "prune_compact")
-                x32, x32_b = x32_b, x32
-                x16, x16_b = x16_b, x16
+                                               ptr(x32s), ptr(x32d), ptr(x16s), ptr(x16d), ptr(rot), ptr(rot_b),
+                                               ptr(rot16), ptr(rot16_b), ptr(ind), ptr(ind_b), ptr(prune_cnt), st),
+                      "prune_compact")
+                x, x_b = x_b, x
                 rot, rot_b = rot_b, rot
+                rot16, rot16_b = rot16_b, rot16
                 ind, ind_b = ind_b, ind
 
         # ---- log assignment (lightglue.py:523-524) ----
         md = msg  # reuse: [T,256] in the activation dtype
         z = torch.zeros(T, **f32)
         lse = torch.zeros(T, **f32)
-        xa = x16 if bf else x32
         for e in np.unique(exit_layer):
             if adaptive and lens is not None and len(np.unique(exit_layer)) > 1:
                 sel = torch.from_numpy(np.repeat(exit_layer == e, 2)).to(dev)
@@ -433,9 +444,8 @@ class LightGlue(nn.Module):
             else:
                 lens_g = lens
             a = W["assign"][int(e)]
-            linear(EPI_ROWMAJOR, xa, a["fp_w"], a["fp_b"], 256, 256, scale=(0.25, 1.0, 1.0), lens_=lens_g,
-                   **rowmajor_out(md))
-            check(lib.lgb200_rowdot(ptr(x32), ptr(a["m_w"]), ptr(a["m_b"]), S, Lp, ptr(lens_g), 0, ptr(z), st), "rowdot")
+            linear(EPI_ROWMAJOR, x, a["fp_w"], a["fp_b"], 256, 256, scale=(0.25, 1.0, 1.0), out=md, lens_=lens_g)
+            rowdot(x, (a["m_w"], a["m_b"]), lens_g, 0, z)
             check(lib.lgb200_assign_lse(prec, ptr(md), S, Lp, ptr(lens_g), ptr(lse), st), "assign_lse")
         if do_prune:
             lens_final = lens.cpu().numpy().reshape(B, 2)  # pruned shape is data dependent (lightglue.py:285 note)
@@ -461,7 +471,7 @@ class LightGlue(nn.Module):
             "filter_matches",
         )
 
-        xv = x32.view(B, 2, Lp, 256)
+        xv = x.view(B, 2, Lp, 256)
         if do_prune:
             pc = prune_cnt.view(B, 2, Lp)
             prune0, prune1 = pc[:, 0, :m].to(torch.int64), pc[:, 1, :n].to(torch.int64)
@@ -476,8 +486,8 @@ class LightGlue(nn.Module):
             "matches1": m1,
             "matching_scores0": ms0,
             "matching_scores1": ms1,
-            "ref_descriptors0": ref0,
-            "ref_descriptors1": ref1,
+            "ref_descriptors0": ref0.float(),  # fp32 like the reference (zero-copy view in fp32 mode)
+            "ref_descriptors1": ref1.float(),
             "log_assignment": scores,
             "prune0": prune0,
             "prune1": prune1,

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define LGB200_ABI_VERSION 1
+#define LGB200_ABI_VERSION 2
 
 enum { LGB200_F32 = 0, LGB200_BF16 = 1 };
 
@@ -62,8 +62,8 @@ unsigned long long lgb200_launch_count(void);
 /* ---- input staging ------------------------------------------------------
  * Replaces descriptors.contiguous() + the implicit [B,N,d] layout,
  * lightglue.py:456-465 (input_proj itself goes through lgb200_linear).
- * src [B, n, dim] fp32 -> rows of sequences (2*b + img): x32 [S,Lp,dim] fp32 and,
- * when x16 != NULL, a bf16 shadow.  Rows >= n are zero-filled. */
+ * src [B, n, dim] fp32 -> rows of sequences (2*b + img): x32 [S,Lp,dim] fp32 and/or
+ * x16 (bf16); either may be NULL, not both.  Rows >= n are zero-filled. */
 int lgb200_pack_rows(const float* src, int B, int n, int dim, int img, int Lp,
                      float* x32, void* x16, void* stream);
 
@@ -74,10 +74,13 @@ int lgb200_pack_rows(const float* src, int B, int n, int dim, int img, int Lp,
  * size [B,2] (W,H) or NULL (extent of the valid points), Wr [32,kdim].
  * rot [S,Lp,64] fp32 receives (cos_f, sin_f) pairs, f = 0..31, for sequence
  * 2*b+img; one table serves the 4 heads and all layers (the reference's
- * repeat_interleave(2) is implicit: rotary pair f uses entry f). */
+ * repeat_interleave(2) is implicit: rotary pair f uses entry f).
+ * rot16 [S,Lp,32] (nullable) receives the same pairs as packed fp16 (cos, sin):
+ * the 128-byte-per-token table the bf16 QKV epilogue fetches by TMA.
+ * At least one of rot / rot16 must be given. */
 int lgb200_posenc(const float* kpts, int B, int n, int kdim, const float* size,
                   const float* Wr, const int32_t* lens, int img, int Lp,
-                  float* rot, void* stream);
+                  float* rot, void* rot16, void* stream);
 
 /* ---- linear layers with fused epilogues -------------------------------------
  * Replaces nn.Linear + the elementwise ops around it:
@@ -91,19 +94,23 @@ int lgb200_posenc(const float* kpts, int B, int n, int kdim, const float* size,
  * A1[T,K-K0] (A1 NULL when K0 == K) -- this is the ffn's torch.cat([x,msg],-1).
  * A and W are fp32 (LGB200_F32) or bf16 (LGB200_BF16); bias/gamma/beta fp32.
  *   ROWMAJOR: out32 (fp32, nullable) / out16 (bf16, nullable), leading dim N;
- *             resid32 [T,N] fp32 nullable.
+ *             residual: resid32 [T,N] fp32 or resid16 [T,N] bf16 (at most one).
+ *             The bf16 throughput path keeps the residual stream in bf16 only
+ *             (resid16 == out16 updates it in place).
  *   HEADS:    N = parts*256, column c = part*256 + head*64 + d (the caller
  *             permutes Wqkv rows from the reference's head*192 + d*3 + part).
- *             Parts < n_rot get the rotary embedding from rot [T,64]; part p is
- *             scaled by scale[p] and written to outp[p] laid out [S,4,Lp,64]
- *             in the precision's element type.
+ *             Parts < n_rot get the rotary embedding from rot [T,64] fp32 or
+ *             rot16 [T,32] packed fp16 (cos,sin) (LGB200_BF16 prefers rot16);
+ *             part p is scaled by scale[p] and written to outp[p] laid out
+ *             [S,4,Lp,64] in the precision's element type.
  *   LN_GELU:  N = 512; out as ROWMAJOR. */
 int lgb200_linear(int precision, int epilogue, const void* A0, const void* A1, int K0,
                   const void* W, const float* bias, int T, int N, int K,
                   const int32_t* lens, int Lp,
                   float scale0, float scale1, float scale2,
-                  const float* resid32, float* out32, void* out16,
-                  const float* rot, int n_rot, void* outp0, void* outp1, void* outp2,
+                  const float* resid32, const void* resid16, float* out32, void* out16,
+                  const float* rot, const void* rot16, int n_rot,
+                  void* outp0, void* outp1, void* outp2,
                   const float* gamma, const float* beta, void* stream);
 
 /* ---- attention ---------------------------------------------------------------
@@ -121,9 +128,10 @@ int lgb200_attention(int precision, const void* Q, const void* K, const void* V,
 
 /* ---- per-token heads -----------------------------------------------------------
  * Replaces matchability / token-confidence Linear(256,1) (+ sigmoid),
- * lightglue.py:72,75-80,285-286,290-291.  out[r] = dot(x32[r,:], w) + b,
- * sigmoid applied when apply_sigmoid != 0; rows >= lens[s] are left untouched. */
-int lgb200_rowdot(const float* x32, const float* w, const float* b, int S, int Lp,
+ * lightglue.py:72,75-80,285-286,290-291.  out[r] = dot(x[r,:], w) + b with x
+ * [S*Lp,256] fp32 (LGB200_F32) or bf16 (LGB200_BF16), w/b fp32; sigmoid applied
+ * when apply_sigmoid != 0; rows >= lens[s] are left untouched. */
+int lgb200_rowdot(int precision, const void* x, const float* w, const float* b, int S, int Lp,
                   const int32_t* lens, int apply_sigmoid, float* out, void* stream);
 
 /* ---- log assignment ---------------------------------------------------------------
@@ -173,12 +181,14 @@ int lgb200_exit_check(const float* conf, int B, int Lp, const int32_t* lens,
  * (conf != NULL && conf[s,l] <= thr).  Rows are compacted from the *_src
  * buffers into the *_dst buffers (stable order), lens[s] is updated on the
  * device, prune_cnt[s, ind] += 1 for kept rows.  Sequences with
- * lens_active[s] == 0 are copied through unchanged in count (not pruned). */
+ * lens_active[s] == 0 are copied through unchanged in count (not pruned).
+ * Each of the x32 / x16 / rot / rot16 buffer pairs may be NULL (not in use). */
 int lgb200_prune_compact(const float* match, const float* conf, float thr, float width_conf,
                          int S, int Lp, int32_t* lens, int32_t* lens_active,
                          const float* x32_src, float* x32_dst,
                          const void* x16_src, void* x16_dst,
                          const float* rot_src, float* rot_dst,
+                         const void* rot16_src, void* rot16_dst,
                          const int32_t* ind_src, int32_t* ind_dst,
                          int32_t* prune_cnt, void* stream);
 

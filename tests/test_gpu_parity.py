@@ -156,14 +156,15 @@ def test_linear_epilogues(prec):
     xa, ya = x.to(adt), y.to(adt)
     st = _stream()
 
-    def lin(epi, A0, W, b, N, K, A1=None, K0=None, scale=(1., 1., 1.), resid=None, out32=None, out16=None,
-            rot=None, n_rot=0, outp=(None, None, None), gamma=None, beta=None):
+    def lin(epi, A0, W, b, N, K, A1=None, K0=None, scale=(1., 1., 1.), resid=None, resid16=None, out32=None,
+            out16=None, rot=None, rot16=None, n_rot=0, outp=(None, None, None), gamma=None, beta=None):
         rc = lib.lgb200_linear(prec, epi, ptr(A0), ptr(A1), K if K0 is None else K0, ptr(W), ptr(b), T, N, K,
-                               ptr(lens), Lp, scale[0], scale[1], scale[2], ptr(resid), ptr(out32), ptr(out16),
-                               ptr(rot), n_rot, ptr(outp[0]), ptr(outp[1]), ptr(outp[2]), ptr(gamma), ptr(beta), st)
+                               ptr(lens), Lp, scale[0], scale[1], scale[2], ptr(resid), ptr(resid16), ptr(out32),
+                               ptr(out16), ptr(rot), ptr(rot16), n_rot, ptr(outp[0]), ptr(outp[1]), ptr(outp[2]),
+                               ptr(gamma), ptr(beta), st)
         assert rc == 0, lib.lgb200_error_string(rc)
 
-    # ROWMAJOR + scale + residual, K = 512 from two sources
+    # ROWMAJOR + scale + fp32 residual, K = 512 from two sources (bf16: first-generation kernel)
     W = (torch.randn(256, 512, device=DEV) / 16).to(adt)
     b = torch.randn(256, device=DEV)
     resid = torch.randn(T, 256, device=DEV)
@@ -175,14 +176,33 @@ def test_linear_epilogues(prec):
     if bf:
         torch.testing.assert_close(o16[tile_valid].float(), ref[tile_valid], atol=5e-2, rtol=2e-2)
     assert (o32[~tile_valid] == 0).all(), "tiles past lens must be skipped"
+    if bf:
+        # v2 kernel (cluster multicast, TMA-staged epilogue): bf16 residual updated in place, K = 512
+        xr = torch.randn(T, 256, device=DEV).to(adt)
+        x_io = xr.clone()
+        lin(_abi.EPI_ROWMAJOR, xa, W, b, 256, 512, A1=ya, K0=256, resid16=x_io, out16=x_io)
+        ref2 = torch.cat([xa, ya], 1).float() @ W.float().t() + b + xr.float()
+        torch.testing.assert_close(x_io[tile_valid].float(), ref2[tile_valid], atol=6e-2, rtol=2e-2)
+        assert torch.equal(x_io[~tile_valid], xr[~tile_valid])
+        # v2, K = 256, N = 256, scale, no residual (out_proj / final_proj shape)
+        W2 = (torch.randn(256, 256, device=DEV) / 16).to(adt)
+        o2 = torch.zeros(T, 256, device=DEV, dtype=adt)
+        lin(_abi.EPI_ROWMAJOR, xa, W2, b, 256, 256, scale=(0.25, 1, 1), out16=o2)
+        ref3 = (xa.float() @ W2.float().t() + b) * 0.25
+        torch.testing.assert_close(o2[tile_valid].float(), ref3[tile_valid], atol=3e-2, rtol=2e-2)
+        # v2, K = 128 (input_proj shape)
+        xs = torch.randn(T, 128, device=DEV).to(adt)
+        W3 = (torch.randn(256, 128, device=DEV) / 11).to(adt)
+        o3 = torch.zeros(T, 256, device=DEV, dtype=adt)
+        lin(_abi.EPI_ROWMAJOR, xs, W3, b, 256, 128, out16=o3)
+        torch.testing.assert_close(o3[tile_valid].float(), (xs.float() @ W3.float().t() + b)[tile_valid], atol=3e-2, rtol=2e-2)
 
     # HEADS with rotary on parts 0,1 (self-attention QKV)
     W = (torch.randn(768, 256, device=DEV) / 16).to(adt)
     b = torch.randn(768, device=DEV)
     ang = torch.randn(T, 32, device=DEV)
     rot = torch.stack([ang.cos(), ang.sin()], -1).reshape(T, 64).contiguous()
-    outs = [torch.zeros(S, 4, Lp, 64, device=DEV, dtype=adt) for _ in range(3)]
-    lin(_abi.EPI_HEADS, xa, W, b, 768, 256, scale=(0.5, 1.0, 2.0), rot=rot, n_rot=2, outp=outs)
+    rot16 = rot.to(torch.float16).contiguous()  # [T,64] halves = [T,32] packed (cos, sin)
     yref = (xa.float() @ W.float().t() + b).view(S, Lp, 3, 4, 64).permute(2, 0, 3, 1, 4)  # [part,S,h,Lp,64]
     c = ang.cos().repeat_interleave(2, -1).view(S, 1, Lp, 64); s_ = ang.sin().repeat_interleave(2, -1).view(S, 1, Lp, 64)
 
@@ -193,8 +213,18 @@ def test_linear_epilogues(prec):
 
     refs = [rotf(yref[0]) * 0.5, rotf(yref[1]), yref[2] * 2.0]
     tv = tile_valid.view(S, 1, Lp, 1).to(DEV)
-    for o, r in zip(outs, refs):
-        torch.testing.assert_close(torch.where(tv, o.float(), 0), torch.where(tv, r, 0), **tol)
+    variants = [dict(rot=rot)] + ([dict(rot16=rot16)] if bf else [])
+    for kw in variants:
+        outs = [torch.zeros(S, 4, Lp, 64, device=DEV, dtype=adt) for _ in range(3)]
+        lin(_abi.EPI_HEADS, xa, W, b, 768, 256, scale=(0.5, 1.0, 2.0), n_rot=2, outp=outs, **kw)
+        for o, r in zip(outs, refs):
+            torch.testing.assert_close(torch.where(tv, o.float(), 0), torch.where(tv, r, 0), **tol)
+    if bf:  # cross-attention projection shape: N = 512, no rotary
+        Wc = W[:512].contiguous(); bc = b[:512].contiguous()
+        outs = [torch.zeros(S, 4, Lp, 64, device=DEV, dtype=adt) for _ in range(2)]
+        lin(_abi.EPI_HEADS, xa, Wc, bc, 512, 256, scale=(0.5, 2.0, 1.0), n_rot=0, outp=(outs[0], outs[1], None))
+        for o, r in zip(outs, [yref[0] * 0.5, yref[1] * 2.0]):
+            torch.testing.assert_close(torch.where(tv, o.float(), 0), torch.where(tv, r, 0), **tol)
 
     # LN + GELU
     W = (torch.randn(512, 512, device=DEV) / 22).to(adt)
@@ -206,6 +236,7 @@ def test_linear_epilogues(prec):
     pre = torch.cat([xa, ya], 1).float() @ W.float().t() + b
     ref = torch.nn.functional.gelu(torch.nn.functional.layer_norm(pre, (512,), gamma, beta, 1e-5))
     torch.testing.assert_close(h[tile_valid].float(), ref[tile_valid], **tol)
+    assert (h[~tile_valid] == 0).all()
 
 
 @pytest.mark.parametrize("prec", [_abi.F32, _abi.BF16], ids=["fp32", "bf16"])
@@ -252,7 +283,9 @@ def test_posenc_and_rowdot():
     lens = torch.tensor([150, 1, 100, 2, 150, 3], dtype=torch.int32, device=DEV)
     for sz in (size, None):
         rot = torch.zeros(2 * B, Lp, 64, device=DEV)
-        assert lib.lgb200_posenc(ptr(kp), B, n, 2, ptr(sz), ptr(Wr), ptr(lens), 0, Lp, ptr(rot), _stream()) == 0
+        rot16 = torch.zeros(2 * B, Lp, 64, device=DEV, dtype=torch.float16)
+        assert lib.lgb200_posenc(ptr(kp), B, n, 2, ptr(sz), ptr(Wr), ptr(lens), 0, Lp, ptr(rot), ptr(rot16), _stream()) == 0
+        torch.testing.assert_close(rot16.float(), rot, atol=1e-3, rtol=0)
         for b in range(B):
             nv = int(lens[2 * b])
             kk = kp[b, :nv]
@@ -264,8 +297,11 @@ def test_posenc_and_rowdot():
             assert (rot[2 * b, nv:] == 0).all()
     x = torch.randn(2 * B * Lp, 256, device=DEV); w = torch.randn(256, device=DEV); bb = torch.randn(1, device=DEV)
     out = torch.zeros(2 * B * Lp, device=DEV)
-    assert lib.lgb200_rowdot(ptr(x), ptr(w), ptr(bb), 2 * B, Lp, None, 1, ptr(out), _stream()) == 0
+    assert lib.lgb200_rowdot(_abi.F32, ptr(x), ptr(w), ptr(bb), 2 * B, Lp, None, 1, ptr(out), _stream()) == 0
     torch.testing.assert_close(out, torch.sigmoid(x @ w + bb), atol=1e-5, rtol=1e-5)
+    xb = x.to(torch.bfloat16)
+    assert lib.lgb200_rowdot(_abi.BF16, ptr(xb), ptr(w), ptr(bb), 2 * B, Lp, None, 0, ptr(out), _stream()) == 0
+    torch.testing.assert_close(out, xb.float() @ w + bb, atol=1e-4, rtol=1e-4)
 
 
 @pytest.mark.parametrize("prec", [_abi.F32, _abi.BF16], ids=["fp32", "bf16"])
