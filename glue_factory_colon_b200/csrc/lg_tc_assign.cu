@@ -94,26 +94,29 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::idesc_bf16(128, 128, 0);
-      const uint32_t aA = tc::smem_u32(sA);
-      tc::mbar_wait(a_full, 0);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        tc::mbar_wait(&b_full[st], ph);
-        tc::mbar_wait(&s_empty[st], ph ^ 1);
-        tc::fence_after_sync();
-        const uint32_t aB = tc::smem_u32(sB + st * AS_OPER);
+    // whole warp, warp-uniform control flow, one elected lane issues (descriptors stay in uniform registers)
+    constexpr uint32_t idesc = tc::idesc_bf16(128, 128, 0);
+    const uint64_t dA = tc::smem_desc_sw128(tc::smem_u32(sA), 0, 1024);
+    const uint64_t dB0 = tc::smem_desc_sw128(tc::smem_u32(sB), 0, 1024);
+    tc::mbar_wait(a_full, 0);
+    for (int j = 0; j < n_tiles; ++j) {
+      const int st = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      tc::mbar_wait(&b_full[st], ph);
+      tc::mbar_wait(&s_empty[st], ph ^ 1);
+      tc::fence_after_sync();
+      const uint64_t dB = dB0 + (uint64_t)(st * (AS_OPER >> 4));
+      if (tc::elect_one()) {
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            tc::umma_ss(tmem + st * 128, tc::smem_desc_sw128(aA + kb * AS_TILE + k * 32, 0, 1024),
-                        tc::smem_desc_sw128(aB + kb * AS_TILE + k * 32, 0, 1024), idesc, (kb | k) != 0);
+            tc::umma_ss(tmem + st * 128, dA + kb * (AS_TILE >> 4) + 2 * k, dB + kb * (AS_TILE >> 4) + 2 * k, idesc,
+                        (kb | k) != 0);
         tc::umma_commit(&s_full[st]);
         tc::umma_commit(&b_empty[st]);
       }
+      __syncwarp();
     }
   } else {
     const int quarter = warp & 3;

@@ -2,9 +2,11 @@
 //
 // One CTA = 128 query rows of one (sequence, head).  Two CTAs are resident per SM (80 KB smem,
 // 256 TMEM columns each) so that one CTA's softmax overlaps the other's MMAs.
-//   warp 0     TMA producer: Q once, then K/V tiles of 128 keys into a 2-stage ring
+//   warp 0     TMA producer: Q once, then K and V tiles of 128 keys into two independent 3-stage rings
+//              (a K stage is released as soon as its QK^T retires, so K runs ~3 tiles ahead; with the
+//              first 2-stage K/V ring the ~2 us TMA latency was exposed on every step: 2830 cycles/step)
 //   warp 1     MMA issuer:   S = Q.K^T (SS, N=128) into TMEM, O += P.V (TS: P read from TMEM, V MN-major)
-//   warps 2-5  softmax:      thread = query row.  tcgen05.ld S -> registers, online max with lazy
+//   warps 2-9  softmax:      two threads per query row (64 key columns each).  tcgen05.ld S -> registers, online max with lazy
 //                            rescale (O is only touched when the max grows by > 8 in log2 units),
 //                            ex2, row sum, bf16 P written back to TMEM with tcgen05.st
 // Issue order QK(j+1) before PV(j): the next score tile is produced while the softmax warps are
@@ -14,13 +16,18 @@
 // Keys >= lens[kv sequence] are masked to -inf; query rows >= lens[q sequence] are not stored.
 #include "lg_internal.cuh"
 #include "lg_tc_common.cuh"
+#include <stdlib.h>
+
+// debug timeline (clock64 stamps of CTA (0,0,0); read back with lgb200_debug_attn_times)
+__device__ long long g_attn_times[2 * 16 * 16];
 
 namespace {
 
 constexpr int AT_BM = 128;   // queries per CTA
 constexpr int AT_BN = 128;   // keys per step
 constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16, 128B-swizzled
-constexpr int AT_SMEM = TILE_BYTES * 5 + 1024 + 128;
+constexpr int KST = 3, VST = 2;            // K / V ring depth
+constexpr int AT_SMEM = TILE_BYTES * (1 + KST + VST) + 192 + 6 * 128 * 4;  // + max/sum exchange
 
 constexpr uint32_t TM_S = 0, TM_P = 128, TM_O = 192, TM_COLS = 256;
 
@@ -30,20 +37,27 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(192, 2)
+template <int CL>
+__global__ void __launch_bounds__(320, 2)
 tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, int Lp, const int32_t* __restrict__ lens,
-                    int kv_xor, __nv_bfloat16* __restrict__ ctx) {
+                    int kv_xor, __nv_bfloat16* __restrict__ ctx, int dbg) {
+  // CL CTAs with consecutive query tiles of the same (sequence, head) form a cluster and share every
+  // K/V tile: each loads 1/CL of it and TMA-multicasts it to the others.  (Measured: with one CTA per
+  // K/V tile the kernel sat at ~5 TB/s of L2->SM traffic regardless of MUFU / pipelining changes.)
+  constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
+  constexpr int SLICE = AT_BN / CL;  // K/V rows this CTA loads per tile
+  const uint32_t crank = CL > 1 ? tc::cluster_ctarank() : 0;
   const int s = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AT_BM;
   const int nq = lens ? lens[s] : Lp;
-  if (q0 >= nq) return;
+  if ((int)(blockIdx.x - crank) * AT_BM >= nq) return;  // whole cluster is past the valid rows
   const int skv = s ^ kv_xor;
   const int nk = lens ? lens[skv] : Lp;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (nk + AT_BN - 1) / AT_BN;
 
   if (n_tiles == 0) {  // no keys: attention output is defined as zero (nan_to_num)
-    if (warp >= 2) {
+    if (warp >= 2 && warp < 6) {  // (uniform across the cluster: no barrier was touched yet)
       const int r = (warp & 3) * 32 + lane;
       if (q0 + r < nq) {
         uint4* dst = reinterpret_cast<uint4*>(ctx + ((size_t)s * Lp + q0 + r) * LG_D + h * LG_DH);
@@ -54,36 +68,41 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     return;
   }
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((tc::smem_u32(smem) & 1023u) != 0) __trap();  // swizzled tiles need a 1024-byte aligned base
   uint8_t* sQ = smem;
-  uint8_t* sK = smem + TILE_BYTES;       // 2 stages
-  uint8_t* sV = smem + 3 * TILE_BYTES;   // 2 stages
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * TILE_BYTES);
+  uint8_t* sK = smem + TILE_BYTES;              // KST stages
+  uint8_t* sV = smem + (1 + KST) * TILE_BYTES;  // VST stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (1 + KST + VST) * TILE_BYTES);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* s_free = bars + 6;
-  uint64_t* p_ready = bars + 7;
-  uint64_t* pv_done = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* k_full = bars + 1;             // [KST]
+  uint64_t* k_empty = k_full + KST;        // [KST]
+  uint64_t* v_full = k_empty + KST;        // [VST]
+  uint64_t* v_empty = v_full + VST;        // [VST]
+  uint64_t* s_full = v_empty + VST;
+  uint64_t* s_free = s_full + 1;
+  uint64_t* p_ready = s_free + 1;
+  uint64_t* pv_done = p_ready + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+  float* s_xch = reinterpret_cast<float*>(smem + (1 + KST + VST) * TILE_BYTES + 192);  // [6][128]
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmQ);
     tc::prefetch_tmap(&tmK);
     tc::prefetch_tmap(&tmV);
     tc::mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&kv_full[i], 1); tc::mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < KST; ++i) { tc::mbar_init(&k_full[i], 1); tc::mbar_init(&k_empty[i], CL); }
+    for (int i = 0; i < VST; ++i) { tc::mbar_init(&v_full[i], 1); tc::mbar_init(&v_empty[i], CL); }
     tc::mbar_init(s_full, 1);
-    tc::mbar_init(s_free, 4);
-    tc::mbar_init(p_ready, 4);
+    tc::mbar_init(s_free, 8);
+    tc::mbar_init(p_ready, 8);
     tc::mbar_init(pv_done, 1);
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, TM_COLS);
   tc::fence_before_sync();
   __syncthreads();
+  if (CL > 1) tc::cluster_sync();  // peers' barriers exist before anyone multicasts into them
   tc::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
 
@@ -94,124 +113,186 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tc::mbar_arrive_expect_tx(q_full, TILE_BYTES);
       tc::tma_load_2d(sQ, &tmQ, q_full, 0, qrow);
       for (int j = 0; j < n_tiles; ++j) {
-        const int st = j & 1;
-        tc::mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
-        tc::mbar_arrive_expect_tx(&kv_full[st], 2 * TILE_BYTES);
-        tc::tma_load_2d(sK + st * TILE_BYTES, &tmK, &kv_full[st], 0, kvrow + j * AT_BN);
-        tc::tma_load_2d(sV + st * TILE_BYTES, &tmV, &kv_full[st], 0, kvrow + j * AT_BN);
+        const int ks = j % KST, vs = j % VST;
+        const int row = kvrow + j * AT_BN + (int)crank * SLICE;
+        const int off = (int)crank * SLICE * 128;
+        tc::mbar_wait(&k_empty[ks], ((j / KST) & 1) ^ 1);  // every CTA of the cluster released the stage
+        tc::mbar_arrive_expect_tx(&k_full[ks], TILE_BYTES);
+        if (CL > 1) tc::tma_load_2d_mc(sK + ks * TILE_BYTES + off, &tmK, &k_full[ks], 0, row, MC_MASK);
+        else tc::tma_load_2d(sK + ks * TILE_BYTES, &tmK, &k_full[ks], 0, row);
+        tc::mbar_wait(&v_empty[vs], ((j / VST) & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(&v_full[vs], TILE_BYTES);
+        if (CL > 1) tc::tma_load_2d_mc(sV + vs * TILE_BYTES + off, &tmV, &v_full[vs], 0, row, MC_MASK);
+        else tc::tma_load_2d(sV + vs * TILE_BYTES, &tmV, &v_full[vs], 0, row);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = tc::idesc_bf16(128, 128, 0);
-      constexpr uint32_t idesc_pv = tc::idesc_bf16(128, 64, 1);
-      const uint32_t aQ = tc::smem_u32(sQ);
-      auto issue_qk = [&](int j) {
-        const uint32_t aK = tc::smem_u32(sK + (j & 1) * TILE_BYTES);
+    // MMA issuer.  The WHOLE warp runs this loop with warp-uniform control flow and one elected lane
+    // issues: descriptors and barrier addresses then live in uniform registers.  (The first version
+    // ran the loop on lane 0 only; every tcgen05.mma needed R2UR moves and cost ~100 issue cycles,
+    // 1190 of the 1730 cycles of a step.)
+    constexpr uint32_t idesc_qk = tc::idesc_bf16(128, 128, 0);
+    constexpr uint32_t idesc_pv = tc::idesc_bf16(128, 64, 1);
+    const uint64_t dQ = tc::smem_desc_sw128(tc::smem_u32(sQ), 0, 1024);
+    const uint64_t dK0 = tc::smem_desc_sw128(tc::smem_u32(sK), 0, 1024);
+    const uint64_t dV0 = tc::smem_desc_sw128(tc::smem_u32(sV), TILE_BYTES, 1024);
+    const uint32_t tS = tmem + TM_S, tP = tmem + TM_P, tO = tmem + TM_O;
+    int ks = 0, vs = 0;            // ring positions of the next K tile to multiply / V tile to consume
+    uint32_t kph = 0, vph = 0;
+    auto issue_qk = [&]() {        // S = Q . K[ks]^T
+      const uint64_t dK = dK0 + (uint64_t)(ks * (TILE_BYTES >> 4));
+      if (tc::elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          tc::umma_ss(tmem + TM_S, tc::smem_desc_sw128(aQ + k * 32, 0, 1024),
-                      tc::smem_desc_sw128(aK + k * 32, 0, 1024), idesc_qk, k != 0);
+          if (dbg != 6) tc::umma_ss(tS, dQ + 2 * k, dK + 2 * k, idesc_qk, k != 0);
         tc::umma_commit(s_full);
-      };
-      tc::mbar_wait(q_full, 0);
-      tc::mbar_wait(&kv_full[0], 0);
-      tc::fence_after_sync();
-      issue_qk(0);
-      for (int j = 0; j < n_tiles; ++j) {
-        if (j + 1 < n_tiles) {
-          tc::mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
-          tc::mbar_wait(s_free, j & 1);  // softmax holds S(j) in registers
-          tc::fence_after_sync();
-          issue_qk(j + 1);
-        }
-        tc::mbar_wait(p_ready, j & 1);
+        if (CL > 1) tc::umma_commit_mc(&k_empty[ks], MC_MASK);  // K stage free once this QK^T retires
+        else tc::umma_commit(&k_empty[ks]);
+      }
+      __syncwarp();
+      if (++ks == KST) { ks = 0; kph ^= 1; }
+    };
+    tc::mbar_wait(q_full, 0);
+    tc::mbar_wait(&k_full[0], 0);
+    tc::fence_after_sync();
+    issue_qk();
+    const bool recm = dbg == 7 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+#define MSTAMP(k) do { if (recm && j < 16) g_attn_times[256 + (j * 16) + (k)] = clock64(); } while (0)
+    for (int j = 0; j < n_tiles; ++j) {
+      MSTAMP(0);
+      if (j + 1 < n_tiles) {
+        tc::mbar_wait(&k_full[ks], kph);
+        MSTAMP(1);
+        tc::mbar_wait(s_free, j & 1);  // softmax holds S(j) in registers
         tc::fence_after_sync();
-        const uint32_t aV = tc::smem_u32(sV + (j & 1) * TILE_BYTES);
+        MSTAMP(2);
+        issue_qk();
+        MSTAMP(3);
+      }
+      tc::mbar_wait(&v_full[vs], vph);
+      tc::mbar_wait(p_ready, j & 1);
+      tc::fence_after_sync();
+      MSTAMP(4);
+      const uint64_t dV = dV0 + (uint64_t)(vs * (TILE_BYTES >> 4));
+      if (tc::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < AT_BN / 16; ++k)  // 16 keys per MMA: P columns k*8.., V rows k*16..
-          tc::umma_ts(tmem + TM_O, tmem + TM_P + k * 8, tc::smem_desc_sw128(aV + k * 2048, TILE_BYTES, 1024),
-                      idesc_pv, (j | k) != 0);
-        tc::umma_commit(&kv_empty[j & 1]);
+        for (int k = 0; k < AT_BN / 16; ++k)  // 16 keys per MMA: P columns k*8.., V rows k*16.. (2048 B)
+          if (dbg != 5) tc::umma_ts(tO, tP + k * 8, dV + k * (2048 >> 4), idesc_pv, (j | k) != 0);
+        if (CL > 1) tc::umma_commit_mc(&v_empty[vs], MC_MASK);
+        else tc::umma_commit(&v_empty[vs]);
         tc::umma_commit(pv_done);
       }
+      __syncwarp();
+      if (++vs == VST) { vs = 0; vph ^= 1; }
+      MSTAMP(5);
     }
   } else {
+    // softmax: 8 warps, two threads per query row.  Warp (quarter, half) owns TMEM lanes
+    // quarter*32.. and key columns half*64..+64 of the score tile; the two threads of a row
+    // exchange their partial row maximum through shared memory (named barrier per quarter).
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    float m_ref = -INFINITY, l_sum = 0.f;
+    float m_ref = -INFINITY, l_part = 0.f;
+    const bool rec = dbg == 7 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0;
+#define STAMP(k) do { if (rec && j < 16) g_attn_times[(j * 16) + (k)] = clock64(); } while (0)
     for (int j = 0; j < n_tiles; ++j) {
+      STAMP(0);
       tc::mbar_wait(s_full, j & 1);
       tc::fence_after_sync();
-      uint32_t sv[128];
-      tc::tmem_ld32(tmem + lane_base + TM_S + 0, sv + 0);
-      tc::tmem_ld32(tmem + lane_base + TM_S + 32, sv + 32);
-      tc::tmem_ld32(tmem + lane_base + TM_S + 64, sv + 64);
-      tc::tmem_ld32(tmem + lane_base + TM_S + 96, sv + 96);
+      STAMP(1);
+      uint32_t sv[64];
+      tc::tmem_ld32(tmem + lane_base + TM_S + half * 64, sv);
+      tc::tmem_ld32(tmem + lane_base + TM_S + half * 64 + 32, sv + 32);
       tc::tmem_ld_wait();
+      STAMP(2);
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(s_free);
-      const int valid = nk - j * AT_BN;  // >= 1
-      float mx = -INFINITY;
-      if (valid < AT_BN) {
+      STAMP(3);
+      const int valid = nk - j * AT_BN - half * 64;  // valid keys among this thread's 64 columns
+      if (valid < 64) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i) {
+        for (int i = 0; i < 64; ++i) {
           if (i >= valid) sv[i] = 0xff800000u;  // -inf
         }
       }
+      if (dbg >= 4 && dbg <= 6) {  // pipeline skeleton only: no softmax math
+        uint32_t pz[32];
 #pragma unroll
-      for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+        for (int i = 0; i < 32; ++i) pz[i] = sv[i] & 0x3f803f80u;
+        if (j > 0) { tc::mbar_wait(pv_done, (j - 1) & 1); tc::fence_after_sync(); }
+        tc::tmem_st32(tmem + lane_base + TM_P + half * 32, pz);
+        tc::tmem_st_wait();
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(p_ready);
+        l_part = 1.f;
+        continue;
+      }
+      float mxs[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mxs[i] = __uint_as_float(sv[i]);
+#pragma unroll
+      for (int i = 4; i < 64; ++i) mxs[i & 3] = fmaxf(mxs[i & 3], __uint_as_float(sv[i]));
+      float mx = fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3]));
+      s_xch[((j & 1) * 2 + half) * 128 + r] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+      mx = fmaxf(mx, s_xch[((j & 1) * 2 + (half ^ 1)) * 128 + r]);
+      STAMP(4);
       // lazy rescale: keep the reference max unless it grows by more than 8 (factor 256)
       float m_new = m_ref;
       if (mx > m_ref + 8.f) m_new = mx;
       const float alpha = ex2(m_ref - m_new);  // 1 when unchanged, 0 on the first tile
-      float rs = 0.f;
-      uint32_t pk[64];
+      float rsum[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t pk[32];
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        const float p0 = ex2(__uint_as_float(sv[2 * i]) - m_new);
-        const float p1 = ex2(__uint_as_float(sv[2 * i + 1]) - m_new);
-        rs += p0 + p1;
+      for (int i = 0; i < 32; ++i) {
+        float p0 = __uint_as_float(sv[2 * i]) - m_new, p1 = __uint_as_float(sv[2 * i + 1]) - m_new;
+        if (dbg == 1) { p0 = p0 * p0; p1 = p1 * p1; } else { p0 = ex2(p0); p1 = ex2(p1); }
+        rsum[i & 3] += p0 + p1;
         pk[i] = tc::pack_bf16(p0, p1);
       }
-      l_sum = l_sum * alpha + rs;
+      l_part = l_part * alpha + ((rsum[0] + rsum[1]) + (rsum[2] + rsum[3]));
+      STAMP(5);
       if (j > 0) {
         tc::mbar_wait(pv_done, (j - 1) & 1);  // PV(j-1) retired: P is free, O is up to date
         tc::fence_after_sync();
+        STAMP(6);
         const bool need = m_new != m_ref;
-        if (__any_sync(0xffffffffu, need)) {
+        if (__any_sync(0xffffffffu, need)) {  // same rows in both half-warps -> same decision
           uint32_t o[32];
+          tc::tmem_ld32(tmem + lane_base + TM_O + half * 32, o);
+          tc::tmem_ld_wait();
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            tc::tmem_ld32(tmem + lane_base + TM_O + half * 32, o);
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tc::tmem_st32(tmem + lane_base + TM_O + half * 32, o);
-          }
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tc::tmem_st32(tmem + lane_base + TM_O + half * 32, o);
         }
       }
       m_ref = m_new;
-      tc::tmem_st32(tmem + lane_base + TM_P + 0, pk + 0);
-      tc::tmem_st32(tmem + lane_base + TM_P + 32, pk + 32);
+      tc::tmem_st32(tmem + lane_base + TM_P + half * 32, pk);
       tc::tmem_st_wait();
+      STAMP(7);
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(p_ready);
+      STAMP(8);
     }
+    // combine the two partial row sums, normalise this thread's 32 output columns
+    s_xch[(4 + half) * 128 + r] = l_part;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+    const float l_sum = l_part + s_xch[(4 + (half ^ 1)) * 128 + r];
     tc::mbar_wait(pv_done, (n_tiles - 1) & 1);
     tc::fence_after_sync();
     const float inv = l_sum > 0.f ? 1.f / l_sum : 0.f;
-    uint32_t o[64];
-    tc::tmem_ld32(tmem + lane_base + TM_O + 0, o);
-    tc::tmem_ld32(tmem + lane_base + TM_O + 32, o + 32);
+    uint32_t o[32];
+    tc::tmem_ld32(tmem + lane_base + TM_O + half * 32, o);
     tc::tmem_ld_wait();
     if (q0 + r < nq) {
-      uint4* dst = reinterpret_cast<uint4*>(ctx + ((size_t)s * Lp + q0 + r) * LG_D + h * LG_DH);
+      uint4* dst = reinterpret_cast<uint4*>(ctx + ((size_t)s * Lp + q0 + r) * LG_D + h * LG_DH + half * 32);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         uint4 w;
         w.x = tc::pack_bf16(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
         w.y = tc::pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
@@ -223,6 +304,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
   tc::fence_before_sync();
   __syncthreads();
+  if (CL > 1) tc::cluster_sync();  // nobody retires while a peer may still multicast into its smem
   if (warp == 1) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem, TM_COLS);
@@ -231,19 +313,53 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
 }  // namespace
 
-int lg_tc_attention(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* V, int S, int Lp,
-                    const int32_t* lens, int kv_xor, __nv_bfloat16* ctx, cudaStream_t st) {
+template <int CL>
+static int launch_attention(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* V, int S, int Lp,
+                            const int32_t* lens, int kv_xor, __nv_bfloat16* ctx, int dbg, cudaStream_t st) {
   CUtensorMap tq, tk, tv;
   const uint64_t d[2] = {64, (uint64_t)S * LG_HEADS * Lp}, sb[1] = {128};
-  const uint32_t box[2] = {64, 128};
+  const uint32_t box[2] = {64, 128}, box_kv[2] = {64, 128 / CL};
   int rc;
   if ((rc = lg_make_tmap_bf16(&tq, Q, 2, d, sb, box))) return rc;
-  if ((rc = lg_make_tmap_bf16(&tk, K, 2, d, sb, box))) return rc;
-  if ((rc = lg_make_tmap_bf16(&tv, V, 2, d, sb, box))) return rc;
-  cudaError_t e = cudaFuncSetAttribute(tc_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+  if ((rc = lg_make_tmap_bf16(&tk, K, 2, d, sb, box_kv))) return rc;
+  if ((rc = lg_make_tmap_bf16(&tv, V, 2, d, sb, box_kv))) return rc;
+  auto kern = tc_attention_kernel<CL>;
+  const int smem = dbg == 3 ? 120 * 1024 : AT_SMEM;  // dbg 3: one CTA per SM
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
-  dim3 grid(Lp / AT_BM, LG_HEADS, S);
-  tc_attention_kernel<<<grid, 192, AT_SMEM, st>>>(tq, tk, tv, Lp, lens, kv_xor, ctx);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(Lp / AT_BM, LG_HEADS, S);
+  cfg.blockDim = dim3(320);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, tq, tk, tv, Lp, lens, kv_xor, ctx, dbg);
+  if (e != cudaSuccess) return (int)e;
   LG_LAUNCH_CHECK();
   return LGB200_OK;
+}
+
+int lg_tc_attention(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* V, int S, int Lp,
+                    const int32_t* lens, int kv_xor, __nv_bfloat16* ctx, cudaStream_t st) {
+  static const int dbg = getenv("LGB200_ATTN_DBG") ? atoi(getenv("LGB200_ATTN_DBG")) : 0;
+  static const int force_cl = getenv("LGB200_ATTN_CL") ? atoi(getenv("LGB200_ATTN_CL")) : 0;
+  const int qt = Lp / AT_BM;
+  // Measured at S=128, Lp=2048: CL=1 0.84 ms, CL=2 0.87 ms, CL=4 0.93 ms -- the kernel is bound by the
+  // softmax/MUFU side, not by L2->SM traffic, so K/V multicast stays opt-in (LGB200_ATTN_CL=2|4).
+  int cl = 1;
+  if (force_cl == 1 || force_cl == 2 || force_cl == 4) cl = (qt % force_cl == 0) ? force_cl : 1;
+  if (cl == 4) return launch_attention<4>(Q, K, V, S, Lp, lens, kv_xor, ctx, dbg, st);
+  if (cl == 2) return launch_attention<2>(Q, K, V, S, Lp, lens, kv_xor, ctx, dbg, st);
+  return launch_attention<1>(Q, K, V, S, Lp, lens, kv_xor, ctx, dbg, st);
+}
+
+extern "C" int lgb200_debug_attn_times(long long* host_out, int n) {
+  if (n > 512) n = 512;
+  return (int)cudaMemcpyFromSymbol(host_out, g_attn_times, sizeof(long long) * n);
 }

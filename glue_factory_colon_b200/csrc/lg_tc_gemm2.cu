@@ -210,56 +210,65 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Producer and MMA warps run their loops with warp-uniform control flow (all 32 lanes wait on the
+  // barriers, one elected lane issues the TMA / tcgen05 instruction): addresses and descriptors then
+  // stay in uniform registers.  Running the loop on lane 0 alone cost ~100 issue cycles per
+  // tcgen05.mma (R2UR traffic), more than the 64 cycles the MMA itself takes.
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (tc::elect_one()) {
       tc::mbar_arrive_expect_tx(w_full, g.kb_total * WB_BYTES);
       for (int kb = 0; kb < g.kb_total; ++kb) tc::tma_load_2d(sW + kb * WB_BYTES, &maps.w, w_full, kb * BK, n0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int mt = m_first; mt < g.m_tiles; mt += m_step) {
-        if (tile_skipped(g, mt)) continue;
-        for (int kb = 0; kb < g.kb_total; ++kb) {
-          tc::mbar_wait(&empty[stage], phase ^ 1);  // all CL consumers released this stage
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int mt = m_first; mt < g.m_tiles; mt += m_step) {
+      if (tile_skipped(g, mt)) continue;
+      const int row = mt * BM + crank * SLICE_ROWS;
+      for (int kb = 0; kb < g.kb_total; ++kb) {
+        tc::mbar_wait(&empty[stage], phase ^ 1);  // all CL consumers released this stage
+        uint8_t* dst = sA + stage * A_STAGE + crank * (SLICE_ROWS * 128);
+        const CUtensorMap* tm = kb < g.kb_a0 ? &maps.a0 : &maps.a1;
+        const int kc = (kb < g.kb_a0 ? kb : kb - g.kb_a0) * BK;
+        if (tc::elect_one()) {
           tc::mbar_arrive_expect_tx(&full[stage], A_STAGE);
-          uint8_t* dst = sA + stage * A_STAGE + crank * (SLICE_ROWS * 128);
-          const CUtensorMap* tm = kb < g.kb_a0 ? &maps.a0 : &maps.a1;
-          const int kc = (kb < g.kb_a0 ? kb : kb - g.kb_a0) * BK;
-          const int row = mt * BM + crank * SLICE_ROWS;
           if (CL > 1) tma_load_2d_mc(dst, tm, &full[stage], kc, row, MC_MASK);
           else tc::tma_load_2d(dst, tm, &full[stage], kc, row);
-          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::idesc_bf16(BM, BN, 0);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      tc::mbar_wait(w_full, 0);
-      const uint32_t aW = tc::smem_u32(sW);
-      for (int mt = m_first; mt < g.m_tiles; mt += m_step) {
-        if (tile_skipped(g, mt)) continue;
-        tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
+    constexpr uint32_t idesc = tc::idesc_bf16(BM, BN, 0);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    tc::mbar_wait(w_full, 0);
+    const uint64_t dW0 = tc::smem_desc_sw128(tc::smem_u32(sW), 0, 1024);
+    const uint64_t dA0 = tc::smem_desc_sw128(tc::smem_u32(sA), 0, 1024);
+    for (int mt = m_first; mt < g.m_tiles; mt += m_step) {
+      if (tile_skipped(g, mt)) continue;
+      tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc::fence_after_sync();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < g.kb_total; ++kb) {
+        tc::mbar_wait(&full[stage], phase);
         tc::fence_after_sync();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < g.kb_total; ++kb) {
-          tc::mbar_wait(&full[stage], phase);
-          tc::fence_after_sync();
-          const uint32_t aA = tc::smem_u32(sA + stage * A_STAGE);
+        const uint64_t dA = dA0 + (uint64_t)(stage * (A_STAGE >> 4));
+        const uint64_t dW = dW0 + (uint64_t)(kb * (WB_BYTES >> 4));
+        if (tc::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            tc::umma_ss(d_tmem, tc::smem_desc_sw128(aA + k * 32, 0, 1024),
-                        tc::smem_desc_sw128(aW + kb * WB_BYTES + k * 32, 0, 1024), idesc, (kb | k) != 0);
+          for (int k = 0; k < BK / 16; ++k) tc::umma_ss(d_tmem, dA + 2 * k, dW + 2 * k, idesc, (kb | k) != 0);
           if (CL > 1) umma_commit_mc(&empty[stage], MC_MASK);
           else tc::umma_commit(&empty[stage]);
-          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          if (kb == g.kb_total - 1) tc::umma_commit(&tfull[acc]);
         }
-        tc::umma_commit(&tfull[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps)
