@@ -279,8 +279,11 @@ def run_gpu_arm(args):
 
     # ---- result gather (NCCL, outside the timed region) ----
     if world > 1:
-        gathered = [torch.empty_like(out["matches0"]) for _ in range(world)] if rank == 0 else None
-        dist.gather(out["matches0"], gathered, dst=0)
+        from glue_factory_colon_b200.shard import gather_to_rank0
+
+        gathered = gather_to_rank0(out["matches0"], [B] * world)
+        if rank == 0:
+            assert gathered.shape[0] == world * B
 
     if rank == 0:
         peaks = load_peaks()
