@@ -12,7 +12,7 @@ LIB_PATH = Path(__file__).resolve().parent / "lib" / "liblightglue_b200.so"
 
 F32, BF16 = 0, 1
 EPI_ROWMAJOR, EPI_HEADS, EPI_LN_GELU = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _p, _i, _f = C.c_void_p, C.c_int, C.c_float
 
@@ -27,8 +27,8 @@ SIGNATURES = {
     "lgb200_attention": [_i, _p, _p, _p, _i, _i, _p, _i, _p, _p],
     "lgb200_rowdot": [_i, _p, _p, _p, _i, _i, _p, _i, _p, _p],
     "lgb200_assign_lse": [_i, _p, _i, _i, _p, _p, _p],
-    "lgb200_assign_scores": [_i, _p, _p, _p, _i, _i, _p, _i, _i, _p, _p],
-    "lgb200_filter_matches": [_p, _i, _i, _i, _p, _f, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p],
+    "lgb200_assign_scores": [_i, _p, _p, _p, _i, _i, _p, _i, _i, _p, _p, _p],
+    "lgb200_filter_matches": [_p, _i, _i, _i, _p, _f, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p],
     "lgb200_exit_check": [_p, _i, _i, _p, _p, _f, _f, _i, _p, _p, _p],
     "lgb200_prune_compact": [_p, _p, _f, _f, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
 }

@@ -95,14 +95,16 @@ extern "C" int lgb200_assign_lse(int precision, const void* md, int S, int Lp, c
 
 extern "C" int lgb200_assign_scores(int precision, const void* md, const float* z, const float* lse,
                                     int B, int Lp, const int32_t* lens, int R, int C, float* scores,
-                                    void* stream) {
+                                    void* best_ws, void* stream) {
   if (!md || !z || !lse || !scores) return LGB200_ERR_NULL;
   if (B <= 0 || Lp <= 0 || Lp % 128 || R < 1 || C < 1 || R - 1 > Lp || C - 1 > Lp)
     return LGB200_ERR_SHAPE;
   cudaStream_t st = lg_stream(stream);
-  if (precision == LGB200_F32)
+  if (precision == LGB200_F32) {
+    if (best_ws) return LGB200_ERR_PRECISION;  // the fused argmax exists in the tcgen05 kernel only
     return lg_simt_assign_scores((const float*)md, z, lse, B, Lp, lens, R, C, scores, st);
+  }
   if (precision == LGB200_BF16)
-    return lg_tc_assign_scores((const __nv_bfloat16*)md, z, lse, B, Lp, lens, R, C, scores, st);
+    return lg_tc_assign_scores((const __nv_bfloat16*)md, z, lse, B, Lp, lens, R, C, scores, best_ws, st);
   return LGB200_ERR_PRECISION;
 }

@@ -34,6 +34,25 @@ __device__ __forceinline__ float lg_gelu_erf(float x) {
   return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
 }
 
+// filter_matches: (value, index) packed so that a 64-bit max picks the largest value and, among equal
+// values, the LOWEST index (torch.max tie rule); NaN sorts above everything (torch.max propagates NaN).
+__device__ __forceinline__ unsigned long long fm_pack(float v, int idx) {
+  const unsigned u = __float_as_uint(v);
+  unsigned key;
+  if (v != v) key = 0xffffffffu;
+  else key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ((unsigned long long)key << 32) | (unsigned)(0xffffffffu - (unsigned)idx);
+}
+__device__ __forceinline__ float fm_value(unsigned long long p) {
+  const unsigned key = (unsigned)(p >> 32);
+  if (key == 0xffffffffu) return __uint_as_float(0x7fc00000u);
+  const unsigned u = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ int fm_index(unsigned long long p) {
+  return (int)(0xffffffffu - (unsigned)(p & 0xffffffffu));
+}
+
 // Epilogue description shared by the fp32 (CUDA-core) and bf16 (tcgen05) GEMMs.
 struct LgEpi {
   int mode;  // LGB200_EPI_*

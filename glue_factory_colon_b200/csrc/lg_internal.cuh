@@ -23,4 +23,4 @@ int lg_tc_attention(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_b
 int lg_tc_assign_lse(const __nv_bfloat16* md, int S, int Lp, const int32_t* lens, float* lse,
                      cudaStream_t st);
 int lg_tc_assign_scores(const __nv_bfloat16* md, const float* z, const float* lse, int B, int Lp,
-                        const int32_t* lens, int R, int C, float* scores, cudaStream_t st);
+                        const int32_t* lens, int R, int C, float* scores, void* best_ws, cudaStream_t st);

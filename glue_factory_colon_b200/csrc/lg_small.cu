@@ -350,23 +350,8 @@ extern "C" int lgb200_prune_compact(const float* match, const float* conf, float
 // (ordered value << 32 | ~index), which also resolves ties to the lowest index.
 // Pass B does the mutual check, exp, threshold and scatter.
 
-__device__ __forceinline__ unsigned long long fm_pack(float v, int idx) {
-  unsigned u = __float_as_uint(v);
-  unsigned key;
-  if (v != v) key = 0xffffffffu;                    // NaN is the maximum (torch.max)
-  else key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-  if (key == 0xffffffffu && v == v) key = 0xfffffffeu;  // keep NaN strictly above everything
-  return ((unsigned long long)key << 32) | (unsigned)(0xffffffffu - (unsigned)idx);
-}
-__device__ __forceinline__ float fm_value(unsigned long long p) {
-  const unsigned key = (unsigned)(p >> 32);
-  if (key == 0xffffffffu) return __uint_as_float(0x7fc00000u);
-  const unsigned u = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
-  return __uint_as_float(u);
-}
-__device__ __forceinline__ int fm_index(unsigned long long p) {
-  return (int)(0xffffffffu - (unsigned)(p & 0xffffffffu));
-}
+// (fm_pack / fm_value / fm_index live in lg_common.cuh: the bf16 assignment kernel produces the same
+// packed maxima in its epilogue so that this pass can be skipped.)
 
 #define FM_ROWS 32
 __global__ void __launch_bounds__(256) fm_argmax_kernel(const float* __restrict__ scores, int R, int C,
@@ -474,7 +459,8 @@ __global__ void fm_mutual_kernel(int R, int C, const int32_t* __restrict__ lens,
 extern "C" int lgb200_filter_matches(const float* scores, int B, int R, int C, const int32_t* lens,
                                      float threshold, const int32_t* ind0, const int32_t* ind1,
                                      int ind_ld, int N0, int N1, int64_t* m0, int64_t* m1,
-                                     float* ms0, float* ms1, void* workspace, void* stream) {
+                                     float* ms0, float* ms1, void* workspace, int workspace_has_best,
+                                     void* stream) {
   if (B <= 0 || R < 1 || C < 1 || N0 < 0 || N1 < 0) return LGB200_ERR_SHAPE;
   if ((N0 > 0 && (!m0 || !ms0)) || (N1 > 0 && (!m1 || !ms1))) return LGB200_ERR_NULL;
   cudaStream_t st = lg_stream(stream);
@@ -485,14 +471,16 @@ extern "C" int lgb200_filter_matches(const float* scores, int B, int R, int C, c
     LG_LAUNCH_CHECK();
   }
   if (R == 1 || C == 1) return LGB200_OK;  // empty side
-  if (!scores || !workspace) return LGB200_ERR_NULL;
+  if ((!scores && !workspace_has_best) || !workspace) return LGB200_ERR_NULL;
   unsigned long long* best0 = reinterpret_cast<unsigned long long*>(workspace);
   unsigned long long* best1 = best0 + (size_t)B * R;
-  cudaError_t e = cudaMemsetAsync(workspace, 0, sizeof(unsigned long long) * (size_t)B * (R + C), st);
-  if (e != cudaSuccess) return (int)e;
-  dim3 g1((R - 1 + FM_ROWS - 1) / FM_ROWS, B);
-  fm_argmax_kernel<<<g1, 256, 0, st>>>(scores, R, C, lens, best0, best1);
-  LG_LAUNCH_CHECK();
+  if (!workspace_has_best) {  // otherwise lgb200_assign_scores already left the packed maxima there
+    cudaError_t e = cudaMemsetAsync(workspace, 0, sizeof(unsigned long long) * (size_t)B * (R + C), st);
+    if (e != cudaSuccess) return (int)e;
+    dim3 g1((R - 1 + FM_ROWS - 1) / FM_ROWS, B);
+    fm_argmax_kernel<<<g1, 256, 0, st>>>(scores, R, C, lens, best0, best1);
+    LG_LAUNCH_CHECK();
+  }
   const int mxn = (R > C ? R : C) - 1;
   dim3 g2((mxn + 255) / 256, B);
   fm_mutual_kernel<<<g2, 256, 0, st>>>(R, C, lens, threshold, best0, best1, ind0, ind1, ind_ld, N0, N1,

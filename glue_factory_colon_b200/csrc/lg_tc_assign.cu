@@ -21,7 +21,7 @@ constexpr int AS_OPER = 4 * AS_TILE;         // 128 rows x K=256 (64 KB)
 constexpr int AS_STAGE_OFF = AS_OPER;        // B stages follow A
 constexpr int AS_BAR_OFF = 3 * AS_OPER;
 constexpr int AS_XPOSE_OFF = AS_BAR_OFF + 128;
-constexpr int AS_SMEM = AS_XPOSE_OFF + 4 * 32 * 33 * 4 + 1024;
+constexpr int AS_SMEM = AS_XPOSE_OFF + 4 * 32 * 33 * 4 + 4 * 32 * 4 + 1024;
 
 __device__ __forceinline__ float ex2a(float x) {
   float y;
@@ -33,7 +33,8 @@ template <bool SCORES>
 __global__ void __launch_bounds__(192, 1)
 tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t* __restrict__ lens,
                  const float* __restrict__ z, const float* __restrict__ lse_in, float* __restrict__ lse_out,
-                 int R, int C, float* __restrict__ scores) {
+                 int R, int C, float* __restrict__ scores, unsigned long long* __restrict__ best0,
+                 unsigned long long* __restrict__ best1) {
   // SCORES: blockIdx.y = pair b, rows from sequence 2b.  LSE: blockIdx.y = sequence s.
   const int s = SCORES ? 2 * blockIdx.y : blockIdx.y;
   const int so = s ^ 1;
@@ -127,6 +128,9 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t
     float rowconst = 0.f;
     if (SCORES && row < nq) rowconst = lg_logsigmoid(z[(size_t)s * Lp + row]) - lse_in[(size_t)s * Lp + row];
     float* xp = xpose + (warp - 2) * 32 * 33;
+    float* xc = xpose + 4 * 32 * 33 + (warp - 2) * 32;  // this chunk's 32 column constants
+    float rbest = -INFINITY;                            // fused filter_matches: running row argmax
+    int ridx = 0;
     for (int j = 0; j < n_tiles; ++j) {
       const int st = j & 1;
       tc::mbar_wait(&s_full[st], (j >> 1) & 1);
@@ -167,19 +171,38 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t
           const int col = j * 128 + c * 32 + lane;  // this lane's column in the transposed phase
           float colconst = 0.f;
           if (col < nk) colconst = lg_logsigmoid(z[(size_t)so * Lp + col]) - lse_in[(size_t)so * Lp + col];
+          if (best0) xc[lane] = col < nk ? colconst : -INFINITY;  // -inf: column takes no part in the row max
 #pragma unroll
           for (int i = 0; i < 32; ++i) xp[lane * 33 + i] = fmaf(2.f, __uint_as_float(v[i]), rowconst);
           __syncwarp();
+          if (best0) {
+            // row phase (thread = row): running argmax over exactly the values that get written
+            const int cb = j * 128 + c * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float val = fmaf(2.f, __uint_as_float(v[i]), rowconst) + xc[i];
+              if (val > rbest || (val != val && rbest == rbest)) { rbest = val; ridx = cb + i; }
+            }
+          }
           float* out = scores + ((size_t)blockIdx.y * R + m0 + quarter * 32) * C + col;
           const int rows_here = min(32, nq - (m0 + quarter * 32));
           if (col < nk) {
-            for (int rr = 0; rr < rows_here; ++rr) out[(size_t)rr * C] = xp[rr * 33 + lane] + colconst;
+            float cbest = -INFINITY;
+            int cidx = 0;
+            for (int rr = 0; rr < rows_here; ++rr) {
+              const float val = xp[rr * 33 + lane] + colconst;
+              out[(size_t)rr * C] = val;
+              if (val > cbest || (val != val && cbest == cbest)) { cbest = val; cidx = rr; }
+            }
+            if (best1 && rows_here > 0)
+              atomicMax(best1 + (size_t)blockIdx.y * C + col, fm_pack(cbest, m0 + quarter * 32 + cidx));
           }
           __syncwarp();
         }
       }
     }
     if (!SCORES && row < nq) lse_out[(size_t)s * Lp + row] = m_run + logf(l_run);
+    if (SCORES && best0 && row < nq) best0[(size_t)blockIdx.y * R + row] = fm_pack(rbest, ridx);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -222,13 +245,14 @@ int lg_tc_assign_lse(const __nv_bfloat16* md, int S, int Lp, const int32_t* lens
   cudaError_t e = cudaFuncSetAttribute(tc_assign_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AS_SMEM);
   if (e != cudaSuccess) return (int)e;
   dim3 grid(Lp / 128, S);
-  tc_assign_kernel<false><<<grid, 192, AS_SMEM, st>>>(tm, Lp, lens, nullptr, nullptr, lse, 0, 0, nullptr);
+  tc_assign_kernel<false><<<grid, 192, AS_SMEM, st>>>(tm, Lp, lens, nullptr, nullptr, lse, 0, 0, nullptr, nullptr,
+                                                      nullptr);
   LG_LAUNCH_CHECK();
   return LGB200_OK;
 }
 
 int lg_tc_assign_scores(const __nv_bfloat16* md, const float* z, const float* lse, int B, int Lp,
-                        const int32_t* lens, int R, int C, float* scores, cudaStream_t st) {
+                        const int32_t* lens, int R, int C, float* scores, void* best_ws, cudaStream_t st) {
   CUtensorMap tm;
   int rc = make_md_map(&tm, md, 2 * B, Lp);
   if (rc) return rc;
@@ -236,9 +260,15 @@ int lg_tc_assign_scores(const __nv_bfloat16* md, const float* z, const float* ls
   if (e != cudaSuccess) return (int)e;
   assign_border_kernel<<<dim3(R, B), 128, 0, st>>>(z, Lp, lens, R, C, scores);
   LG_LAUNCH_CHECK();
+  unsigned long long* best0 = reinterpret_cast<unsigned long long*>(best_ws);
+  unsigned long long* best1 = best0 ? best0 + (size_t)B * R : nullptr;
+  if (best_ws) {
+    e = cudaMemsetAsync(best_ws, 0, sizeof(unsigned long long) * (size_t)B * (R + C), st);
+    if (e != cudaSuccess) return (int)e;
+  }
   if (R > 1 && C > 1) {
     dim3 grid((R - 1 + 127) / 128, B);
-    tc_assign_kernel<true><<<grid, 192, AS_SMEM, st>>>(tm, Lp, lens, z, lse, nullptr, R, C, scores);
+    tc_assign_kernel<true><<<grid, 192, AS_SMEM, st>>>(tm, Lp, lens, z, lse, nullptr, R, C, scores, best0, best1);
     LG_LAUNCH_CHECK();
   }
   return LGB200_OK;

@@ -326,12 +326,15 @@ class LightGlue(nn.Module):
         x = torch.empty(T, 256, **adt)
         rot = None if bf else torch.empty(T, 64, **f32)           # (cos, sin) fp32 pairs
         rot16 = torch.empty(T, 32, **i32) if bf else None          # packed fp16 (cos, sin)
-        q = torch.zeros(T * 256, **adt)
-        k = torch.zeros(T * 256, **adt)
-        v = torch.zeros(T * 256, **adt)
-        ctx = torch.zeros(T, 256, **adt)
-        msg = torch.zeros(T, 256, **adt)
-        hid = torch.zeros(T, 512, **adt)
+        # padded rows must hold finite values (masked keys multiply V rows by exactly 0); without
+        # padding every row is written before it is read, so the fills are skipped
+        alloc = torch.zeros if use_lens else torch.empty
+        q = alloc(T * 256, **adt)
+        k = alloc(T * 256, **adt)
+        v = alloc(T * 256, **adt)
+        ctx = alloc(T, 256, **adt)
+        msg = alloc(T, 256, **adt)
+        hid = alloc(T, 512, **adt)
 
         def linear(epi, A0, Wt, bias, N, K, A1=None, K0=None, scale=(1.0, 1.0, 1.0), resid=None,
                    out=None, n_rot=0, outp=(None, None, None), gamma=None, beta=None, lens_=None):
@@ -453,20 +456,22 @@ class LightGlue(nn.Module):
         else:
             R, C = m + 1, n + 1
         scores = torch.empty(B, R, C, **f32)
-        check(lib.lgb200_assign_scores(prec, ptr(md), ptr(z), ptr(lse), B, Lp, ptr(lens), R, C, ptr(scores), st),
-              "assign_scores")
+        fm_ws = torch.empty(B * (R + C), device=dev, dtype=torch.int64)
+        # bf16: the assignment epilogue also emits the row/column arg-maxima, so filter_matches never
+        # re-reads the 1 GB score matrix
+        check(lib.lgb200_assign_scores(prec, ptr(md), ptr(z), ptr(lse), B, Lp, ptr(lens), R, C, ptr(scores),
+                                       ptr(fm_ws) if bf else None, st), "assign_scores")
 
         # ---- filter_matches (lightglue.py:525-536) ----
         m0 = torch.empty(B, m, device=dev, dtype=torch.int64)
         m1 = torch.empty(B, n, device=dev, dtype=torch.int64)
         ms0 = torch.empty(B, m, **f32)
         ms1 = torch.empty(B, n, **f32)
-        fm_ws = torch.empty(B * (R + C), device=dev, dtype=torch.int64)
         check(
             lib.lgb200_filter_matches(
                 ptr(scores), B, R, C, ptr(lens), float(conf.filter_threshold),
                 ptr(ind) if do_prune else None, ptr(ind[1:]) if do_prune else None, 2 * Lp,
-                m, n, ptr(m0), ptr(m1), ptr(ms0), ptr(ms1), ptr(fm_ws), st,
+                m, n, ptr(m0), ptr(m1), ptr(ms0), ptr(ms1), ptr(fm_ws), 1 if bf else 0, st,
             ),
             "filter_matches",
         )

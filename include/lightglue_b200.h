@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define LGB200_ABI_VERSION 2
+#define LGB200_ABI_VERSION 3
 
 enum { LGB200_F32 = 0, LGB200_BF16 = 1 };
 
@@ -144,12 +144,16 @@ int lgb200_rowdot(int precision, const void* x, const float* w, const float* b, 
  *          scores [B,R,C] fp32 (R = n0max+1, C = n1max+1) exactly once:
  *          valid block 2*sim - lse0[i] - lse1[j] + logsigmoid(z0[i]) + logsigmoid(z1[j]),
  *          dustbin column C-1 = logsigmoid(-z0), dustbin row R-1 = logsigmoid(-z1),
- *          everything else (padding, corner) 0. */
+ *          everything else (padding, corner) 0.
+ *          best_ws (nullable, 8*B*(R+C) bytes, LGB200_BF16 only): the kernel also leaves the packed
+ *          row / column maxima of the valid block there (computed on exactly the values it writes),
+ *          which lgb200_filter_matches accepts with workspace_has_best = 1 and then does not
+ *          re-read the score matrix at all. */
 int lgb200_assign_lse(int precision, const void* md, int S, int Lp, const int32_t* lens,
                       float* lse, void* stream);
 int lgb200_assign_scores(int precision, const void* md, const float* z, const float* lse,
                          int B, int Lp, const int32_t* lens, int R, int C,
-                         float* scores, void* stream);
+                         float* scores, void* best_ws, void* stream);
 
 /* ---- filter_matches -------------------------------------------------------------------
  * Replaces filter_matches, lightglue.py:294-319 (and the scatter back to
@@ -159,11 +163,12 @@ int lgb200_assign_scores(int precision, const void* md, const float* z, const fl
  * ind0/ind1 (int32 [B,ind_ld], nullable) map current rows to original indices;
  * outputs are indexed by ORIGINAL index: m0 [B,N0] int64, m1 [B,N1] int64,
  * ms0 [B,N0], ms1 [B,N1] fp32; untouched entries are -1 / 0.
- * workspace: 8 * B * (R + C) bytes. */
+ * workspace: 8 * B * (R + C) bytes; workspace_has_best != 0 means it already holds the packed maxima
+ * written by lgb200_assign_scores (scores may then be NULL). */
 int lgb200_filter_matches(const float* scores, int B, int R, int C, const int32_t* lens,
                           float threshold, const int32_t* ind0, const int32_t* ind1, int ind_ld,
                           int N0, int N1, int64_t* m0, int64_t* m1, float* ms0, float* ms1,
-                          void* workspace, void* stream);
+                          void* workspace, int workspace_has_best, void* stream);
 
 /* ---- adaptive depth (early exit) ---------------------------------------------------------
  * Replaces check_if_stop, lightglue.py:569-580.  conf [S,Lp] = sigmoid token

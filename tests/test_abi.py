@@ -55,7 +55,7 @@ def test_argument_validation_without_gpu(libpath):
     lib = _abi.load()
     assert lib.lgb200_attention(0, None, None, None, 2, 128, None, 0, None, None) == -2
     assert lib.lgb200_pack_rows(1, 1, 10, 255, 0, 128, 1, None, None) == -1
-    assert lib.lgb200_filter_matches(None, 1, 5, 5, None, 0.0, None, None, 0, 4, 4, None, None, None, None, None, None) == -2
+    assert lib.lgb200_filter_matches(None, 1, 5, 5, None, 0.0, None, None, 0, 4, 4, None, None, None, None, None, 0, None) == -2
 
 
 def test_product_path_has_no_cpu_fallback():

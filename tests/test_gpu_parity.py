@@ -100,7 +100,7 @@ def test_filter_matches_kat_bit_exact(golden_dir):
         s1 = torch.empty(B, C - 1, device=DEV)
         ws = torch.empty(B * (R + C), device=DEV, dtype=torch.int64)
         rc = lib.lgb200_filter_matches(ptr(sc), B, R, C, None, case["th"], None, None, 0, R - 1, C - 1,
-                                       ptr(m0), ptr(m1), ptr(s0), ptr(s1), ptr(ws), _stream())
+                                       ptr(m0), ptr(m1), ptr(s0), ptr(s1), ptr(ws), 0, _stream())
         assert rc == 0
         assert torch.equal(m0.cpu(), case["m0"]) and torch.equal(m1.cpu(), case["m1"])
         torch.testing.assert_close(s0.cpu(), case["ms0"], atol=1e-6, rtol=1e-5)
@@ -118,7 +118,7 @@ def test_filter_matches_large_random_against_torch():
     s0 = torch.empty(B, R - 1, device=DEV); s1 = torch.empty(B, C - 1, device=DEV)
     ws = torch.empty(B * (R + C), device=DEV, dtype=torch.int64)
     assert lib.lgb200_filter_matches(ptr(sc), B, R, C, None, 0.01, None, None, 0, R - 1, C - 1,
-                                     ptr(m0), ptr(m1), ptr(s0), ptr(s1), ptr(ws), _stream()) == 0
+                                     ptr(m0), ptr(m1), ptr(s0), ptr(s1), ptr(ws), 0, _stream()) == 0
     inner = sc[:, :-1, :-1]
     mx0, mx1 = inner.max(2), inner.max(1)
     i0 = torch.arange(R - 1, device=DEV)[None]; i1 = torch.arange(C - 1, device=DEV)[None]
@@ -319,7 +319,18 @@ def test_assignment_kernels(prec):
     assert lib.lgb200_assign_lse(prec, ptr(md), S, Lp, ptr(lens), ptr(lse), _stream()) == 0
     R, C = 257, 257
     sc = torch.full((B, R, C), 99.0, device=DEV)
-    assert lib.lgb200_assign_scores(prec, ptr(md), ptr(z), ptr(lse), B, Lp, ptr(lens), R, C, ptr(sc), _stream()) == 0
+    ws = torch.empty(B * (R + C), device=DEV, dtype=torch.int64) if bf else None
+    assert lib.lgb200_assign_scores(prec, ptr(md), ptr(z), ptr(lse), B, Lp, ptr(lens), R, C, ptr(sc), ptr(ws), _stream()) == 0
+    if bf:  # fused arg-maxima must give exactly what the stand-alone filter finds on the written matrix
+        outs = []
+        for has_best in (1, 0):
+            m0 = torch.empty(B, R - 1, device=DEV, dtype=torch.int64); m1 = torch.empty(B, C - 1, device=DEV, dtype=torch.int64)
+            s0 = torch.empty(B, R - 1, device=DEV); s1 = torch.empty(B, C - 1, device=DEV)
+            assert lib.lgb200_filter_matches(ptr(sc), B, R, C, ptr(lens), 0.0, None, None, 0, R - 1, C - 1, ptr(m0), ptr(m1),
+                                             ptr(s0), ptr(s1), ptr(ws), has_best, _stream()) == 0
+            outs.append((m0, m1, s0, s1))
+        for a, b_ in zip(*outs):
+            assert torch.equal(a, b_)
     ls = torch.nn.functional.logsigmoid
     for b in range(B):
         n0, n1 = int(lens[2 * b]), int(lens[2 * b + 1])
