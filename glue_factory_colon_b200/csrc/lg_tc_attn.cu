@@ -37,6 +37,22 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// 2^x for x <= 8 on the FMA/ALU pipes (the MUFU unit delivers only 16 ex2/clk/SM, which is what bounds
+// this kernel at d = 64): round-to-nearest split x = n + f, |f| <= 0.5, degree-3 minimax polynomial
+// (max rel. err 1.0e-4, far below the bf16 rounding of P), exponent patched in with integer ops.
+// tools/micro/softmax_rate.cu: 13.7 -> 15.3 elements/clk/SM with one exponential in four done this way,
+// but inside this kernel (96-register cap at 2 CTAs/SM) it measured slower (1.05 vs 0.89 ms), so it is
+// opt-in only (LGB200_ATTN_DBG=8) until the register budget is reworked.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(f, 0.05500889f, 0.24221097f);
+  p = fmaf(p, f, 0.69328294f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 template <int CL>
 __global__ void __launch_bounds__(320, 2)
 tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -250,7 +266,8 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         float p0 = __uint_as_float(sv[2 * i]) - m_new, p1 = __uint_as_float(sv[2 * i + 1]) - m_new;
-        if (dbg == 1) { p0 = p0 * p0; p1 = p1 * p1; } else { p0 = ex2(p0); p1 = ex2(p1); }
+        if (dbg == 1) { p0 = p0 * p0; p1 = p1 * p1; }
+        else { p0 = ex2(p0); p1 = ((i & 1) && dbg == 8) ? ex2_poly(p1) : ex2(p1); }
         rsum[i & 3] += p0 + p1;
         pk[i] = tc::pack_bf16(p0, p1);
       }

@@ -27,6 +27,7 @@
 #include "lg_tc_common.cuh"
 
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -59,6 +60,8 @@ struct Args {
   int n_groups;  // column-block groups (clusters) per M tile: N / (128 * CL)
   int m_tiles;
   int Lp;
+  int prefetch_tiles;  // L2 prefetch distance in M tiles (0 = off)
+  int exact_gelu;      // 1: erf-form GELU (LGB200_GELU_ERF=1), 0: tanh form
   int has_in;    // rotary table (HEADS) or residual (ROW) present
   int n_rot;
   float scale[3];
@@ -118,6 +121,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
                "r"(tc::smem_u32(src)), "r"(c0), "r"(c1)
                : "memory");
 }
+// L2 prefetch of a tensor box: no shared memory, no barrier -- shortens the later smem fill from HBM
+// latency to L2-hit latency (the A ring holds only 48-64 KB, ~40-50 % of what HBM latency would need)
+__device__ __forceinline__ void tma_prefetch_l2(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -139,6 +149,19 @@ __device__ __forceinline__ float gelu_fast(float x) {
   const float h = 0.5f * x;
   return fmaf(copysignf(erf_abs, x), h, h);
 }
+
+// tanh-form GELU, 5 FMA-pipe ops + 1 MUFU.  |gelu_tanh - gelu_erf| <= 4.7e-4 absolute (at |x| ~ 2), an eighth
+// of a bf16 ulp there; with the erf form the FFN1 epilogue needed ~2560 issue cycles per 128x128 tile
+// against 2048 tensor cycles.  bf16 mode only -- the fp32 parity path uses erff().
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float k = fmaf(x * x, 0.0356774081f, 0.7978845608f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * k));
+  const float h = 0.5f * x;
+  return fmaf(h, t, h);
+}
+
+__device__ __forceinline__ float gelu_act(float x, int exact) { return exact ? gelu_fast(x) : gelu_tanh(x); }
 
 __device__ __forceinline__ bool tile_skipped(const Args& g, int m_tile) {
   if (!g.lens) return false;
@@ -235,6 +258,10 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
           tc::mbar_arrive_expect_tx(&full[stage], A_STAGE);
           if (CL > 1) tma_load_2d_mc(dst, tm, &full[stage], kc, row, MC_MASK);
           else tc::tma_load_2d(dst, tm, &full[stage], kc, row);
+          if (g.prefetch_tiles > 0) {
+            const int mp = mt + g.prefetch_tiles * m_step;  // same k-block, a few M tiles ahead
+            if (mp < g.m_tiles) tma_prefetch_l2(tm, kc, mp * BM + crank * SLICE_ROWS);
+          }
         }
         __syncwarp();
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -342,11 +369,12 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
         const float inv_n = 1.f / (float)(BN * CL);
         const float mean = ts * inv_n;
         const float rstd = rsqrtf(fmaxf(tq * inv_n - mean * mean, 0.f) + 1e-5f);
+        const float nmr = -mean * rstd;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int c = c_warp + 2 * j;
-          const float a = gelu_fast(fmaf((__uint_as_float(v[2 * j]) - mean) * rstd, s_par[BN + c], s_par[2 * BN + c]));
-          const float b = gelu_fast(fmaf((__uint_as_float(v[2 * j + 1]) - mean) * rstd, s_par[BN + c + 1], s_par[2 * BN + c + 1]));
+          const float a = gelu_act(fmaf(fmaf(__uint_as_float(v[2 * j]), rstd, nmr), s_par[BN + c], s_par[2 * BN + c]), g.exact_gelu);
+          const float b = gelu_act(fmaf(fmaf(__uint_as_float(v[2 * j + 1]), rstd, nmr), s_par[BN + c + 1], s_par[2 * BN + c + 1]), g.exact_gelu);
           pk[j] = tc::pack_bf16(a, b);
         }
       } else {
@@ -502,6 +530,10 @@ int lg_tc_linear_v2(int epilogue, const __nv_bfloat16* A0, const __nv_bfloat16* 
   g.scale[0] = epi.scale[0]; g.scale[1] = epi.scale[1]; g.scale[2] = epi.scale[2];
   g.n_rot = epi.n_rot;
   g.has_in = 0;
+  static const int pf = getenv("LGB200_GEMM_PREFETCH") ? atoi(getenv("LGB200_GEMM_PREFETCH")) : 1;
+  g.prefetch_tiles = pf;
+  static const int erf_gelu = getenv("LGB200_GELU_ERF") ? atoi(getenv("LGB200_GELU_ERF")) : 0;
+  g.exact_gelu = erf_gelu;
   maps.in = maps.a0;
   if (epilogue == LGB200_EPI_HEADS) {
     const uint64_t rows = (uint64_t)T * LG_HEADS;  // [S*4*Lp, 64]
