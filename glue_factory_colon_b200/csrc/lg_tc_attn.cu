@@ -20,6 +20,14 @@
 
 // debug timeline (clock64 stamps of CTA (0,0,0); read back with lgb200_debug_attn_times)
 __device__ long long g_attn_times[2 * 16 * 16];
+// Arrival counter per SM: the two CTAs that share an SM take alternating slots, and the odd one starts half
+// a step late.  Without this the co-resident CTAs run in lockstep: all 16 softmax warps exponentiate at the
+// same time (MUFU 100 % busy for ~2000 cycles) and then all leave it idle for ~1000 (measured timeline).
+__device__ unsigned int g_attn_sm_slot[1024];
+
+#ifndef LG_ATTN_POLY
+#define LG_ATTN_POLY 2  // one exponential in (2 * LG_ATTN_POLY) is evaluated by polynomial on the FMA pipe
+#endif
 
 namespace {
 
@@ -40,9 +48,8 @@ __device__ __forceinline__ float ex2(float x) {
 // 2^x for x <= 8 on the FMA/ALU pipes (the MUFU unit delivers only 16 ex2/clk/SM, which is what bounds
 // this kernel at d = 64): round-to-nearest split x = n + f, |f| <= 0.5, degree-3 minimax polynomial
 // (max rel. err 1.0e-4, far below the bf16 rounding of P), exponent patched in with integer ops.
-// tools/micro/softmax_rate.cu: 13.7 -> 15.3 elements/clk/SM with one exponential in four done this way,
-// but inside this kernel (96-register cap at 2 CTAs/SM) it measured slower (1.05 vs 0.89 ms), so it is
-// opt-in only (LGB200_ATTN_DBG=8) until the register budget is reworked.
+// tools/micro/softmax_rate.cu: 13.7 -> 15.3 elements/clk/SM with one exponential in four done this way;
+// in this kernel 0.774 -> 0.717 ms per launch at S=128, Lp=2048 (LG_ATTN_POLY=2; 3 gives 0.730).
 __device__ __forceinline__ float ex2_poly(float x) {
   x = fmaxf(x, -126.f);
   const float t = x + 12582912.f;
@@ -57,7 +64,16 @@ template <int CL>
 __global__ void __launch_bounds__(320, 2)
 tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, int Lp, const int32_t* __restrict__ lens,
-                    int kv_xor, __nv_bfloat16* __restrict__ ctx, int dbg) {
+                    int kv_xor, __nv_bfloat16* __restrict__ ctx, int dbg_arg, unsigned stagger_ns) {
+  // Debug modes (skeleton runs, no-MUFU run, clock64 timeline) exist only when the file is compiled with
+  // -DLG_ATTN_DEBUG; in the product build `dbg` is the constant 0 and every debug branch folds away
+  // (leaving them as run-time branches cost ~50 BRA per 64 exponentials in the unrolled loop).
+#ifdef LG_ATTN_DEBUG
+  const int dbg_in = dbg_arg;
+#else
+  constexpr int dbg_in = 0;
+#endif
+  const int dbg = dbg_in & 15;  // bit 4 of dbg_in enables the clock64 timeline
   // CL CTAs with consecutive query tiles of the same (sequence, head) form a cluster and share every
   // K/V tile: each loads 1/CL of it and TMA-multicasts it to the others.  (Measured: with one CTA per
   // K/V tile the kernel sat at ~5 TB/s of L2->SM traffic regardless of MUFU / pipelining changes.)
@@ -116,6 +132,11 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, TM_COLS);
+  if (threadIdx.x == 64 && stagger_ns > 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (atomicAdd(&g_attn_sm_slot[smid & 1023], 1u) & 1u) __nanosleep(stagger_ns);
+  }
   tc::fence_before_sync();
   __syncthreads();
   if (CL > 1) tc::cluster_sync();  // peers' barriers exist before anyone multicasts into them
@@ -172,7 +193,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tc::mbar_wait(&k_full[0], 0);
     tc::fence_after_sync();
     issue_qk();
-    const bool recm = dbg == 7 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+    const bool recm = (dbg_in & 16) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
 #define MSTAMP(k) do { if (recm && j < 16) g_attn_times[256 + (j * 16) + (k)] = clock64(); } while (0)
     for (int j = 0; j < n_tiles; ++j) {
       MSTAMP(0);
@@ -211,7 +232,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     float m_ref = -INFINITY, l_part = 0.f;
-    const bool rec = dbg == 7 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0;
+    const bool rec = (dbg_in & 16) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0;
 #define STAMP(k) do { if (rec && j < 16) g_attn_times[(j * 16) + (k)] = clock64(); } while (0)
     for (int j = 0; j < n_tiles; ++j) {
       STAMP(0);
@@ -267,7 +288,14 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       for (int i = 0; i < 32; ++i) {
         float p0 = __uint_as_float(sv[2 * i]) - m_new, p1 = __uint_as_float(sv[2 * i + 1]) - m_new;
         if (dbg == 1) { p0 = p0 * p0; p1 = p1 * p1; }
-        else { p0 = ex2(p0); p1 = ((i & 1) && dbg == 8) ? ex2_poly(p1) : ex2(p1); }
+        else {
+          p0 = ex2(p0);
+#if LG_ATTN_POLY > 0
+          p1 = (i % LG_ATTN_POLY == 0) ? ex2_poly(p1) : ex2(p1);
+#else
+          p1 = ex2(p1);
+#endif
+        }
         rsum[i & 3] += p0 + p1;
         pk[i] = tc::pack_bf16(p0, p1);
       }
@@ -341,7 +369,7 @@ static int launch_attention(const __nv_bfloat16* Q, const __nv_bfloat16* K, cons
   if ((rc = lg_make_tmap_bf16(&tk, K, 2, d, sb, box_kv))) return rc;
   if ((rc = lg_make_tmap_bf16(&tv, V, 2, d, sb, box_kv))) return rc;
   auto kern = tc_attention_kernel<CL>;
-  const int smem = dbg == 3 ? 120 * 1024 : AT_SMEM;  // dbg 3: one CTA per SM
+  const int smem = (dbg & 15) == 3 ? 120 * 1024 : AT_SMEM;  // dbg 3: one CTA per SM
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
   cudaLaunchConfig_t cfg = {};
@@ -356,7 +384,8 @@ static int launch_attention(const __nv_bfloat16* Q, const __nv_bfloat16* K, cons
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, kern, tq, tk, tv, Lp, lens, kv_xor, ctx, dbg);
+  static const unsigned stagger = getenv("LGB200_ATTN_STAGGER_NS") ? (unsigned)atoi(getenv("LGB200_ATTN_STAGGER_NS")) : 600u;
+  e = cudaLaunchKernelEx(&cfg, kern, tq, tk, tv, Lp, lens, kv_xor, ctx, dbg, stagger);
   if (e != cudaSuccess) return (int)e;
   LG_LAUNCH_CHECK();
   return LGB200_OK;

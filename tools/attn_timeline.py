@@ -1,6 +1,6 @@
 import sys, ctypes, torch, numpy as np, os
 from pathlib import Path
-os.environ["LGB200_ATTN_DBG"] = "7"
+os.environ["LGB200_ATTN_DBG"] = str(16 + int(sys.argv[1]) if len(sys.argv) > 1 else 16)
 os.environ.setdefault("LGB200_ATTN_CL", "1")
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from glue_factory_colon_b200 import _abi
