@@ -61,7 +61,6 @@ struct Args {
   int m_tiles;
   int Lp;
   int prefetch_tiles;  // L2 prefetch distance in M tiles (0 = off)
-  int exact_gelu;      // 1: erf-form GELU (LGB200_GELU_ERF=1), 0: tanh form
   int has_in;    // rotary table (HEADS) or residual (ROW) present
   int n_rot;
   float scale[3];
@@ -161,7 +160,11 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   return fmaf(h, t, h);
 }
 
-__device__ __forceinline__ float gelu_act(float x, int exact) { return exact ? gelu_fast(x) : gelu_tanh(x); }
+#ifdef LG_GELU_ERF
+__device__ __forceinline__ float gelu_act(float x) { return gelu_fast(x); }
+#else
+__device__ __forceinline__ float gelu_act(float x) { return gelu_tanh(x); }
+#endif
 
 __device__ __forceinline__ bool tile_skipped(const Args& g, int m_tile) {
   if (!g.lens) return false;
@@ -373,8 +376,8 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int c = c_warp + 2 * j;
-          const float a = gelu_act(fmaf(fmaf(__uint_as_float(v[2 * j]), rstd, nmr), s_par[BN + c], s_par[2 * BN + c]), g.exact_gelu);
-          const float b = gelu_act(fmaf(fmaf(__uint_as_float(v[2 * j + 1]), rstd, nmr), s_par[BN + c + 1], s_par[2 * BN + c + 1]), g.exact_gelu);
+          const float a = gelu_act(fmaf(fmaf(__uint_as_float(v[2 * j]), rstd, nmr), s_par[BN + c], s_par[2 * BN + c]));
+          const float b = gelu_act(fmaf(fmaf(__uint_as_float(v[2 * j + 1]), rstd, nmr), s_par[BN + c + 1], s_par[2 * BN + c + 1]));
           pk[j] = tc::pack_bf16(a, b);
         }
       } else {
@@ -389,30 +392,35 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
           __syncwarp();  // every lane has read the input tile before anyone overwrites it (aliasing)
         }
         if constexpr (MODE == MODE_ROW) {
+          if (use_in) {  // residual add (branch hoisted out of the unrolled loop)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float a = (__uint_as_float(v[2 * j]) + s_par[c_warp + 2 * j]) * sc;
-            float b = (__uint_as_float(v[2 * j + 1]) + s_par[c_warp + 2 * j + 1]) * sc;
-            if (use_in) {
+            for (int j = 0; j < 32; ++j) {
               const __nv_bfloat162 r = *reinterpret_cast<const __nv_bfloat162*>(&in[j]);
-              a += __low2float(r);
-              b += __high2float(r);
+              const float a = fmaf(__uint_as_float(v[2 * j]) + s_par[c_warp + 2 * j], sc, __low2float(r));
+              const float b = fmaf(__uint_as_float(v[2 * j + 1]) + s_par[c_warp + 2 * j + 1], sc, __high2float(r));
+              pk[j] = tc::pack_bf16(a, b);
             }
-            pk[j] = tc::pack_bf16(a, b);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              pk[j] = tc::pack_bf16((__uint_as_float(v[2 * j]) + s_par[c_warp + 2 * j]) * sc,
+                                    (__uint_as_float(v[2 * j + 1]) + s_par[c_warp + 2 * j + 1]) * sc);
           }
         } else {  // MODE_HEADS: pair j = head-dim (2j, 2j+1) rotates by frequency j
+          if (use_in) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float a = __uint_as_float(v[2 * j]) + s_par[c_warp + 2 * j];
-            float b = __uint_as_float(v[2 * j + 1]) + s_par[c_warp + 2 * j + 1];
-            if (use_in) {
+            for (int j = 0; j < 32; ++j) {
+              const float a = __uint_as_float(v[2 * j]) + s_par[c_warp + 2 * j];
+              const float b = __uint_as_float(v[2 * j + 1]) + s_par[c_warp + 2 * j + 1];
               const __half2 cs = *reinterpret_cast<const __half2*>(&in[j]);
-              const float c = __low2float(cs), s = __high2float(cs);
-              const float ra = a * c - b * s, rb = b * c + a * s;
-              a = ra;
-              b = rb;
+              const float c = __low2float(cs) * sc, s = __high2float(cs) * sc;  // scale folded into cos/sin
+              pk[j] = tc::pack_bf16(a * c - b * s, b * c + a * s);
             }
-            pk[j] = tc::pack_bf16(a * sc, b * sc);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              pk[j] = tc::pack_bf16((__uint_as_float(v[2 * j]) + s_par[c_warp + 2 * j]) * sc,
+                                    (__uint_as_float(v[2 * j + 1]) + s_par[c_warp + 2 * j + 1]) * sc);
           }
         }
       }
@@ -532,8 +540,6 @@ int lg_tc_linear_v2(int epilogue, const __nv_bfloat16* A0, const __nv_bfloat16* 
   g.has_in = 0;
   static const int pf = getenv("LGB200_GEMM_PREFETCH") ? atoi(getenv("LGB200_GEMM_PREFETCH")) : 1;
   g.prefetch_tiles = pf;
-  static const int erf_gelu = getenv("LGB200_GELU_ERF") ? atoi(getenv("LGB200_GELU_ERF")) : 0;
-  g.exact_gelu = erf_gelu;
   maps.in = maps.a0;
   if (epilogue == LGB200_EPI_HEADS) {
     const uint64_t rows = (uint64_t)T * LG_HEADS;  // [S*4*Lp, 64]
