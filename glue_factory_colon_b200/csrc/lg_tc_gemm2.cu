@@ -29,6 +29,11 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+// debug timeline (compile with -DLG_GEMM_DEBUG): accumulated wait cycles of cluster 0 / CTA rank 0
+//   [0] MMA warp waiting for an accumulator (epilogue too slow)   [1] MMA warp waiting for A stages (loads too slow)
+//   [2] MMA warp total   [3] epilogue warp 0 waiting for tfull   [4] epilogue warp 0 total   [5] tiles   [6] epilogue stats wait
+__device__ long long g_gemm_times[16];
+
 namespace {
 
 constexpr int BM = 128, BK = 64, BN = 128;
@@ -278,13 +283,26 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
     tc::mbar_wait(w_full, 0);
     const uint64_t dW0 = tc::smem_desc_sw128(tc::smem_u32(sW), 0, 1024);
     const uint64_t dA0 = tc::smem_desc_sw128(tc::smem_u32(sA), 0, 1024);
+#ifdef LG_GEMM_DEBUG
+    long long w_acc = 0, w_full_c = 0, t_begin = clock64(), tt;
+    const bool rec = blockIdx.x == 0 && lane == 0;
+#define GT0() tt = clock64()
+#define GT1(v) v += clock64() - tt
+#else
+#define GT0()
+#define GT1(v)
+#endif
     for (int mt = m_first; mt < g.m_tiles; mt += m_step) {
       if (tile_skipped(g, mt)) continue;
+      GT0();
       tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
+      GT1(w_acc);
       tc::fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * BN;
       for (int kb = 0; kb < g.kb_total; ++kb) {
+        GT0();
         tc::mbar_wait(&full[stage], phase);
+        GT1(w_full_c);
         tc::fence_after_sync();
         const uint64_t dA = dA0 + (uint64_t)(stage * (A_STAGE >> 4));
         const uint64_t dW = dW0 + (uint64_t)(kb * (WB_BYTES >> 4));
@@ -300,6 +318,9 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+#ifdef LG_GEMM_DEBUG
+    if (rec) { g_gemm_times[0] = w_acc; g_gemm_times[1] = w_full_c; g_gemm_times[2] = clock64() - t_begin; }
+#endif
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps)
     const int ew = warp - 2;        // 0..7
@@ -322,6 +343,10 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
     const bool use_in = g.has_in && (MODE == MODE_ROW || (MODE == MODE_HEADS && part < g.n_rot));
     int acc = 0, iter = 0;
     uint32_t acc_phase = 0;
+#ifdef LG_GEMM_DEBUG
+    long long e_wait = 0, e_stats = 0, e_begin = clock64(), tt;
+    const bool rec = blockIdx.x == 0 && ew == 0 && lane == 0;
+#endif
     for (int mt = m_first; mt < g.m_tiles; mt += m_step) {
       if (tile_skipped(g, mt)) continue;
       const int row0 = mt * BM + quarter * 32;  // first global row of this warp
@@ -333,7 +358,9 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
       }
       if (MODE == MODE_LN && ew == 0 && lane == 0)
         tc::mbar_arrive_expect_tx(&stats_bar[iter & 1], 2 * CL * 128 * 8);  // partials from every peer warp
+      GT0();
       tc::mbar_wait(&tfull[acc], acc_phase);
+      GT1(e_wait);
       tc::fence_after_sync();
       uint32_t v[64];
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c_warp;
@@ -361,7 +388,9 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
         const uint32_t bar = tc::smem_u32(&stats_bar[buf]);
 #pragma unroll
         for (int p = 0; p < CL; ++p) st_async_f2(map_to_rank(slot, p), sum, sq, map_to_rank(bar, p));
+        GT0();
         tc::mbar_wait(&stats_bar[buf], (iter >> 1) & 1);
+        GT1(e_stats);
         float ts = 0.f, tq = 0.f;
 #pragma unroll
         for (int p = 0; p < 2 * CL; ++p) {
@@ -447,6 +476,9 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
       ++iter;
     }
     if (lane == 0) bulk_wait0();  // all stores of this warp have landed before the CTA retires
+#ifdef LG_GEMM_DEBUG
+    if (rec) { g_gemm_times[3] = e_wait; g_gemm_times[4] = clock64() - e_begin; g_gemm_times[5] = iter; g_gemm_times[6] = e_stats; }
+#endif
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -568,4 +600,9 @@ int lg_tc_linear_v2(int epilogue, const __nv_bfloat16* A0, const __nv_bfloat16* 
   if (epilogue == LGB200_EPI_HEADS) return launch<MODE_HEADS, 2, false>(maps, g, n_blocks, st);
   if (kbig) return launch<MODE_ROW, 2, true>(maps, g, n_blocks, st);
   return launch<MODE_ROW, 2, false>(maps, g, n_blocks, st);
+}
+
+extern "C" int lgb200_debug_gemm_times(long long* host_out, int n) {
+  if (n > 16) n = 16;
+  return (int)cudaMemcpyFromSymbol(host_out, g_gemm_times, sizeof(long long) * n);
 }

@@ -37,7 +37,23 @@ __global__ void k(float* out, int iters, float seed) {
       if (MODE == 3) { p0 = ex2(v[2 * i] - m); p1 = (i & 1) ? ex2_poly(v[2 * i + 1] - m) : ex2(v[2 * i + 1] - m); }  // 25 % poly
       if (MODE == 4) { p0 = ex2(v[2 * i] - m); p1 = ex2_poly(v[2 * i + 1] - m); }                                    // 50 % poly
       if (MODE == 5) { p0 = ex2(v[2 * i] - m); p1 = (i % 3 == 0) ? ex2_poly(v[2 * i + 1] - m) : ex2(v[2 * i + 1] - m); }  // 17 %
-      if (MODE != 2) rs[i & 3] += p0 + p1;
+      if (MODE == 6 || MODE == 7) {  // packed fp32x2 (FADD2 / FFMA2) for the subtract, the sum and the polynomial
+        const float2 x2 = __fadd2_rn(make_float2(v[2 * i], v[2 * i + 1]), make_float2(-m, -m));
+        if (MODE == 7 && (i & 1)) {
+          // both lanes by polynomial: 2 of every 4 elements... (i odd) -> 25 % of pairs fully poly = 25 % elements
+          float2 xc = make_float2(fmaxf(x2.x, -126.f), fmaxf(x2.y, -126.f));
+          const float2 t = __fadd2_rn(xc, make_float2(12582912.f, 12582912.f));
+          const float2 f = __fadd2_rn(xc, __fmul2_rn(__fadd2_rn(t, make_float2(-12582912.f, -12582912.f)), make_float2(-1.f, -1.f)));
+          float2 p = __ffma2_rn(f, make_float2(0.05500889f, 0.05500889f), make_float2(0.24221097f, 0.24221097f));
+          p = __ffma2_rn(p, f, make_float2(0.69328294f, 0.69328294f));
+          p = __ffma2_rn(p, f, make_float2(1.f, 1.f));
+          p0 = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+          p1 = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+        } else { p0 = ex2(x2.x); p1 = ex2(x2.y); }
+        const float2 r2 = __fadd2_rn(make_float2(rs[(i & 1) * 2], rs[(i & 1) * 2 + 1]), make_float2(p0, p1));
+        rs[(i & 1) * 2] = r2.x; rs[(i & 1) * 2 + 1] = r2.y;
+      }
+      if (MODE != 2 && MODE != 6 && MODE != 7) rs[i & 3] += p0 + p1;
       const uint32_t pk = pack(p0, p1);
       x ^= pk;
       v[2 * i] = p0 * 0.25f - 3.f; v[2 * i + 1] = p1 * 0.25f - 2.f;  // feed back so nothing is hoisted
@@ -59,6 +75,6 @@ template <int MODE> void run(const char* n, int threads) {
   cudaFree(d);
 }
 int main() {
-  for (int t : {256, 512}) { run<0>("ex2+sum+pack   ", t); run<5>("17% poly       ", t); run<3>("25% poly       ", t); run<4>("50% poly       ", t); }
+  for (int t : {256, 512}) { run<0>("ex2+sum+pack   ", t); run<3>("25% poly       ", t); run<6>("f32x2 no poly  ", t); run<7>("f32x2 25% poly ", t); }
   return 0;
 }
