@@ -1,10 +1,10 @@
 """Times the attention kernel alone at the bench shape (S=128, Lp=2048)."""
-import sys, torch
+import os, sys, torch
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from glue_factory_colon_b200 import _abi
 from glue_factory_colon_b200._abi import BF16, ptr
-lib = _abi.load()
+lib = _abi.load(Path(os.environ['LGB200_LIB']).resolve()) if os.environ.get('LGB200_LIB') else _abi.load()
 S, Lp = 128, 2048
 g = torch.Generator(device="cuda").manual_seed(0)
 q = (torch.randn(S * 4 * Lp, 64, device="cuda", generator=g) * 0.5).to(torch.bfloat16)

@@ -4,7 +4,8 @@ from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from glue_factory_colon_b200 import _abi
 from glue_factory_colon_b200._abi import BF16, EPI_LN_GELU, EPI_ROWMAJOR, EPI_HEADS, ptr
-lib = _abi.load()
+import os
+lib = _abi.load(Path(os.environ['LGB200_LIB']).resolve()) if os.environ.get('LGB200_LIB') else _abi.load()
 lib.lgb200_debug_gemm_times.argtypes = [ctypes.c_void_p, ctypes.c_int]
 S, Lp = 128, 2048
 T = S * Lp

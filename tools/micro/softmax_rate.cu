@@ -17,8 +17,11 @@ __device__ __forceinline__ float ex2_poly(float x) {
   p = fmaf(p, f, 1.0f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
+__device__ unsigned long long g_clk[4];
 template <int MODE>
 __global__ void k(float* out, int iters, float seed) {
+  unsigned long long c0 = clock64(), g0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
   float v[64];
   for (int i = 0; i < 64; ++i) v[i] = seed * (threadIdx.x + i) * 1e-3f;
   float m = 0.5f, acc = 0.f; uint32_t x = 0;
@@ -61,6 +64,11 @@ __global__ void k(float* out, int iters, float seed) {
     acc += (rs[0] + rs[1]) + (rs[2] + rs[3]);
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc + __uint_as_float(x & 0x7fffff);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    g_clk[0] = clock64() - c0; g_clk[1] = g1 - g0;
+  }
 }
 template <int MODE> void run(const char* n, int threads) {
   float* d; cudaMalloc(&d, 148 * 1024 * 4);
@@ -69,9 +77,10 @@ template <int MODE> void run(const char* n, int threads) {
   k<MODE><<<148, threads>>>(d, 10, 1.f);
   cudaEventRecord(e0); k<MODE><<<148, threads>>>(d, iters, 1.f); cudaEventRecord(e1); cudaEventSynchronize(e1);
   float ms; cudaEventElapsedTime(&ms, e0, e1);
+  unsigned long long hc[4]; cudaMemcpyFromSymbol(hc, g_clk, sizeof(hc));
   double elems = (double)threads * 64 * iters;  // per SM
-  printf("%s threads/SM=%4d: %.3f ms -> %.2f ns per 1024 elements/SM; elements/clk/SM @1.9GHz = %.1f\n", n, threads, ms,
-         ms * 1e6 / (elems / 1024), elems / (ms * 1e-3 * 1.9e9));
+  printf("%s threads/SM=%4d: %.3f ms, SM clock %.0f MHz -> elements/clk/SM = %.2f\n", n, threads, ms,
+         hc[0] * 1e3 / (double)hc[1], elems / (double)hc[0]);
   cudaFree(d);
 }
 int main() {
