@@ -42,6 +42,9 @@ KPTS = 2048
 PAIRS_PER_GPU = 64
 
 
+ATT_DRAM_BYTES_PER_LAUNCH = 402_726_144 + 116_338_176  # measured, see roofline.traffic below
+
+
 def flops_per_pair(n, m, n_layers=9):
     t = n + m
     return float(n_layers * (2_490_368 * t + 1024 * (n * n + m * m) + 1536 * n * m) + 131_584 * t + 512 * n * m)
@@ -330,7 +333,10 @@ def run_gpu_arm(args):
             "roofline": {
                 "bound": "tensor", "kernel": "tc_attention_kernel (self-attention, S=%d x 4 heads x %d^2)" % (2 * B, KPTS),
                 "achieved": att_tf, "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": att_tf / peaks["bf16"],
-                "traffic": None, "peak_source": peaks["src"] + " burst (kernel timed alone)",
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape, ncu --set full
+                # (profiles/r1_ncu_attention_summary.txt); algorithmic bytes are 4 x 134.2 MB
+                "traffic": ATT_DRAM_BYTES_PER_LAUNCH if (2 * B, KPTS) == (128, 2048) else None,
+                "traffic_unit": "bytes", "peak_source": peaks["src"] + " burst (kernel timed alone)",
                 "kernel_ms": att_ms, "flops_per_launch": att_flops,
                 "whole_step": {"achieved": step_tf, "peak": peaks["bf16_sustained"],
                                "frac": step_tf / peaks["bf16_sustained"], "flops_per_pair": F,

@@ -21,9 +21,3 @@ for _ in range(10):
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
 print(f"attention {ms:.3f} ms  {4.0*S*4*Lp*Lp*64/ms/1e9:.0f} TFLOP/s")
-if os.environ.get("LGB200_ATTN_CLOCK"):
-    import ctypes
-    buf = (ctypes.c_longlong * 772)()
-    lib.lgb200_debug_attn_times.argtypes = [ctypes.c_void_p, ctypes.c_int]
-    lib.lgb200_debug_attn_times(buf, 772)
-    print(f"CTA 0 of the last launch: {buf[770]-buf[768]} cycles in {(buf[771]-buf[769])*1e-3:.1f} us -> SM clock {(buf[770]-buf[768])*1e3/(buf[771]-buf[769]):.0f} MHz")

@@ -12,16 +12,12 @@ ctx = torch.empty(S*Lp, 256, device="cuda", dtype=torch.bfloat16)
 st = torch.cuda.current_stream().cuda_stream
 for _ in range(2): lib.lgb200_attention(BF16, ptr(q), ptr(k), ptr(v), S, Lp, None, 0, ptr(ctx), st)
 torch.cuda.synchronize()
-buf = (ctypes.c_longlong * 768)()
+buf = (ctypes.c_longlong * 512)()
 lib.lgb200_debug_attn_times.argtypes = [ctypes.c_void_p, ctypes.c_int]
-print("rc", lib.lgb200_debug_attn_times(buf, 768))
-t = np.array(buf[:512]).reshape(2, 16, 16)
-se = np.array(buf[512:768]).reshape(128, 2)
+print("rc", lib.lgb200_debug_attn_times(buf, 512))
+t = np.array(buf[:]).reshape(2, 16, 16)
 t0 = t[0, 2, 0]
 print("softmax warp (cycles rel. to step 2 start): cols = start, s_full woke, ld done, s_free arrived, max xchg, exp done, pv_done woke, st done, p_ready arrived")
 for j in range(2, 12): print(j, (t[0, j, :9] - t0).tolist())
-print("mma warp: iter start, -, -, qk issued, p_ready woke, pv issued")
+print("mma thread: iter start, k_full, s_free woke, qk issued, p_ready woke, pv issued")
 for j in range(2, 12): print(j, (t[1, j, :6] - t0).tolist())
-print("first 16 tile starts:", (t[0, :16, 0] - t[0, 0, 0]).tolist())
-print("tile durations g=0..63 (start->p_ready):", (se[:64, 1] - se[:64, 0]).tolist())
-print("gaps between tiles (p_ready -> next start), g=0..62:", (se[1:64, 0] - se[:63, 1]).tolist())
