@@ -21,7 +21,10 @@ constexpr int AS_OPER = 4 * AS_TILE;         // 128 rows x K=256 (64 KB)
 constexpr int AS_STAGE_OFF = AS_OPER;        // B stages follow A
 constexpr int AS_BAR_OFF = 3 * AS_OPER;
 constexpr int AS_XPOSE_OFF = AS_BAR_OFF + 128;
-constexpr int AS_SMEM = AS_XPOSE_OFF + 4 * 32 * 33 * 4 + 4 * 32 * 4 + 1024;
+constexpr int AS_EPI_WARPS = 8;              // epilogue warps: (TMEM lane quarter) x (64-column half of the tile)
+constexpr int AS_THREADS = (2 + AS_EPI_WARPS) * 32;
+constexpr int AS_XP = 32 * 33;               // floats of one warp's 32 x 32 transpose tile (padded)
+constexpr int AS_SMEM = AS_XPOSE_OFF + AS_EPI_WARPS * (AS_XP + 32) * 4;
 
 __device__ __forceinline__ float ex2a(float x) {
   float y;
@@ -29,8 +32,20 @@ __device__ __forceinline__ float ex2a(float x) {
   return y;
 }
 
+// (value, index) update for torch.max semantics: the candidate with the HIGHER index (b) replaces the running one
+// only if it is strictly larger, or if it is the first NaN.  (A depth-5 tournament tree over the 32 candidates of
+// a chunk was tried against this serial chain: 827 us vs 628 us for pass 2 -- more selects than it saved stalls.)
+__device__ __forceinline__ void amax_merge(float& va, int& ia, float vb, int ib) {
+  if (vb > va || (vb != vb && va == va)) { va = vb; ia = ib; }
+}
+
+// Epilogue history: the first version had 4 epilogue warps and a rolled, dependent LDS -> FADD -> STG loop per
+// output row, and fetched z / lse for the column constants on the critical path of every chunk; pass 2 wrote its
+// 1.075 GB at 0.88 TB/s (1.30 ms at 64 pairs x 2048).  Now 8 warps, each owning 32 rows x 64 columns of a tile,
+// finished values staged transposed in shared memory, an unrolled store loop (32 independent 128-byte row
+// segments in flight per warp) and the column constants prefetched one chunk ahead: 0.63 ms (1.9 TB/s).
 template <bool SCORES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(AS_THREADS, 1)
 tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t* __restrict__ lens,
                  const float* __restrict__ z, const float* __restrict__ lse_in, float* __restrict__ lse_out,
                  int R, int C, float* __restrict__ scores, unsigned long long* __restrict__ best0,
@@ -45,15 +60,15 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (nk + 127) / 128;
   if (n_tiles == 0) {
-    if (!SCORES && warp >= 2) {
+    if (!SCORES && warp >= 2 && warp < 6) {
       const int r = (warp & 3) * 32 + lane;
       if (m0 + r < nq) lse_out[(size_t)s * Lp + m0 + r] = 0.f;
     }
     return;
   }
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((tc::smem_u32(smem) & 1023u) != 0) __trap();  // swizzled tiles need a 1024-byte aligned base
   uint8_t* sA = smem;
   uint8_t* sB = smem + AS_STAGE_OFF;  // 2 stages of AS_OPER
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AS_BAR_OFF);
@@ -72,7 +87,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t
       tc::mbar_init(&b_full[i], 1);
       tc::mbar_init(&b_empty[i], 1);
       tc::mbar_init(&s_full[i], 1);
-      tc::mbar_init(&s_empty[i], 4);
+      tc::mbar_init(&s_empty[i], AS_EPI_WARPS);
     }
     tc::fence_barrier_init();
   }
@@ -120,79 +135,113 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t
       __syncwarp();
     }
   } else {
-    const int quarter = warp & 3;
+    const int ew = warp - 2;
+    const int quarter = warp & 3;   // TMEM lane quarter this warp may read
+    const int half = ew >> 2;       // 64-column half of every tile
     const int r = quarter * 32 + lane;
     const int row = m0 + r;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     float m_run = -INFINITY, l_run = 0.f;
     float rowconst = 0.f;
     if (SCORES && row < nq) rowconst = lg_logsigmoid(z[(size_t)s * Lp + row]) - lse_in[(size_t)s * Lp + row];
-    float* xp = xpose + (warp - 2) * 32 * 33;
-    float* xc = xpose + 4 * 32 * 33 + (warp - 2) * 32;  // this chunk's 32 column constants
-    float rbest = -INFINITY;                            // fused filter_matches: running row argmax
+    float* xp = xpose + ew * (AS_XP + 32);
+    float* xc = xp + AS_XP;      // this chunk's 32 column constants
+    float rbest = -INFINITY;     // fused filter_matches: running row argmax over this warp's columns
     int ridx = 0;
+    float pf_z = 0.f, pf_lse = 0.f;  // prefetched z / lse of the next 32-column chunk (lane = column)
+    if (SCORES && half * 64 + lane < nk) {
+      pf_z = z[(size_t)so * Lp + half * 64 + lane];
+      pf_lse = lse_in[(size_t)so * Lp + half * 64 + lane];
+    }
     for (int j = 0; j < n_tiles; ++j) {
       const int st = j & 1;
       tc::mbar_wait(&s_full[st], (j >> 1) & 1);
       tc::fence_after_sync();
-      const int valid = nk - j * 128;
       if constexpr (!SCORES) {
-        uint32_t sv[128];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tc::tmem_ld32(tmem + lane_base + st * 128 + c * 32, sv + c * 32);
+        const int valid = nk - j * 128 - half * 64;  // valid keys among this thread's 64 columns
+        uint32_t sv[64];
+        tc::tmem_ld32(tmem + lane_base + st * 128 + half * 64, sv);
+        tc::tmem_ld32(tmem + lane_base + st * 128 + half * 64 + 32, sv + 32);
         tc::tmem_ld_wait();
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&s_empty[st]);
-        float mx = -INFINITY;
+        if (valid < 64) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i) {
-          if (i >= valid) sv[i] = 0xff800000u;
-          mx = fmaxf(mx, __uint_as_float(sv[i]));
+          for (int i = 0; i < 64; ++i)
+            if (i >= valid) sv[i] = 0xff800000u;
         }
-        const float m_new = fmaxf(m_run, mx);
-        const float ml2 = m_new * 1.4426950408889634f;
-        float rs = 0.f;
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int i = 0; i < 128; ++i) rs += ex2a(fmaf(__uint_as_float(sv[i]), 1.4426950408889634f, -ml2));
-        l_run = l_run * ex2a((m_run - m_new) * 1.4426950408889634f) + rs;
-        m_run = m_new;
+        for (int i = 0; i < 64; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv[i]));
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        if (mx > -INFINITY) {  // (a fully masked half keeps its running state)
+          const float m_new = fmaxf(m_run, mx);
+          const float ml2 = m_new * 1.4426950408889634f;
+          float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int i = 0; i < 64; ++i) rs4[i & 3] += ex2a(fmaf(__uint_as_float(sv[i]), 1.4426950408889634f, -ml2));
+          l_run = l_run * ex2a((m_run - m_new) * 1.4426950408889634f) + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
+          m_run = m_new;
+        }
       } else {
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           uint32_t v[32];
-          tc::tmem_ld32(tmem + lane_base + st * 128 + c * 32, v);
+          tc::tmem_ld32(tmem + lane_base + st * 128 + half * 64 + c * 32, v);
+          const int cb = j * 128 + half * 64 + c * 32;  // first column of this chunk
+          const int col = cb + lane;                    // this lane's column in the transposed phase
+          // column constant of this chunk from the values fetched one chunk ago; fetch the next chunk's now
+          // (an un-prefetched global load here cost ~1000 cycles per chunk on the critical path)
+          float colconst = -INFINITY;                   // -inf: the column takes no part in the row max
+          if (col < nk) colconst = lg_logsigmoid(pf_z) - pf_lse;
+          {
+            const int ncol = (c == 0 ? cb + 32 : cb + 96) + lane;  // next chunk: same tile, or next tile
+            if (ncol < nk) { pf_z = z[(size_t)so * Lp + ncol]; pf_lse = lse_in[(size_t)so * Lp + ncol]; }
+          }
           tc::tmem_ld_wait();
-          if (c == 3) {
+          if (c == 1) {
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&s_empty[st]);
           }
-          const int col = j * 128 + c * 32 + lane;  // this lane's column in the transposed phase
-          float colconst = 0.f;
-          if (col < nk) colconst = lg_logsigmoid(z[(size_t)so * Lp + col]) - lse_in[(size_t)so * Lp + col];
-          if (best0) xc[lane] = col < nk ? colconst : -INFINITY;  // -inf: column takes no part in the row max
-#pragma unroll
-          for (int i = 0; i < 32; ++i) xp[lane * 33 + i] = fmaf(2.f, __uint_as_float(v[i]), rowconst);
+          xc[lane] = colconst;
           __syncwarp();
-          if (best0) {
-            // row phase (thread = row): running argmax over exactly the values that get written
-            const int cb = j * 128 + c * 32;
+          // row phase (thread = row): final values, running row argmax over exactly what gets written
+          float val[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float val = fmaf(2.f, __uint_as_float(v[i]), rowconst) + xc[i];
-              if (val > rbest || (val != val && rbest == rbest)) { rbest = val; ridx = cb + i; }
-            }
+          for (int i = 0; i < 32; ++i) {
+            val[i] = fmaf(2.f, __uint_as_float(v[i]), rowconst) + xc[i];
+            xp[lane * 33 + i] = val[i];
           }
+          if (best0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) amax_merge(rbest, ridx, val[i], cb + i);
+          }
+          __syncwarp();
+          // column phase (thread = column): every warp store is one contiguous 128-byte row segment
           float* out = scores + ((size_t)blockIdx.y * R + m0 + quarter * 32) * C + col;
           const int rows_here = min(32, nq - (m0 + quarter * 32));
           if (col < nk) {
             float cbest = -INFINITY;
             int cidx = 0;
-            for (int rr = 0; rr < rows_here; ++rr) {
-              const float val = xp[rr * 33 + lane] + colconst;
-              out[(size_t)rr * C] = val;
-              if (val > cbest || (val != val && cbest == cbest)) { cbest = val; cidx = rr; }
+            if (rows_here == 32) {
+              float cv[32];
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr) {
+                cv[rr] = xp[rr * 33 + lane];
+                out[(size_t)rr * C] = cv[rr];
+              }
+              if (best1) {
+#pragma unroll
+                for (int rr = 0; rr < 32; ++rr) amax_merge(cbest, cidx, cv[rr], rr);
+              }
+            } else {
+              for (int rr = 0; rr < rows_here; ++rr) {
+                const float val = xp[rr * 33 + lane];
+                out[(size_t)rr * C] = val;
+                if (val > cbest || (val != val && cbest == cbest)) { cbest = val; cidx = rr; }
+              }
             }
             if (best1 && rows_here > 0)
               atomicMax(best1 + (size_t)blockIdx.y * C + col, fm_pack(cbest, m0 + quarter * 32 + cidx));
@@ -201,8 +250,22 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t
         }
       }
     }
-    if (!SCORES && row < nq) lse_out[(size_t)s * Lp + row] = m_run + logf(l_run);
-    if (SCORES && best0 && row < nq) best0[(size_t)blockIdx.y * R + row] = fm_pack(rbest, ridx);
+    if constexpr (!SCORES) {
+      // combine the two column halves of a row: half 1 publishes (m, l), half 0 merges and writes
+      float* ex = xpose + (ew & 3) * (AS_XP + 32);
+      if (half == 1) { ex[2 * lane] = m_run; ex[2 * lane + 1] = l_run; }
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+      if (half == 0 && row < nq) {
+        const float m1 = ex[2 * lane], l1 = ex[2 * lane + 1];
+        const float m = fmaxf(m_run, m1);
+        const float l = l_run * ex2a((m_run - m) * 1.4426950408889634f) + l1 * ex2a((m1 - m) * 1.4426950408889634f);
+        lse_out[(size_t)s * Lp + row] = m + logf(l);
+      }
+    } else {
+      // both column halves of a row race on one packed (value, ~index) word: 64-bit max keeps the larger value
+      // and, among equal values, the lower index (best0 is zeroed by the caller)
+      if (best0 && row < nq) atomicMax(best0 + (size_t)blockIdx.y * R + row, fm_pack(rbest, ridx));
+    }
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -245,7 +308,7 @@ int lg_tc_assign_lse(const __nv_bfloat16* md, int S, int Lp, const int32_t* lens
   cudaError_t e = cudaFuncSetAttribute(tc_assign_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AS_SMEM);
   if (e != cudaSuccess) return (int)e;
   dim3 grid(Lp / 128, S);
-  tc_assign_kernel<false><<<grid, 192, AS_SMEM, st>>>(tm, Lp, lens, nullptr, nullptr, lse, 0, 0, nullptr, nullptr,
+  tc_assign_kernel<false><<<grid, AS_THREADS, AS_SMEM, st>>>(tm, Lp, lens, nullptr, nullptr, lse, 0, 0, nullptr, nullptr,
                                                       nullptr);
   LG_LAUNCH_CHECK();
   return LGB200_OK;
@@ -268,7 +331,7 @@ int lg_tc_assign_scores(const __nv_bfloat16* md, const float* z, const float* ls
   }
   if (R > 1 && C > 1) {
     dim3 grid((R - 1 + 127) / 128, B);
-    tc_assign_kernel<true><<<grid, 192, AS_SMEM, st>>>(tm, Lp, lens, z, lse, nullptr, R, C, scores, best0, best1);
+    tc_assign_kernel<true><<<grid, AS_THREADS, AS_SMEM, st>>>(tm, Lp, lens, z, lse, nullptr, R, C, scores, best0, best1);
     LG_LAUNCH_CHECK();
   }
   return LGB200_OK;
