@@ -215,20 +215,33 @@ class LightGlue(nn.Module):
 
         # Wqkv rows: reference row = head*192 + d*3 + part (lightglue.py:158) -> part*256 + head*64 + d
         perm = torch.arange(768).view(4, 64, 3).permute(2, 0, 1).reshape(-1)
+        def fold_out_proj(ffn0, out_proj):
+            """bf16 mode: x + ffn(cat[x, out_proj(ctx)]) (lightglue.py:163, :221-222) with the out_proj GEMM folded
+            into the first FFN matrix -- W1.cat[x, Wo.ctx + bo] = [W1x | W1m.Wo].cat[x, ctx] + (b1 + W1m.bo) -- so the
+            [T,256]x[256,256] launch and the `msg` round trip through HBM disappear (exact in real arithmetic; the
+            product is formed in fp32 and rounded to bf16 once, like every other weight)."""
+            w1 = ffn0.weight.detach().float()
+            wo, bo = out_proj.weight.detach().float(), out_proj.bias.detach().float()
+            d = wo.shape[0]
+            return torch.cat([w1[:, :d], w1[:, d:] @ wo], 1), ffn0.bias.detach().float() + w1[:, d:] @ bo
+
+        fold = prec == BF16
         layers = []
         for lyr in self.transformers:
             sa, ca = lyr.self_attn, lyr.cross_attn
+            sf0 = fold_out_proj(sa.ffn[0], sa.out_proj) if fold else (sa.ffn[0].weight, sa.ffn[0].bias)
+            cf0 = fold_out_proj(ca.ffn[0], ca.to_out) if fold else (ca.ffn[0].weight, ca.ffn[0].bias)
             layers.append(
                 dict(
                     qkv_w=W(sa.Wqkv.weight[perm]), qkv_b=Fp(sa.Wqkv.bias[perm]),
                     so_w=W(sa.out_proj.weight), so_b=Fp(sa.out_proj.bias),
-                    sf0_w=W(sa.ffn[0].weight), sf0_b=Fp(sa.ffn[0].bias),
+                    sf0_w=W(sf0[0]), sf0_b=Fp(sf0[1]),
                     sln_g=Fp(sa.ffn[1].weight), sln_b=Fp(sa.ffn[1].bias),
                     sf3_w=W(sa.ffn[3].weight), sf3_b=Fp(sa.ffn[3].bias),
                     cqv_w=W(torch.cat([ca.to_qk.weight, ca.to_v.weight], 0)),
                     cqv_b=Fp(torch.cat([ca.to_qk.bias, ca.to_v.bias], 0)),
                     co_w=W(ca.to_out.weight), co_b=Fp(ca.to_out.bias),
-                    cf0_w=W(ca.ffn[0].weight), cf0_b=Fp(ca.ffn[0].bias),
+                    cf0_w=W(cf0[0]), cf0_b=Fp(cf0[1]),
                     cln_g=Fp(ca.ffn[1].weight), cln_b=Fp(ca.ffn[1].bias),
                     cf3_w=W(ca.ffn[3].weight), cf3_b=Fp(ca.ffn[3].bias),
                 )
@@ -396,16 +409,18 @@ class LightGlue(nn.Module):
             linear(EPI_HEADS, x, w["qkv_w"], w["qkv_b"], 768, 256, scale=(q_scale, 1.0, 1.0), n_rot=2,
                    outp=(q, k, v), lens_=la)
             check(lib.lgb200_attention(prec, ptr(q), ptr(k), ptr(v), S, Lp, ptr(la), 0, ptr(ctx), st), "attention")
-            linear(EPI_ROWMAJOR, ctx, w["so_w"], w["so_b"], 256, 256, out=msg, lens_=la)
-            linear(EPI_LN_GELU, x, w["sf0_w"], w["sf0_b"], 512, 512, A1=msg, K0=256, gamma=w["sln_g"],
+            if not bf:  # (bf16: out_proj is folded into sf0_w, see _pack)
+                linear(EPI_ROWMAJOR, ctx, w["so_w"], w["so_b"], 256, 256, out=msg, lens_=la)
+            linear(EPI_LN_GELU, x, w["sf0_w"], w["sf0_b"], 512, 512, A1=ctx if bf else msg, K0=256, gamma=w["sln_g"],
                    beta=w["sln_b"], out=hid, lens_=la)
             linear(EPI_ROWMAJOR, hid, w["sf3_w"], w["sf3_b"], 256, 512, resid=x, out=x, lens_=la)
             # cross block (lightglue.py:193-222)
             linear(EPI_HEADS, x, w["cqv_w"], w["cqv_b"], 512, 256, scale=(c_scale, 1.0, 1.0), n_rot=0,
                    outp=(q, v, None), lens_=la)
             check(lib.lgb200_attention(prec, ptr(q), ptr(q), ptr(v), S, Lp, ptr(la), 1, ptr(ctx), st), "attention")
-            linear(EPI_ROWMAJOR, ctx, w["co_w"], w["co_b"], 256, 256, out=msg, lens_=la)
-            linear(EPI_LN_GELU, x, w["cf0_w"], w["cf0_b"], 512, 512, A1=msg, K0=256, gamma=w["cln_g"],
+            if not bf:
+                linear(EPI_ROWMAJOR, ctx, w["co_w"], w["co_b"], 256, 256, out=msg, lens_=la)
+            linear(EPI_LN_GELU, x, w["cf0_w"], w["cf0_b"], 512, 512, A1=ctx if bf else msg, K0=256, gamma=w["cln_g"],
                    beta=w["cln_b"], out=hid, lens_=la)
             linear(EPI_ROWMAJOR, hid, w["cf3_w"], w["cf3_b"], 256, 512, resid=x, out=x, lens_=la)
             if i == L - 1 or not adaptive:
@@ -491,8 +506,11 @@ class LightGlue(nn.Module):
             "matches1": m1,
             "matching_scores0": ms0,
             "matching_scores1": ms1,
-            "ref_descriptors0": ref0.float(),  # fp32 like the reference (zero-copy view in fp32 mode)
-            "ref_descriptors1": ref1.float(),
+            # activation dtype, like the reference: fp32 by default, half precision under mp / autocast
+            # (lightglue.py:466-468 casts desc to half; :541-553 returns the stacked layer outputs as they are).
+            # Zero-copy views of the residual stream; the two fp32 copies cost 0.2 ms per 64-pair batch.
+            "ref_descriptors0": ref0,
+            "ref_descriptors1": ref1,
             "log_assignment": scores,
             "prune0": prune0,
             "prune1": prune1,
