@@ -489,6 +489,606 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
   }
 }
 
+// =====================================================================================================
+// CTA-pair variant (tcgen05 cta_group::2) for the ROW epilogue at K = 512, N = 256 (second FFN layer).
+//
+// Why: the 1-CTA kernel above issues 128x128x16 SS MMAs, which read 8 KB of operands from shared memory per 64
+// tensor cycles = 128 B/clk, the whole shared-memory bandwidth of the SM -- and the TMA fill of the A ring and the
+// epilogue staging share it.  Measured (LG_GEMM_DEBUG): the issuer needs ~4000 cycles for the 32 MMAs of a K = 512
+// tile against 2048 tensor cycles.  A CTA pair computes a 256 x 256 tile with M = 256 MMAs: each CTA supplies its
+// own 128 rows of A and HALF of B (its resident 128-column block of W), so every operand byte read from shared
+// memory feeds twice the flops (64 B/clk/SM), and an A stage covers twice the tensor time (the 3-stage ring hides
+// twice the load latency).
+//   cluster = 2 CTAs = one pair; rank 0 (leader) issues all MMAs and commits, rank 1 relays "my A stage / my W is
+//   loaded" to the leader with remote mbarrier arrives; both run the producer and the epilogue for their own
+//   128 rows x 256 columns (accumulators: 2 x 256 TMEM columns per CTA).
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {  // one full warp, in each CTA
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_ss2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit2_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   tc::smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  const uint32_t ra = map_to_rank(tc::smem_u32(bar), rank);
+  // relaxed: the relay publishes nothing of its own (the data were written by TMA / read through tcgen05);
+  // a release at cluster scope costs a MEMBAR + L1 invalidate (~1300 cycles per arrive, measured)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+// wait with cluster-scope acquire (the arrival may come from the peer CTA)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = tc::smem_u32(bar);
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "WAIT_LOOP_C:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra.uni WAIT_DONE_C;\n\t"
+      "bra.uni WAIT_LOOP_C;\n\t"
+      "WAIT_DONE_C:\n\t}\n" ::"r"(addr),
+      "r"(parity)
+      : "memory");
+}
+
+// both 128-row halves of super-tile `mt2` (256 rows) lie beyond their sequence's valid rows
+__device__ __forceinline__ bool pair_skipped(const Args& g, int mt2) {
+  return tile_skipped(g, 2 * mt2) && tile_skipped(g, 2 * mt2 + 1);
+}
+
+template <bool KBIG>
+__global__ void __launch_bounds__(320, 1)
+tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
+  using L = Lay<KBIG>;
+  constexpr int NSTAGE = L::NSTAGE;
+  constexpr int BN2 = 256;  // columns of the pair's tile = accumulator columns per CTA
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + L::OFF_A;
+  float* s_par = reinterpret_cast<float*>(smem + L::OFF_PAR);  // bias of the pair's 256 columns
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* empty = full + NSTAGE;
+  uint64_t* peer_full = empty + NSTAGE;  // leader only: the peer's stage is loaded
+  uint64_t* tfull = peer_full + NSTAGE;  // [2]
+  uint64_t* tempty = tfull + 2;          // [2] leader only: 16 epilogue warps of the pair
+  uint64_t* w_full = tempty + 2;
+  uint64_t* peer_w = w_full + 1;
+  uint64_t* in_bar = peer_w + 1;         // [8] one per epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_bar + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_rank();  // 0 = leader
+  const int cid = (int)cluster_id_x(), ncl = (int)n_clusters_x();
+  const int group = cid % g.n_groups;     // which 256-column block
+  const int m_first = cid / g.n_groups;
+  const int m_step = ncl / g.n_groups;
+  const int n0 = (group * 2 + (int)crank) * BN;  // this CTA's resident 128-column block of W
+  const int pair_col0 = group * BN2;
+
+  if ((tc::smem_u32(smem) & 1023u) != 0) __trap();
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&maps.a0);
+    tc::prefetch_tmap(&maps.a1);
+    tc::prefetch_tmap(&maps.w);
+    tc::prefetch_tmap(&maps.out0);
+    tc::prefetch_tmap(&maps.in);
+    for (int i = 0; i < NSTAGE; ++i) {
+      tc::mbar_init(&full[i], 1);
+      tc::mbar_init(&empty[i], 1);
+      tc::mbar_init(&peer_full[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&tfull[i], 1);
+      tc::mbar_init(&tempty[i], 16);
+    }
+    for (int i = 0; i < 8; ++i) tc::mbar_init(&in_bar[i], 1);
+    tc::mbar_init(w_full, 1);
+    tc::mbar_init(peer_w, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc2(tmem_slot, 512);
+  for (int i = threadIdx.x; i < BN2; i += blockDim.x) s_par[i] = g.bias[pair_col0 + i];
+  tc::fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers and TMEM exist before any cross-CTA traffic
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (own 128 rows, own W block)
+    if (tc::elect_one()) {
+      tc::mbar_arrive_expect_tx(w_full, g.kb_total * WB_BYTES);
+      for (int kb = 0; kb < g.kb_total; ++kb) tc::tma_load_2d(sW + kb * WB_BYTES, &maps.w, w_full, kb * BK, n0);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int mt = m_first; mt < g.m_tiles; mt += m_step) {
+      if (pair_skipped(g, mt)) continue;
+      const int row = mt * 2 * BM + (int)crank * BM;
+      for (int kb = 0; kb < g.kb_total; ++kb) {
+        tc::mbar_wait(&empty[stage], phase ^ 1);  // the pair's MMAs have read this stage (in both CTAs)
+        const CUtensorMap* tm = kb < g.kb_a0 ? &maps.a0 : &maps.a1;
+        const int kc = (kb < g.kb_a0 ? kb : kb - g.kb_a0) * BK;
+        if (tc::elect_one()) {
+          tc::mbar_arrive_expect_tx(&full[stage], A_STAGE);
+          tc::tma_load_2d(sA + stage * A_STAGE, tm, &full[stage], kc, row);
+          if (g.prefetch_tiles > 0) {
+            const int mp = mt + g.prefetch_tiles * m_step;
+            if (mp < g.m_tiles) tma_prefetch_l2(tm, kc, mp * 2 * BM + (int)crank * BM);
+          }
+        }
+        __syncwarp();
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    tc::mbar_wait(w_full, 0);
+    if (crank == 0) {
+      // ---------------------------------------------------------------- MMA issuer (leader CTA)
+      constexpr uint32_t idesc = tc::idesc_bf16(256, BN2, 0);
+      mbar_wait_cluster(peer_w, 0);
+      const uint64_t dW0 = tc::smem_desc_sw128(tc::smem_u32(sW), 0, 1024);
+      const uint64_t dA0 = tc::smem_desc_sw128(tc::smem_u32(sA), 0, 1024);
+#ifdef LG_GEMM_DEBUG
+      long long w_acc = 0, w_full_c = 0, w_peer = 0, t_begin = clock64(), tt;
+      int n_t = 0;
+      const bool rec = blockIdx.x == 0 && lane == 0;
+#endif
+      for (int mt = m_first; mt < g.m_tiles; mt += m_step) {
+        if (pair_skipped(g, mt)) continue;
+        GT0();
+        mbar_wait_cluster(&tempty[acc], acc_phase ^ 1);
+        GT1(w_acc);
+        tc::fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BN2;
+        for (int kb = 0; kb < g.kb_total; ++kb) {
+          GT0();
+          tc::mbar_wait(&full[stage], phase);
+          GT1(w_full_c);
+          GT0();
+          mbar_wait_cluster(&peer_full[stage], phase);
+          GT1(w_peer);
+          tc::fence_after_sync();
+          const uint64_t dA = dA0 + (uint64_t)(stage * (A_STAGE >> 4));
+          const uint64_t dW = dW0 + (uint64_t)(kb * (WB_BYTES >> 4));
+          if (tc::elect_one()) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma_ss2(d_tmem, dA + 2 * k, dW + 2 * k, idesc, (kb | k) != 0);
+            umma_commit2_mc(&empty[stage], 3);
+            if (kb == g.kb_total - 1) umma_commit2_mc(&tfull[acc], 3);
+          }
+          __syncwarp();
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+#ifdef LG_GEMM_DEBUG
+        ++n_t;
+#endif
+      }
+#ifdef LG_GEMM_DEBUG
+      if (rec) { g_gemm_times[0] = w_acc; g_gemm_times[1] = w_full_c; g_gemm_times[7] = w_peer; g_gemm_times[2] = clock64() - t_begin; g_gemm_times[5] = n_t; g_gemm_times[3] = 0; g_gemm_times[4] = 0; g_gemm_times[6] = 0; }
+#endif
+    } else {
+      // ---------------------------------------------------------------- relay (peer CTA): tell the leader what has landed here
+      if (lane == 0) mbar_arrive_remote(peer_w, 0);
+      for (int mt = m_first; mt < g.m_tiles; mt += m_step) {
+        if (pair_skipped(g, mt)) continue;
+        for (int kb = 0; kb < g.kb_total; ++kb) {
+          tc::mbar_wait(&full[stage], phase);
+          if (lane == 0) mbar_arrive_remote(&peer_full[stage], 0);
+          __syncwarp();
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (8 warps): own 128 rows x 256 columns
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    const int c_warp = half * 64;
+    uint8_t* stg_out = smem + L::OFF_SOUT + ew * STG;
+    uint8_t* stg_in = smem + L::OFF_SIN + ew * STG;
+    const uint32_t my_row_off = (uint32_t)lane * 128u;
+    const uint32_t sw = (uint32_t)(lane & 7);
+    const float sc = g.scale[0];
+    const bool use_in = g.has_in != 0;
+    int acc = 0;
+    uint32_t acc_phase = 0, n_in = 0;
+    for (int mt = m_first; mt < g.m_tiles; mt += m_step) {
+      if (pair_skipped(g, mt)) continue;
+      const int row0 = mt * 2 * BM + (int)crank * BM + quarter * 32;
+      const bool store_rows = !tile_skipped(g, 2 * mt + (int)crank);  // rows of a fully padded half stay untouched
+#pragma unroll 1
+      for (int cb = 0; cb < 2; ++cb) {
+        const int cw = cb * BN + c_warp;        // first column of this warp within the pair's 256
+        const int colg = pair_col0 + cw;        // global output column
+        if (use_in && lane == 0) {
+          if (KBIG) bulk_wait_read0();          // the input tile aliases the previous output tile
+          tc::mbar_arrive_expect_tx(&in_bar[ew], STG);
+          tc::tma_load_2d(stg_in, &maps.in, &in_bar[ew], colg, row0);  // residual rows
+        }
+        if (cb == 0) {
+          tc::mbar_wait(&tfull[acc], acc_phase);
+          tc::fence_after_sync();
+        }
+        uint32_t v[64];
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN2 + cw;
+        tc::tmem_ld32(t_addr, v);
+        tc::tmem_ld32(t_addr + 32, v + 32);
+        tc::tmem_ld_wait();
+        if (cb == 1) {  // the whole accumulator is in registers / stored: release it to the leader's issuer
+          tc::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) {
+            if (crank == 0) tc::mbar_arrive(&tempty[acc]);
+            else mbar_arrive_remote(&tempty[acc], 0);
+          }
+        }
+        uint32_t pk[32];
+        uint32_t in[32];
+        if (use_in) {
+          tc::mbar_wait(&in_bar[ew], n_in & 1);
+          ++n_in;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 t = *reinterpret_cast<const uint4*>(stg_in + my_row_off + ((j ^ sw) << 4));
+            in[4 * j] = t.x; in[4 * j + 1] = t.y; in[4 * j + 2] = t.z; in[4 * j + 3] = t.w;
+          }
+          __syncwarp();  // every lane has read the input tile before anyone overwrites it (aliasing)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const __nv_bfloat162 r = *reinterpret_cast<const __nv_bfloat162*>(&in[j]);
+            const float a = fmaf(__uint_as_float(v[2 * j]) + s_par[cw + 2 * j], sc, __low2float(r));
+            const float b = fmaf(__uint_as_float(v[2 * j + 1]) + s_par[cw + 2 * j + 1], sc, __high2float(r));
+            pk[j] = tc::pack_bf16(a, b);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            pk[j] = tc::pack_bf16((__uint_as_float(v[2 * j]) + s_par[cw + 2 * j]) * sc,
+                                  (__uint_as_float(v[2 * j + 1]) + s_par[cw + 2 * j + 1]) * sc);
+        }
+        if (!(KBIG && use_in)) {
+          if (lane == 0) bulk_wait_read0();  // previous store has finished reading stg_out
+          __syncwarp();
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(stg_out + my_row_off + ((j ^ sw) << 4)) =
+              make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && store_rows) {
+          tma_store_2d(&maps.out0, stg_out, colg, row0);
+          bulk_commit();
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (lane == 0) bulk_wait0();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();  // nobody exits (or frees TMEM) while the pair's MMAs / remote arrives may still touch it
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+// -----------------------------------------------------------------------------------------------------
+// CTA-pair kernel for the first FFN layer: K = 512 (two 256-wide sources), N = 512, LayerNorm + GELU epilogue.
+// Cluster of 4 = two pairs: pair p = ranks {2p, 2p+1} computes rows [0,256) x columns [256p, 256p+256) of the
+// cluster's 256-row super-tile.  Rank r holds W columns [128r, 128r+128) (resident) and A rows of parity r&1;
+// the two CTAs of one parity (r, r^2) each load half of that 128-row A stage and multicast it to both.
+// LayerNorm: a row's 512 columns live in CTAs r and r^2 (256 each); per-row (sum, sum^2) partials are exchanged
+// with st.async.  The 256 accumulator columns of a CTA do not fit in registers, so the epilogue reads TMEM twice:
+// pass 1 statistics, pass 2 normalise + GELU + store.
+struct LayPL {
+  static constexpr int NSTAGE = 3;
+  static constexpr int W_BYTES = 128 * 1024;
+  static constexpr int OFF_A = W_BYTES;
+  static constexpr int OFF_SOUT = OFF_A + NSTAGE * A_STAGE;
+  static constexpr int OFF_PAR = OFF_SOUT + 8 * STG;        // bias | gamma | beta, 3 x 256 floats
+  static constexpr int OFF_STATS = OFF_PAR + 3 * 256 * 4;   // [2 bufs][4 slots][128 rows] float2
+  static constexpr int OFF_BAR = OFF_STATS + 2 * 4 * 128 * 8;
+  static constexpr int SMEM = OFF_BAR + 256;
+};
+
+__global__ void __launch_bounds__(320, 1)
+tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
+  using L = LayPL;
+  constexpr int NSTAGE = L::NSTAGE;
+  constexpr int BN2 = 256;
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + L::OFF_A;
+  float* s_par = reinterpret_cast<float*>(smem + L::OFF_PAR);
+  float2* s_stats = reinterpret_cast<float2*>(smem + L::OFF_STATS);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* empty = full + NSTAGE;
+  uint64_t* peer_full = empty + NSTAGE;
+  uint64_t* tfull = peer_full + NSTAGE;  // [2]
+  uint64_t* tempty = tfull + 2;          // [2]
+  uint64_t* w_full = tempty + 2;
+  uint64_t* peer_w = w_full + 1;
+  uint64_t* stats_bar = peer_w + 1;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stats_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_rank();        // 0..3
+  const uint32_t parity = crank & 1;            // A row half; 0 = leader of its pair
+  const uint32_t pair = crank >> 1;             // column half of the 512-wide output
+  const uint32_t partner = crank ^ 2;           // same rows, other 256 columns
+  const int cid = (int)cluster_id_x(), ncl = (int)n_clusters_x();
+  const int n0 = (int)crank * BN;               // resident W block
+  const int pair_col0 = (int)pair * BN2;
+  const uint16_t mc_mask = (uint16_t)((1u << crank) | (1u << partner));
+
+  if ((tc::smem_u32(smem) & 1023u) != 0) __trap();
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&maps.a0);
+    tc::prefetch_tmap(&maps.a1);
+    tc::prefetch_tmap(&maps.w);
+    tc::prefetch_tmap(&maps.out0);
+    for (int i = 0; i < NSTAGE; ++i) {
+      tc::mbar_init(&full[i], 1);
+      tc::mbar_init(&empty[i], 2);  // both pairs of the cluster have consumed the stage
+      tc::mbar_init(&peer_full[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&tfull[i], 1);
+      tc::mbar_init(&tempty[i], 16);
+      tc::mbar_init(&stats_bar[i], 1);
+    }
+    tc::mbar_init(w_full, 1);
+    tc::mbar_init(peer_w, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc2(tmem_slot, 512);
+  for (int i = threadIdx.x; i < BN2; i += blockDim.x) {
+    s_par[i] = g.bias[pair_col0 + i];
+    s_par[BN2 + i] = g.gamma[pair_col0 + i];
+    s_par[2 * BN2 + i] = g.beta[pair_col0 + i];
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer: half of this parity's A stage, multicast
+    if (tc::elect_one()) {
+      tc::mbar_arrive_expect_tx(w_full, g.kb_total * WB_BYTES);
+      for (int kb = 0; kb < g.kb_total; ++kb) tc::tma_load_2d(sW + kb * WB_BYTES, &maps.w, w_full, kb * BK, n0);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int mt = cid; mt < g.m_tiles; mt += ncl) {
+      if (pair_skipped(g, mt)) continue;
+      const int row = mt * 2 * BM + (int)parity * BM + (int)pair * 64;  // this CTA loads 64 of the 128 rows
+      for (int kb = 0; kb < g.kb_total; ++kb) {
+        tc::mbar_wait(&empty[stage], phase ^ 1);
+        const CUtensorMap* tm = kb < g.kb_a0 ? &maps.a0 : &maps.a1;
+        const int kc = (kb < g.kb_a0 ? kb : kb - g.kb_a0) * BK;
+        if (tc::elect_one()) {
+          tc::mbar_arrive_expect_tx(&full[stage], A_STAGE);
+          tma_load_2d_mc(sA + stage * A_STAGE + (int)pair * (64 * 128), tm, &full[stage], kc, row, mc_mask);
+          if (g.prefetch_tiles > 0) {
+            const int mp = mt + g.prefetch_tiles * ncl;
+            if (mp < g.m_tiles) tma_prefetch_l2(tm, kc, mp * 2 * BM + (int)parity * BM + (int)pair * 64);
+          }
+        }
+        __syncwarp();
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    tc::mbar_wait(w_full, 0);
+    if (parity == 0) {
+      // ---------------------------------------------------------------- MMA issuer (leader of the pair)
+      constexpr uint32_t idesc = tc::idesc_bf16(256, BN2, 0);
+      const uint16_t pair_mask = (uint16_t)(3u << (2 * pair));
+      mbar_wait_cluster(peer_w, 0);
+      const uint64_t dW0 = tc::smem_desc_sw128(tc::smem_u32(sW), 0, 1024);
+      const uint64_t dA0 = tc::smem_desc_sw128(tc::smem_u32(sA), 0, 1024);
+#ifdef LG_GEMM_DEBUG
+      long long w_acc = 0, w_full_c = 0, w_peer = 0, t_begin = clock64(), tt;
+      int n_t = 0;
+      const bool rec = blockIdx.x == 0 && lane == 0;
+#endif
+      for (int mt = cid; mt < g.m_tiles; mt += ncl) {
+        if (pair_skipped(g, mt)) continue;
+        GT0();
+        mbar_wait_cluster(&tempty[acc], acc_phase ^ 1);
+        GT1(w_acc);
+        tc::fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BN2;
+        for (int kb = 0; kb < g.kb_total; ++kb) {
+          GT0();
+          tc::mbar_wait(&full[stage], phase);
+          GT1(w_full_c);
+          GT0();
+          mbar_wait_cluster(&peer_full[stage], phase);
+          GT1(w_peer);
+          tc::fence_after_sync();
+          const uint64_t dA = dA0 + (uint64_t)(stage * (A_STAGE >> 4));
+          const uint64_t dW = dW0 + (uint64_t)(kb * (WB_BYTES >> 4));
+          if (tc::elect_one()) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma_ss2(d_tmem, dA + 2 * k, dW + 2 * k, idesc, (kb | k) != 0);
+            umma_commit2_mc(&empty[stage], 0xF);  // every CTA of the cluster fills stages of this pair's CTAs
+            if (kb == g.kb_total - 1) umma_commit2_mc(&tfull[acc], pair_mask);
+          }
+          __syncwarp();
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+#ifdef LG_GEMM_DEBUG
+        ++n_t;
+#endif
+      }
+#ifdef LG_GEMM_DEBUG
+      if (rec) { g_gemm_times[0] = w_acc; g_gemm_times[1] = w_full_c; g_gemm_times[7] = w_peer; g_gemm_times[2] = clock64() - t_begin; g_gemm_times[5] = n_t; }
+#endif
+    } else {
+      // ---------------------------------------------------------------- relay (odd rank): tell the pair's leader what has landed here
+      if (lane == 0) mbar_arrive_remote(peer_w, crank - 1);
+      for (int mt = cid; mt < g.m_tiles; mt += ncl) {
+        if (pair_skipped(g, mt)) continue;
+        for (int kb = 0; kb < g.kb_total; ++kb) {
+          tc::mbar_wait(&full[stage], phase);
+          if (lane == 0) mbar_arrive_remote(&peer_full[stage], crank - 1);
+          __syncwarp();
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (8 warps): own 128 rows x 256 columns
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    const int c_warp = half * 64;
+    uint8_t* stg_out = smem + L::OFF_SOUT + ew * STG;
+    const uint32_t my_row_off = (uint32_t)lane * 128u;
+    const uint32_t sw = (uint32_t)(lane & 7);
+    const int r_in_tile = quarter * 32 + lane;
+    int acc = 0, iter = 0;
+    uint32_t acc_phase = 0;
+#ifdef LG_GEMM_DEBUG
+    long long e_wait = 0, e_stats = 0, e_begin = clock64(), tt;
+    const bool rec = blockIdx.x == 0 && ew == 0 && lane == 0;
+#endif
+    for (int mt = cid; mt < g.m_tiles; mt += ncl) {
+      if (pair_skipped(g, mt)) continue;
+      const int row0 = mt * 2 * BM + (int)parity * BM + quarter * 32;
+      const bool store_rows = !tile_skipped(g, 2 * mt + (int)parity);  // rows of a fully padded half stay untouched
+      const int buf = iter & 1;
+      if (ew == 0 && lane == 0) tc::mbar_arrive_expect_tx(&stats_bar[buf], 4 * 128 * 8);  // 2 CTAs x 2 column halves
+      GT0();
+      tc::mbar_wait(&tfull[acc], acc_phase);
+      GT1(e_wait);
+      tc::fence_after_sync();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN2 + c_warp;
+      // ---- pass 1: statistics over this thread's 128 columns (2 blocks x 64)
+      float sum = 0.f, sq = 0.f;
+#pragma unroll 1
+      for (int cb = 0; cb < 2; ++cb) {
+        uint32_t v[64];
+        tc::tmem_ld32(t_row + cb * BN, v);
+        tc::tmem_ld32(t_row + cb * BN + 32, v + 32);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          const float x = __uint_as_float(v[j]) + s_par[cb * BN + c_warp + j];
+          sum += x;
+          sq = fmaf(x, x, sq);
+        }
+      }
+      {
+        const uint32_t slot = tc::smem_u32(&s_stats[(buf * 4 + (int)pair * 2 + half) * 128 + r_in_tile]);
+        const uint32_t bar = tc::smem_u32(&stats_bar[buf]);
+        st_async_f2(map_to_rank(slot, crank), sum, sq, map_to_rank(bar, crank));
+        st_async_f2(map_to_rank(slot, partner), sum, sq, map_to_rank(bar, partner));
+      }
+      GT0();
+      tc::mbar_wait(&stats_bar[buf], (iter >> 1) & 1);
+      GT1(e_stats);
+      float ts = 0.f, tq = 0.f;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float2 st = s_stats[(buf * 4 + p) * 128 + r_in_tile];
+        ts += st.x;
+        tq += st.y;
+      }
+      const float inv_n = 1.f / 512.f;
+      const float mean = ts * inv_n;
+      const float rstd = rsqrtf(fmaxf(tq * inv_n - mean * mean, 0.f) + 1e-5f);
+      const float nmr = -mean * rstd;
+      // ---- pass 2: normalise, GELU, store
+#pragma unroll 1
+      for (int cb = 0; cb < 2; ++cb) {
+        uint32_t v[64];
+        tc::tmem_ld32(t_row + cb * BN, v);
+        tc::tmem_ld32(t_row + cb * BN + 32, v + 32);
+        tc::tmem_ld_wait();
+        if (cb == 1) {  // accumulator fully consumed: release it to the pair's issuer
+          tc::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) {
+            if (parity == 0) tc::mbar_arrive(&tempty[acc]);
+            else mbar_arrive_remote(&tempty[acc], crank - 1);
+          }
+        }
+        const int cw = cb * BN + c_warp;
+        uint32_t pk[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int c = cw + 2 * j;
+          const float x0 = __uint_as_float(v[2 * j]) + s_par[c], x1 = __uint_as_float(v[2 * j + 1]) + s_par[c + 1];
+          const float a = gelu_act(fmaf(fmaf(x0, rstd, nmr), s_par[BN2 + c], s_par[2 * BN2 + c]));
+          const float b = gelu_act(fmaf(fmaf(x1, rstd, nmr), s_par[BN2 + c + 1], s_par[2 * BN2 + c + 1]));
+          pk[j] = tc::pack_bf16(a, b);
+        }
+        if (lane == 0) bulk_wait_read0();  // previous store has finished reading stg_out
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(stg_out + my_row_off + ((j ^ sw) << 4)) =
+              make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && store_rows) {
+          tma_store_2d(&maps.out0, stg_out, pair_col0 + cw, row0);
+          bulk_commit();
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      ++iter;
+    }
+    if (lane == 0) bulk_wait0();
+#ifdef LG_GEMM_DEBUG
+    if (rec) { g_gemm_times[3] = e_wait; g_gemm_times[4] = clock64() - e_begin; g_gemm_times[6] = e_stats; }
+#endif
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
 int make_map(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint32_t box_rows) {
   const uint64_t d[2] = {inner, rows}, s[1] = {inner * 2};
   const uint32_t b[2] = {64, box_rows};
@@ -529,6 +1129,84 @@ int launch(const Maps& maps, Args g, int n_blocks, cudaStream_t st) {
   if (clusters > need) clusters = need;
   if (clusters < g.n_groups) clusters = g.n_groups;
   cfg.gridDim = dim3(clusters * CL);
+  e = cudaLaunchKernelEx(&cfg, kern, maps, g);
+  if (e != cudaSuccess) return (int)e;
+  LG_LAUNCH_CHECK();
+  return LGB200_OK;
+}
+
+
+template <bool KBIG>
+int launch_pair_row(const Maps& maps, Args g, int N, cudaStream_t st) {
+  using L = Lay<KBIG>;
+  auto kern = tc_pair_row_kernel<KBIG>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM);
+  if (e != cudaSuccess) return (int)e;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  g.n_groups = N / 256;
+  g.m_tiles = g.m_tiles / 2;  // 256-row super-tiles
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(320);
+  cfg.dynamicSmemBytes = L::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    int n = 0;
+    cfg.gridDim = dim3(sms / 2 * 2);
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) n = sms / 2;
+    max_clusters = n;
+  }
+  int clusters = max_clusters / g.n_groups * g.n_groups;
+  const int need = g.m_tiles * g.n_groups;
+  if (clusters > need) clusters = need;
+  if (clusters < g.n_groups) clusters = g.n_groups;
+  cfg.gridDim = dim3(clusters * 2);
+  e = cudaLaunchKernelEx(&cfg, kern, maps, g);
+  if (e != cudaSuccess) return (int)e;
+  LG_LAUNCH_CHECK();
+  return LGB200_OK;
+}
+
+int launch_pair_ln(const Maps& maps, Args g, cudaStream_t st) {
+  auto kern = tc_pair_ln_kernel;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LayPL::SMEM);
+  if (e != cudaSuccess) return (int)e;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  g.n_groups = 1;
+  g.m_tiles = g.m_tiles / 2;  // 256-row super-tiles
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(320);
+  cfg.dynamicSmemBytes = LayPL::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 4;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    int n = 0;
+    cfg.gridDim = dim3(sms / 4 * 4);
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) n = sms / 4;
+    max_clusters = n;
+  }
+  int clusters = max_clusters;
+  if (clusters > g.m_tiles) clusters = g.m_tiles;
+  if (clusters < 1) clusters = 1;
+  cfg.gridDim = dim3(clusters * 4);
   e = cudaLaunchKernelEx(&cfg, kern, maps, g);
   if (e != cudaSuccess) return (int)e;
   LG_LAUNCH_CHECK();
@@ -596,8 +1274,27 @@ int lg_tc_linear_v2(int epilogue, const __nv_bfloat16* A0, const __nv_bfloat16* 
     }
   }
   const int n_blocks = N / BN;
+  // bit 1: CTA-pair kernel for the LayerNorm layer (default on: 150 vs 225 us at T = 262144);
+  // bit 0: CTA-pair kernel for the K = 512 ROW layer (default off: that layer already runs at 88 % of HBM peak, 93 us both ways)
+  static const int pair_mode = getenv("LGB200_GEMM_PAIR") ? atoi(getenv("LGB200_GEMM_PAIR")) : 2;
+  if (ln && (pair_mode & 2) && T % 256 == 0) {  // CTA-pair kernel: each CTA loads 64-row boxes of A
+    Maps pm = maps;
+    if ((rc = make_map(&pm.a0, A0, K0, T, 64))) return rc;
+    if ((rc = make_map(&pm.a1, A1, K - K0, T, 64))) return rc;
+    return launch_pair_ln(pm, g, st);
+  }
   if (ln) return launch<MODE_LN, 4, true>(maps, g, n_blocks, st);
   if (epilogue == LGB200_EPI_HEADS) return launch<MODE_HEADS, 2, false>(maps, g, n_blocks, st);
+  if (kbig && (pair_mode & 1) && T % 256 == 0) {  // CTA-pair kernel: the A boxes are 128 rows (no multicast inside a pair)
+    Maps pm = maps;
+    if ((rc = make_map(&pm.a0, A0, K0, T, BM))) return rc;
+    if (K0 < K) {
+      if ((rc = make_map(&pm.a1, A1, K - K0, T, BM))) return rc;
+    } else {
+      pm.a1 = pm.a0;
+    }
+    return launch_pair_row<true>(pm, g, N, st);
+  }
   if (kbig) return launch<MODE_ROW, 2, true>(maps, g, n_blocks, st);
   return launch<MODE_ROW, 2, false>(maps, g, n_blocks, st);
 }

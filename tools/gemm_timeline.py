@@ -30,7 +30,7 @@ def run(name, epi, N, K, **kw):
     ms = e0.elapsed_time(e1) / 5
     tiles = max(t[5], 1)
     print(f"{name}: {ms*1e3:.1f} us  {2.0*T*N*K/ms/1e9:.0f} TFLOP/s | per tile (cycles): mma-warp total {t[2]/tiles:.0f} = wait-acc {t[0]/tiles:.0f} + wait-A {t[1]/tiles:.0f} + issue; "
-          f"epilogue total {t[4]/tiles:.0f}, wait-tfull {t[3]/tiles:.0f}, wait-stats {t[6]/tiles:.0f}  (tiles/CTA {tiles})")
+          f"epilogue total {t[4]/tiles:.0f}, wait-tfull {t[3]/tiles:.0f}, wait-stats {t[6]/tiles:.0f}, wait-peer {t[7]/tiles:.0f}  (tiles/CTA {tiles})")
 hid = torch.empty(T, 512, device="cuda", dtype=torch.bfloat16)
 g = torch.ones(512, device="cuda"); be = torch.zeros(512, device="cuda")
 run("FFN1 LN  K512 N512", EPI_LN_GELU, 512, 512, A1=y, K0=256, out16=hid, gamma=g, beta=be)
