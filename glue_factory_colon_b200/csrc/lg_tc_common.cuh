@@ -246,3 +246,6 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // bf16 tensor, innermost dimension contiguous, 128-byte swizzle, box inner extent 64 elements.
 int lg_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                       const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box);
+// same with a 64-byte swizzle (box inner extent 32 elements)
+int lg_make_tmap_bf16_sw(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box, int swizzle_bytes);

@@ -36,6 +36,11 @@ static PFN_encodeTiled lg_get_encode() {
 
 int lg_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                       const uint64_t* strides_bytes, const uint32_t* box) {
+  return lg_make_tmap_bf16_sw(out, base, rank, dims, strides_bytes, box, 128);
+}
+
+int lg_make_tmap_bf16_sw(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
   PFN_encodeTiled enc = lg_get_encode();
   if (!enc) return LGB200_ERR_DRIVER;
   cuuint64_t gdim[5];
@@ -48,7 +53,8 @@ int lg_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64
     if (i + 1 < rank) gstr[i] = strides_bytes[i];
   }
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr,
-                   bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? LGB200_OK : LGB200_ERR_DRIVER;
 }

@@ -50,7 +50,8 @@ struct Lay {
   static constexpr int OFF_A = W_BYTES;
   static constexpr int OFF_SOUT = OFF_A + NSTAGE * A_STAGE;
   static constexpr int OFF_SIN = KBIG ? OFF_SOUT : OFF_SOUT + 8 * STG;  // K = 512: input aliases output tile
-  static constexpr int OFF_PAR = OFF_SIN + 8 * STG;                     // bias | gamma | beta (3 x 128 floats)
+  static constexpr int OFF_PAR = OFF_SIN + (KBIG ? 8 : 16) * STG;       // (K <= 256: two input tiles per warp, see the
+                                                                        //  rotary prefetch) then bias | gamma | beta
   static constexpr int OFF_STATS = OFF_PAR + 3 * BN * 4;                // [2][8 slots][128 rows] float2
   static constexpr int OFF_BAR = OFF_STATS + (KBIG ? 2 * 8 * 128 * 8 : 0);
   static constexpr int SMEM = OFF_BAR + 256;
@@ -197,8 +198,8 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
   uint64_t* tempty = tfull + 2;      // [2]
   uint64_t* w_full = tempty + 2;
   uint64_t* stats_bar = w_full + 1;  // [2]
-  uint64_t* in_bar = stats_bar + 2;  // [8] one per epilogue warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_bar + 8);
+  uint64_t* in_bar = stats_bar + 2;  // [16] two per epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_bar + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = CL > 1 ? cluster_rank() : 0;
@@ -223,7 +224,7 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
       tc::mbar_init(&tempty[i], 8);
       tc::mbar_init(&stats_bar[i], 1);
     }
-    for (int i = 0; i < 8; ++i) tc::mbar_init(&in_bar[i], 1);
+    for (int i = 0; i < 16; ++i) tc::mbar_init(&in_bar[i], 1);
     tc::mbar_init(w_full, 1);
     tc::fence_barrier_init();
   }
@@ -347,10 +348,35 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
     long long e_wait = 0, e_stats = 0, e_begin = clock64(), tt;
     const bool rec = blockIdx.x == 0 && ew == 0 && lane == 0;
 #endif
+    // HEADS: the rotary rows of the NEXT tile are fetched while this tile is processed (two input tiles per warp).
+    // Fetching them at the top of the tile's own iteration left the ~1.5 us load exposed whenever the accumulator
+    // was already waiting (the QKV projection was epilogue-bound: the issuer waited 38 % of its time for TMEM).
+    constexpr bool PF = MODE == MODE_HEADS && !KBIG;
+    auto next_tile = [&](int mt) {
+      for (mt += m_step; mt < g.m_tiles && tile_skipped(g, mt); mt += m_step) {}
+      return mt;
+    };
+    if (PF && use_in && lane == 0) {
+      int mt0 = m_first;
+      if (mt0 < g.m_tiles && tile_skipped(g, mt0)) mt0 = next_tile(mt0);
+      if (mt0 < g.m_tiles) {
+        tc::mbar_arrive_expect_tx(&in_bar[ew], STG);
+        tc::tma_load_2d(stg_in, &maps.in, &in_bar[ew], 0, mt0 * BM + quarter * 32);
+      }
+    }
     for (int mt = m_first; mt < g.m_tiles; mt += m_step) {
       if (tile_skipped(g, mt)) continue;
       const int row0 = mt * BM + quarter * 32;  // first global row of this warp
-      if (use_in && lane == 0) {
+      if (PF) {
+        if (use_in && lane == 0) {
+          const int mn = next_tile(mt);
+          if (mn < g.m_tiles) {  // buffer (iter+1)&1 was read in the previous iteration (all lanes, then __syncwarp)
+            const int nb_ = (iter + 1) & 1;
+            tc::mbar_arrive_expect_tx(&in_bar[nb_ * 8 + ew], STG);
+            tc::tma_load_2d(stg_in + nb_ * 8 * STG, &maps.in, &in_bar[nb_ * 8 + ew], 0, mn * BM + quarter * 32);
+          }
+        }
+      } else if (use_in && lane == 0) {
         if (KBIG) bulk_wait_read0();            // input tile aliases the previous output tile
         tc::mbar_arrive_expect_tx(&in_bar[ew], STG);
         if (MODE == MODE_ROW) tc::tma_load_2d(stg_in, &maps.in, &in_bar[ew], col0, row0);  // residual rows
@@ -412,10 +438,16 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
       } else {
         uint32_t in[32];
         if (use_in) {
-          tc::mbar_wait(&in_bar[ew], iter & 1);
+          const uint8_t* tin = stg_in;
+          if (PF) {
+            tc::mbar_wait(&in_bar[(iter & 1) * 8 + ew], (iter >> 1) & 1);
+            tin = stg_in + (iter & 1) * 8 * STG;
+          } else {
+            tc::mbar_wait(&in_bar[ew], iter & 1);
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const uint4 t = *reinterpret_cast<const uint4*>(stg_in + my_row_off + ((j ^ sw) << 4));
+            const uint4 t = *reinterpret_cast<const uint4*>(tin + my_row_off + ((j ^ sw) << 4));
             in[4 * j] = t.x; in[4 * j + 1] = t.y; in[4 * j + 2] = t.z; in[4 * j + 3] = t.w;
           }
           __syncwarp();  // every lane has read the input tile before anyone overwrites it (aliasing)
@@ -811,13 +843,13 @@ struct LayPL {
   static constexpr int W_BYTES = 128 * 1024;
   static constexpr int OFF_A = W_BYTES;
   static constexpr int OFF_SOUT = OFF_A + NSTAGE * A_STAGE;
-  static constexpr int OFF_PAR = OFF_SOUT + 8 * STG;        // bias | gamma | beta, 3 x 256 floats
-  static constexpr int OFF_STATS = OFF_PAR + 3 * 256 * 4;   // [2 bufs][4 slots][128 rows] float2
-  static constexpr int OFF_BAR = OFF_STATS + 2 * 4 * 128 * 8;
+  static constexpr int OFF_PAR = OFF_SOUT + 16 * 2048;      // 16 epilogue warps x (32 rows x 64 B); then bias | gamma | beta, 3 x 256 floats
+  static constexpr int OFF_STATS = OFF_PAR + 3 * 256 * 4;   // [2 bufs][2 CTAs][128 rows] float2 | local scratch [4][128] float2
+  static constexpr int OFF_BAR = OFF_STATS + 2 * 2 * 128 * 8 + 2 * 4 * 128 * 8;  // exchanged partials + 2 local scratch buffers
   static constexpr int SMEM = OFF_BAR + 256;
 };
 
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(576, 1)
 tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
   using L = LayPL;
   constexpr int NSTAGE = L::NSTAGE;
@@ -862,7 +894,7 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
     }
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&tfull[i], 1);
-      tc::mbar_init(&tempty[i], 16);
+      tc::mbar_init(&tempty[i], 32);  // 16 epilogue warps in each CTA of the pair
       tc::mbar_init(&stats_bar[i], 1);
     }
     tc::mbar_init(w_full, 1);
@@ -973,15 +1005,17 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (8 warps): own 128 rows x 256 columns
-    const int ew = warp - 2;
+    // ------------------------------------------------------------------ epilogue (16 warps): own 128 rows x 256 columns
+    // warp = (TMEM lane quarter, 32-column slice cq of each 128-column block).  With 8 warps (2 per SM sub-partition)
+    // the epilogue was busy 6600 cycles per 256-row super-tile against ~3500 issue cycles of work.
+    const int ew = warp - 2;        // 0..15
     const int quarter = warp & 3;
-    const int half = ew >> 2;
-    const int c_warp = half * 64;
-    uint8_t* stg_out = smem + L::OFF_SOUT + ew * STG;
-    const uint32_t my_row_off = (uint32_t)lane * 128u;
-    const uint32_t sw = (uint32_t)(lane & 7);
+    const int cq = ew >> 2;         // 0..3
+    uint8_t* stg_out = smem + L::OFF_SOUT + ew * 2048;  // 32 rows x 64 B, 64-byte swizzle
+    const uint32_t my_row_off = (uint32_t)lane * 64u;
+    const uint32_t sw = (uint32_t)((lane >> 1) & 3);
     const int r_in_tile = quarter * 32 + lane;
+    float2* s_local0 = s_stats + 2 * 2 * 128;  // [2 bufs][4 cq][128 rows] partials of this CTA
     int acc = 0, iter = 0;
     uint32_t acc_phase = 0;
 #ifdef LG_GEMM_DEBUG
@@ -993,29 +1027,38 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
       const int row0 = mt * 2 * BM + (int)parity * BM + quarter * 32;
       const bool store_rows = !tile_skipped(g, 2 * mt + (int)parity);  // rows of a fully padded half stay untouched
       const int buf = iter & 1;
-      if (ew == 0 && lane == 0) tc::mbar_arrive_expect_tx(&stats_bar[buf], 4 * 128 * 8);  // 2 CTAs x 2 column halves
+      if (ew == 0 && lane == 0) tc::mbar_arrive_expect_tx(&stats_bar[buf], 2 * 128 * 8);  // one partial per row from each CTA
       GT0();
       tc::mbar_wait(&tfull[acc], acc_phase);
       GT1(e_wait);
       tc::fence_after_sync();
-      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN2 + c_warp;
-      // ---- pass 1: statistics over this thread's 128 columns (2 blocks x 64)
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN2 + cq * 32;
+      // ---- pass 1: statistics over this thread's 64 columns (2 blocks x 32)
       float sum = 0.f, sq = 0.f;
-#pragma unroll 1
+#pragma unroll
       for (int cb = 0; cb < 2; ++cb) {
-        uint32_t v[64];
+        uint32_t v[32];
         tc::tmem_ld32(t_row + cb * BN, v);
-        tc::tmem_ld32(t_row + cb * BN + 32, v + 32);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
-          const float x = __uint_as_float(v[j]) + s_par[cb * BN + c_warp + j];
+        for (int j = 0; j < 32; ++j) {
+          const float x = __uint_as_float(v[j]) + s_par[cb * BN + cq * 32 + j];
           sum += x;
           sq = fmaf(x, x, sq);
         }
       }
-      {
-        const uint32_t slot = tc::smem_u32(&s_stats[(buf * 4 + (int)pair * 2 + half) * 128 + r_in_tile]);
+      // the 4 column slices of a row are summed inside the CTA first, then ONE partial per row goes to both CTAs
+      float2* s_local = s_local0 + buf * 4 * 128;
+      s_local[cq * 128 + r_in_tile] = make_float2(sum, sq);
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
+      if (cq == 0) {
+#pragma unroll
+        for (int p = 1; p < 4; ++p) {
+          const float2 o = s_local[p * 128 + r_in_tile];
+          sum += o.x;
+          sq += o.y;
+        }
+        const uint32_t slot = tc::smem_u32(&s_stats[(buf * 2 + (int)pair) * 128 + r_in_tile]);
         const uint32_t bar = tc::smem_u32(&stats_bar[buf]);
         st_async_f2(map_to_rank(slot, crank), sum, sq, map_to_rank(bar, crank));
         st_async_f2(map_to_rank(slot, partner), sum, sq, map_to_rank(bar, partner));
@@ -1023,23 +1066,16 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
       GT0();
       tc::mbar_wait(&stats_bar[buf], (iter >> 1) & 1);
       GT1(e_stats);
-      float ts = 0.f, tq = 0.f;
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const float2 st = s_stats[(buf * 4 + p) * 128 + r_in_tile];
-        ts += st.x;
-        tq += st.y;
-      }
+      const float2 st0 = s_stats[(buf * 2 + 0) * 128 + r_in_tile], st1 = s_stats[(buf * 2 + 1) * 128 + r_in_tile];
       const float inv_n = 1.f / 512.f;
-      const float mean = ts * inv_n;
-      const float rstd = rsqrtf(fmaxf(tq * inv_n - mean * mean, 0.f) + 1e-5f);
+      const float mean = (st0.x + st1.x) * inv_n;
+      const float rstd = rsqrtf(fmaxf((st0.y + st1.y) * inv_n - mean * mean, 0.f) + 1e-5f);
       const float nmr = -mean * rstd;
       // ---- pass 2: normalise, GELU, store
-#pragma unroll 1
+#pragma unroll
       for (int cb = 0; cb < 2; ++cb) {
-        uint32_t v[64];
+        uint32_t v[32];
         tc::tmem_ld32(t_row + cb * BN, v);
-        tc::tmem_ld32(t_row + cb * BN + 32, v + 32);
         tc::tmem_ld_wait();
         if (cb == 1) {  // accumulator fully consumed: release it to the pair's issuer
           tc::fence_before_sync();
@@ -1049,10 +1085,10 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
             else mbar_arrive_remote(&tempty[acc], crank - 1);
           }
         }
-        const int cw = cb * BN + c_warp;
-        uint32_t pk[32];
+        const int cw = cb * BN + cq * 32;
+        uint32_t pk[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < 16; ++j) {
           const int c = cw + 2 * j;
           const float x0 = __uint_as_float(v[2 * j]) + s_par[c], x1 = __uint_as_float(v[2 * j + 1]) + s_par[c + 1];
           const float a = gelu_act(fmaf(fmaf(x0, rstd, nmr), s_par[BN2 + c], s_par[2 * BN2 + c]));
@@ -1062,13 +1098,13 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
         if (lane == 0) bulk_wait_read0();  // previous store has finished reading stg_out
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < 4; ++j)
           *reinterpret_cast<uint4*>(stg_out + my_row_off + ((j ^ sw) << 4)) =
               make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         tc::fence_proxy_async();
         __syncwarp();
         if (lane == 0 && store_rows) {
-          tma_store_2d(&maps.out0, stg_out, pair_col0 + cw, row0);
+          tma_store_2d(&maps.out1, stg_out, pair_col0 + cw, row0);  // out1: 32-column boxes, 64-byte swizzle
           bulk_commit();
         }
       }
@@ -1186,7 +1222,7 @@ int launch_pair_ln(const Maps& maps, Args g, cudaStream_t st) {
   g.n_groups = 1;
   g.m_tiles = g.m_tiles / 2;  // 256-row super-tiles
   cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(320);
+  cfg.blockDim = dim3(576);
   cfg.dynamicSmemBytes = LayPL::SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1281,6 +1317,11 @@ int lg_tc_linear_v2(int epilogue, const __nv_bfloat16* A0, const __nv_bfloat16* 
     Maps pm = maps;
     if ((rc = make_map(&pm.a0, A0, K0, T, 64))) return rc;
     if ((rc = make_map(&pm.a1, A1, K - K0, T, 64))) return rc;
+    {  // output boxes of 32 rows x 32 columns, 64-byte swizzle (one per epilogue warp and column block)
+      const uint64_t d[2] = {(uint64_t)N, (uint64_t)T}, sb[1] = {(uint64_t)N * 2};
+      const uint32_t bx[2] = {32, 32};
+      if ((rc = lg_make_tmap_bf16_sw(&pm.out1, epi.out16, 2, d, sb, bx, 64))) return rc;
+    }
     return launch_pair_ln(pm, g, st);
   }
   if (ln) return launch<MODE_LN, 4, true>(maps, g, n_blocks, st);
