@@ -15,6 +15,8 @@
 // Scores arrive in the log2 domain (the Q projection epilogue folds log2(e)/sqrt(64)).
 // Keys >= lens[kv sequence] are masked to -inf; query rows >= lens[q sequence] are not stored.
 //
+// r1 instruction diet (the loop is issue-bound): max subtraction folded into the QK^T MMA (LG_ATTN_MSUB, 0.721 ->
+// 0.697 ms), polynomial share retuned to 3/16 (0.681), packed f32x2 row sum (0.675 ms = 814 TFLOP/s).
 // Structures tried against this one at S=128, Lp=2048 (0.72 ms), all parity-green, none faster (git history,
 // DESIGN.md section 3.2): persistent CTAs with a dynamic work ring (0.74-0.75), issuer/producer at the highest
 // warp ids (0.75), sleeping waits for issuer/producer (no change), four "fat" softmax warps with one thread per
@@ -33,9 +35,13 @@ __device__ long long g_attn_times[2 * 16 * 16];
 // same time (MUFU 100 % busy for ~2000 cycles) and then all leave it idle for ~1000 (measured timeline).
 __device__ unsigned int g_attn_sm_slot[1024];
 
-#ifndef LG_ATTN_POLY
-#define LG_ATTN_POLY 2  // one exponential in (2 * LG_ATTN_POLY) is evaluated by polynomial on the FMA pipe
+#ifndef LG_ATTN_MSUB
+#define LG_ATTN_MSUB 1  // 1: the row-max subtraction s - m_ref is folded into the QK^T MMA (a fifth K=16 slice)
 #endif
+#ifndef LG_ATTN_POLY16
+#define LG_ATTN_POLY16 3  // LG_ATTN_POLY16 of every 16 exponentials are evaluated by polynomial on the FMA pipe (0..8)
+#endif
+#define LG_POLY_HERE(i) ((((i) * LG_ATTN_POLY16) % 8) < LG_ATTN_POLY16)
 
 namespace {
 
@@ -43,7 +49,10 @@ constexpr int AT_BM = 128;   // queries per CTA
 constexpr int AT_BN = 128;   // keys per step
 constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16, 128B-swizzled
 constexpr int KST = 3, VST = 2;            // K / V ring depth
-constexpr int AT_SMEM = TILE_BYTES * (1 + KST + VST) + 192 + 6 * 128 * 4;  // + max/sum exchange
+constexpr int XT_BYTES = 128 * 16 * 2;     // 4 KB: 128 rows x 16 bf16 (one K=16 MMA slice), 32-byte swizzle
+constexpr int AT_XOFF = TILE_BYTES * (1 + KST + VST);             // Q_ext | K_ext (LG_ATTN_MSUB)
+constexpr int AT_BAROFF = AT_XOFF + (LG_ATTN_MSUB ? 2 * XT_BYTES : 0);
+constexpr int AT_SMEM = AT_BAROFF + 192 + 6 * 128 * 4;  // + barriers + max/sum exchange
 
 constexpr uint32_t TM_S = 0, TM_P = 128, TM_O = 192, TM_COLS = 256;
 
@@ -57,7 +66,9 @@ __device__ __forceinline__ float ex2(float x) {
 // this kernel at d = 64): round-to-nearest split x = n + f, |f| <= 0.5, degree-3 minimax polynomial
 // (max rel. err 1.0e-4, far below the bf16 rounding of P), exponent patched in with integer ops.
 // tools/micro/softmax_rate.cu: 13.7 -> 15.3 elements/clk/SM with one exponential in four done this way;
-// in this kernel 0.774 -> 0.717 ms per launch at S=128, Lp=2048 (LG_ATTN_POLY=2; 3 gives 0.730).
+// In this kernel at S=128, Lp=2048, with the subtraction folded into the MMA (LG_ATTN_MSUB), polynomial share of
+// 0 / 1 / 2 / 3 / 4 / 5 / 6 / 8 sixteenths: 0.728 / 0.705 / 0.693 / 0.681 / 0.690 / 0.703 / 0.731 / 0.764 ms -- the
+// polynomial costs 8 issue slots against 1 for MUFU, and the loop is bound by issue slots as much as by MUFU.
 __device__ __forceinline__ float ex2_poly(float x) {
   x = fmaxf(x, -126.f);
   const float t = x + 12582912.f;
@@ -113,7 +124,9 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* sQ = smem;
   uint8_t* sK = smem + TILE_BYTES;              // KST stages
   uint8_t* sV = smem + (1 + KST) * TILE_BYTES;  // VST stages
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (1 + KST + VST) * TILE_BYTES);
+  uint8_t* sQx = smem + AT_XOFF;             // [128 queries][16] bf16: column 0 = -m_ref(row), rest 0
+  uint8_t* sKx = sQx + XT_BYTES;             // [128 keys][16] bf16: 1 in the first element of each 16-byte chunk
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_BAROFF);
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;             // [KST]
   uint64_t* k_empty = k_full + KST;        // [KST]
@@ -124,7 +137,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* p_ready = s_free + 1;
   uint64_t* pv_done = p_ready + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
-  float* s_xch = reinterpret_cast<float*>(smem + (1 + KST + VST) * TILE_BYTES + 192);  // [6][128]
+  float* s_xch = reinterpret_cast<float*>(smem + AT_BAROFF + 192);  // [6][128]
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmQ);
@@ -139,6 +152,18 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tc::mbar_init(pv_done, 1);
     tc::fence_barrier_init();
   }
+#if LG_ATTN_MSUB
+  // S' = Q.K^T + Q_ext.K_ext^T = s - m_ref: the softmax loop then needs no subtraction (64 of its ~480 instructions
+  // per 32x64 block; the loop is issue-bound).  Q_ext starts at 0 and is rewritten by the softmax threads whenever the
+  // reference maximum of a row moves (first tile, then only when the maximum grows by > 8); m_ref is kept bf16-exact.
+  // K_ext carries a 1 at the start of BOTH 16-byte chunks of a row, so the product is -m_ref whichever chunk the
+  // 32-byte swizzle maps Q_ext's single non-zero element to.
+  if (threadIdx.x < 256) {
+    reinterpret_cast<uint4*>(sQx)[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
+    reinterpret_cast<uint4*>(sKx)[threadIdx.x] = make_uint4(0x00003f80u, 0u, 0u, 0u);
+  }
+  tc::fence_proxy_async();
+#endif
   if (warp == 1) tc::tmem_alloc(tmem_slot, TM_COLS);
   if (threadIdx.x == 64 && stagger_ns > 0) {
     unsigned smid;
@@ -182,6 +207,10 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint64_t dK0 = tc::smem_desc_sw128(tc::smem_u32(sK), 0, 1024);
     const uint64_t dV0 = tc::smem_desc_sw128(tc::smem_u32(sV), TILE_BYTES, 1024);
     const uint32_t tS = tmem + TM_S, tP = tmem + TM_P, tO = tmem + TM_O;
+#if LG_ATTN_MSUB
+    const uint64_t dQx = tc::smem_desc_sw32(tc::smem_u32(sQx), 256);
+    const uint64_t dKx = tc::smem_desc_sw32(tc::smem_u32(sKx), 256);
+#endif
     int ks = 0, vs = 0;            // ring positions of the next K tile to multiply / V tile to consume
     uint32_t kph = 0, vph = 0;
     auto issue_qk = [&]() {        // S = Q . K[ks]^T
@@ -190,6 +219,9 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           if (dbg != 6) tc::umma_ss(tS, dQ + 2 * k, dK + 2 * k, idesc_qk, k != 0);
+#if LG_ATTN_MSUB
+        tc::umma_ss(tS, dQx, dKx, idesc_qk, 1);
+#endif
         tc::umma_commit(s_full);
         if (CL > 1) tc::umma_commit_mc(&k_empty[ks], MC_MASK);  // K stage free once this QK^T retires
         else tc::umma_commit(&k_empty[ks]);
@@ -252,9 +284,11 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tc::tmem_ld32(tmem + lane_base + TM_S + half * 64 + 32, sv + 32);
       tc::tmem_ld_wait();
       STAMP(2);
+#if !LG_ATTN_MSUB
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(s_free);
+#endif
       STAMP(3);
       const int valid = nk - j * AT_BN - half * 64;  // valid keys among this thread's 64 columns
       if (valid < 64) {
@@ -262,19 +296,6 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int i = 0; i < 64; ++i) {
           if (i >= valid) sv[i] = 0xff800000u;  // -inf
         }
-      }
-      if (dbg >= 4 && dbg <= 6) {  // pipeline skeleton only: no softmax math
-        uint32_t pz[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) pz[i] = sv[i] & 0x3f803f80u;
-        if (j > 0) { tc::mbar_wait(pv_done, (j - 1) & 1); tc::fence_after_sync(); }
-        tc::tmem_st32(tmem + lane_base + TM_P + half * 32, pz);
-        tc::tmem_st_wait();
-        tc::fence_before_sync();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(p_ready);
-        l_part = 1.f;
-        continue;
       }
       float mxs[4];
 #pragma unroll
@@ -286,35 +307,85 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
       mx = fmaxf(mx, s_xch[((j & 1) * 2 + (half ^ 1)) * 128 + r]);
       STAMP(4);
+      float rsum[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t pk[32];
+#if LG_ATTN_MSUB
+      // scores arrive relative to m_ref (0 on the first tile).  Move the reference only on the first tile and when
+      // the maximum grew by more than 8 (factor 256); the new reference is rounded to bf16 so that the MMA subtracts
+      // exactly what this thread accounts for.
+      float delta = 0.f;
+      const bool move = j == 0 || mx > 8.f;
+      if (move) {
+        const float base = j == 0 ? 0.f : m_ref;
+        const __nv_bfloat16 mb = __float2bfloat16_rn(base + mx);
+        const float m_abs = __bfloat162float(mb);
+        delta = m_abs - base;
+        m_ref = m_abs;
+        if (half == 0) {  // row r of Q_ext: 32-byte rows, the non-zero element at byte 0 of the row
+          const __nv_bfloat16 neg = __float2bfloat16_rn(-m_abs);
+          *reinterpret_cast<unsigned short*>(sQx + r * 32) = *reinterpret_cast<const unsigned short*>(&neg);
+        }
+        tc::fence_proxy_async();  // generic-proxy write -> visible to the next QK^T (async proxy)
+      }
+      const float alpha = j == 0 ? 0.f : ex2(-delta);  // 1 when unchanged
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(s_free);  // S is in registers and Q_ext is up to date: QK^T(j+1) may go
+      const bool any_move = __any_sync(0xffffffffu, move);
+      if (any_move) {  // rare: this tile was produced with the old reference
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float p0 = __uint_as_float(sv[2 * i]) - delta, p1 = __uint_as_float(sv[2 * i + 1]) - delta;
+          p0 = ex2(p0);
+          p1 = LG_POLY_HERE(i) ? ex2_poly(p1) : ex2(p1);
+          rsum[i & 3] += p0 + p1;
+          pk[i] = tc::pack_bf16(p0, p1);
+        }
+      } else {
+#ifndef LG_ATTN_NO_SUM2  // packed f32x2 row sum: one issue slot per pair instead of two (0.682 -> 0.675 ms)
+        float2 rs2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float p0 = ex2(__uint_as_float(sv[2 * i])), p1 = __uint_as_float(sv[2 * i + 1]);
+          p1 = LG_POLY_HERE(i) ? ex2_poly(p1) : ex2(p1);
+          rs2[i & 1] = __fadd2_rn(rs2[i & 1], make_float2(p0, p1));
+          pk[i] = tc::pack_bf16(p0, p1);
+        }
+        rsum[0] = rs2[0].x; rsum[1] = rs2[0].y; rsum[2] = rs2[1].x; rsum[3] = rs2[1].y;
+#else
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float p0 = ex2(__uint_as_float(sv[2 * i])), p1 = __uint_as_float(sv[2 * i + 1]);
+          p1 = LG_POLY_HERE(i) ? ex2_poly(p1) : ex2(p1);
+          rsum[i & 3] += p0 + p1;
+          pk[i] = tc::pack_bf16(p0, p1);
+        }
+#endif
+      }
+      const bool need_rescale = move;
+#else
       // lazy rescale: keep the reference max unless it grows by more than 8 (factor 256)
       float m_new = m_ref;
       if (mx > m_ref + 8.f) m_new = mx;
       const float alpha = ex2(m_ref - m_new);  // 1 when unchanged, 0 on the first tile
-      float rsum[4] = {0.f, 0.f, 0.f, 0.f};
-      uint32_t pk[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         float p0 = __uint_as_float(sv[2 * i]) - m_new, p1 = __uint_as_float(sv[2 * i + 1]) - m_new;
-        if (dbg == 1) { p0 = p0 * p0; p1 = p1 * p1; }
-        else {
-          p0 = ex2(p0);
-#if LG_ATTN_POLY > 0
-          p1 = (i % LG_ATTN_POLY == 0) ? ex2_poly(p1) : ex2(p1);
-#else
-          p1 = ex2(p1);
-#endif
-        }
+        p0 = ex2(p0);
+        p1 = LG_POLY_HERE(i) ? ex2_poly(p1) : ex2(p1);
         rsum[i & 3] += p0 + p1;
         pk[i] = tc::pack_bf16(p0, p1);
       }
+      const bool need_rescale = m_new != m_ref;
+      m_ref = m_new;
+#endif
       l_part = l_part * alpha + ((rsum[0] + rsum[1]) + (rsum[2] + rsum[3]));
       STAMP(5);
       if (j > 0) {
         tc::mbar_wait(pv_done, (j - 1) & 1);  // PV(j-1) retired: P is free, O is up to date
         tc::fence_after_sync();
         STAMP(6);
-        const bool need = m_new != m_ref;
-        if (__any_sync(0xffffffffu, need)) {  // same rows in both half-warps -> same decision
+        if (__any_sync(0xffffffffu, need_rescale)) {  // same rows in both half-warps -> same decision
           uint32_t o[32];
           tc::tmem_ld32(tmem + lane_base + TM_O + half * 32, o);
           tc::tmem_ld_wait();
@@ -323,7 +394,6 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tc::tmem_st32(tmem + lane_base + TM_O + half * 32, o);
         }
       }
-      m_ref = m_new;
       tc::tmem_st32(tmem + lane_base + TM_P + half * 32, pk);
       tc::tmem_st_wait();
       STAMP(7);

@@ -206,6 +206,18 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo
   return d;
 }
 
+// K-major operand with 32-byte rows (16 bf16 = one K=16 MMA slice), 32-byte swizzle: 8-row groups are SBO = 256 B
+// apart; layout code 6 (0 none, 2 = 128 B, 4 = 64 B, 6 = 32 B).
+__device__ __forceinline__ uint64_t smem_desc_sw32(uint32_t saddr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;  // LBO unused for swizzled K-major
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.
 //   bits 4-5 D format (1 = f32)  7-9 A format (1 = bf16)  10-12 B format (1 = bf16)
 //   bit 15 A major (0 = K)  bit 16 B major (0 = K, 1 = MN)  bits 17-22 N >> 3  bits 24-28 M >> 4
