@@ -124,8 +124,8 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* sQ = smem;
   uint8_t* sK = smem + TILE_BYTES;              // KST stages
   uint8_t* sV = smem + (1 + KST) * TILE_BYTES;  // VST stages
-  uint8_t* sQx = smem + AT_XOFF;             // [128 queries][16] bf16: column 0 = -m_ref(row), rest 0
-  uint8_t* sKx = sQx + XT_BYTES;             // [128 keys][16] bf16: 1 in the first element of each 16-byte chunk
+  uint8_t* sQx = smem + AT_XOFF;             // [128 queries][16] bf16: columns 0,1 = -m_ref(row) as hi, lo; rest 0
+  uint8_t* sKx = sQx + XT_BYTES;             // [128 keys][16] bf16: 1, 1 at the start of each 16-byte chunk
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_BAROFF);
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;             // [KST]
@@ -155,12 +155,13 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #if LG_ATTN_MSUB
   // S' = Q.K^T + Q_ext.K_ext^T = s - m_ref: the softmax loop then needs no subtraction (64 of its ~480 instructions
   // per 32x64 block; the loop is issue-bound).  Q_ext starts at 0 and is rewritten by the softmax threads whenever the
-  // reference maximum of a row moves (first tile, then only when the maximum grows by > 8); m_ref is kept bf16-exact.
-  // K_ext carries a 1 at the start of BOTH 16-byte chunks of a row, so the product is -m_ref whichever chunk the
-  // 32-byte swizzle maps Q_ext's single non-zero element to.
+  // reference maximum of a row moves (first tile, then only when the maximum grows by > 8).  m_ref is kept exactly
+  // representable as hi + lo of two bf16 (16 mantissa bits: < 1 unit of error up to |m| = 65 536 log2 units), carried
+  // in Q_ext columns 0 and 1.  K_ext has ones in the first two elements of BOTH 16-byte chunks of a row, so the
+  // product is -(hi + lo) whichever chunk the 32-byte swizzle maps Q_ext's non-zero pair to.
   if (threadIdx.x < 256) {
     reinterpret_cast<uint4*>(sQx)[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
-    reinterpret_cast<uint4*>(sKx)[threadIdx.x] = make_uint4(0x00003f80u, 0u, 0u, 0u);
+    reinterpret_cast<uint4*>(sKx)[threadIdx.x] = make_uint4(0x3f803f80u, 0u, 0u, 0u);  // two leading ones
   }
   tc::fence_proxy_async();
 #endif
@@ -317,13 +318,16 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const bool move = j == 0 || mx > 8.f;
       if (move) {
         const float base = j == 0 ? 0.f : m_ref;
-        const __nv_bfloat16 mb = __float2bfloat16_rn(base + mx);
-        const float m_abs = __bfloat162float(mb);
+        const float m_want = base + mx;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(m_want);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(m_want - __bfloat162float(hi));
+        const float m_abs = __bfloat162float(hi) + __bfloat162float(lo);
         delta = m_abs - base;
         m_ref = m_abs;
-        if (half == 0) {  // row r of Q_ext: 32-byte rows, the non-zero element at byte 0 of the row
-          const __nv_bfloat16 neg = __float2bfloat16_rn(-m_abs);
-          *reinterpret_cast<unsigned short*>(sQx + r * 32) = *reinterpret_cast<const unsigned short*>(&neg);
+        if (half == 0) {  // row r of Q_ext: 32-byte rows, (-hi, -lo) in the first two elements of the row
+          const uint32_t bits = ((uint32_t)(*reinterpret_cast<const unsigned short*>(&hi)) |
+                                 ((uint32_t)(*reinterpret_cast<const unsigned short*>(&lo)) << 16)) ^ 0x80008000u;
+          *reinterpret_cast<uint32_t*>(sQx + r * 32) = bits;
         }
         tc::fence_proxy_async();  // generic-proxy write -> visible to the next QK^T (async proxy)
       }

@@ -263,6 +263,32 @@ def test_attention(prec, kv_xor):
         torch.testing.assert_close(ctx[s, :nq].float(), ref, **tol)
 
 
+@pytest.mark.parametrize("scale", [20.0, 300.0], ids=["logits~1e3", "logits~2e4"])
+def test_attention_bf16_large_and_drifting_logits(scale):
+    """bf16 kernel folds the row-max subtraction into the QK^T MMA (reference max kept as hi + lo bf16): scores of
+    large magnitude whose running maximum keeps growing along the key axis must still match the fp32 softmax."""
+    lib = _abi.load()
+    torch.manual_seed(5)
+    S, Lp = 2, 1024
+    lens = torch.tensor([1024, 900], dtype=torch.int32, device=DEV)
+    q = torch.randn(S, 4, Lp, 64, device=DEV)
+    k = torch.randn(S, 4, Lp, 64, device=DEV)
+    # keys grow in norm along the sequence -> the row maximum moves in (almost) every 128-key tile
+    k = k * torch.linspace(0.2, 1.0, Lp, device=DEV)[None, None, :, None]
+    q = (q * scale).to(torch.bfloat16)
+    k = k.to(torch.bfloat16)
+    v = torch.randn(S, 4, Lp, 64, device=DEV).to(torch.bfloat16)
+    ctx = torch.zeros(S, Lp, 256, device=DEV, dtype=torch.bfloat16)
+    rc = lib.lgb200_attention(_abi.BF16, ptr(q), ptr(k), ptr(v), S, Lp, ptr(lens), 0, ptr(ctx), _stream())
+    assert rc == 0, lib.lgb200_error_string(rc)
+    for s in range(S):
+        n = int(lens[s])
+        sc = q[s, :, :n].double() @ k[s, :, :n].double().transpose(-1, -2) * math.log(2.0)
+        ref = (torch.softmax(sc, -1) @ v[s, :, :n].double()).permute(1, 0, 2).reshape(n, 256).float()
+        assert torch.isfinite(ctx[s, :n].float()).all()
+        torch.testing.assert_close(ctx[s, :n].float(), ref, atol=3e-2, rtol=3e-2)
+
+
 def test_attention_empty_keys_give_zeros():
     lib = _abi.load()
     S, Lp = 2, 128
