@@ -431,6 +431,51 @@ def test_forward_adaptive_against_oracle(prec):
         assert out["log_assignment"].isfinite().all()
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_forward_ragged_batch_with_empty_images(prec):
+    """Padded batch in which one pair has no keypoints in image 0, one none in image 1 and one none at all
+    (reference, lightglue.py:298-303: an empty side gives matches -1 / scores 0); the other pair must be unaffected."""
+    conf = {"filter_threshold": 0.0, "precision": prec}
+    model = build_model(conf, 7).to(DEV)
+    data = make_pairs(B=4, n0=200, n1=140, seed=61)
+    num0, num1 = [200, 0, 57, 0], [140, 140, 0, 0]
+    d = to_device(data, DEV)
+    d["num_keypoints0"], d["num_keypoints1"] = torch.tensor(num0), torch.tensor(num1)
+    out = model(d)
+    for k in ("matches0", "matches1", "matching_scores0", "matching_scores1", "log_assignment"):
+        assert out[k].isfinite().all() if out[k].is_floating_point() else True, k
+    for b in (1, 2, 3):
+        assert (out["matches0"][b] == -1).all() and (out["matches1"][b] == -1).all()
+        assert (out["matching_scores0"][b] == 0).all() and (out["matching_scores1"][b] == 0).all()
+    # pair 0 equals the same pair run alone
+    single = {k: (v[:1] if isinstance(v, torch.Tensor) else {kk: vv[:1] for kk, vv in v.items()}) for k, v in data.items()}
+    ref = model(to_device(single, DEV))
+    if prec == "fp32":
+        torch.testing.assert_close(out["log_assignment"][0], ref["log_assignment"][0], atol=2e-4, rtol=1e-4)
+        assert (out["matches0"][0] == ref["matches0"][0]).float().mean() > 0.995
+    else:
+        assert (out["log_assignment"][0] - ref["log_assignment"][0]).abs().mean() < 0.05
+
+
+def test_large_pair_properties_bf16():
+    """One pair at 4096 x 3000 keypoints (ragged, Lp = 4096): shapes, finiteness, mutual consistency."""
+    conf = {"filter_threshold": 0.0, "precision": "bf16"}
+    model = build_model(conf, 0).to(DEV)
+    data = make_pairs(B=1, n0=4096, n1=3000, seed=71, device=DEV)
+    out = model(data)
+    la = out["log_assignment"]
+    assert la.shape == (1, 4097, 3001) and la.isfinite().all()
+    m0, m1 = out["matches0"][0], out["matches1"][0]
+    assert m0.shape == (4096,) and m1.shape == (3000,)
+    assert ((m0 >= -1) & (m0 < 3000)).all() and ((m1 >= -1) & (m1 < 4096)).all()
+    j = (m1 > -1).nonzero()[:, 0]
+    assert torch.equal(m0[m1[j]], j)
+    # the row arg-maxima fused into the assignment epilogue agree with torch on the written matrix
+    rows = la[0, :-1, :-1].argmax(1)
+    mutual = (la[0, :-1, :-1].argmax(0)[rows] == torch.arange(4096, device=DEV))
+    assert torch.equal(torch.where(mutual, rows, torch.full_like(rows, -1)), m0)
+
+
 def test_full_size_properties_bf16():
     """BASELINE config shape (2048 kpts), properties that need no oracle run."""
     conf = {"filter_threshold": 0.0, "precision": "bf16"}
