@@ -51,6 +51,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// non-blocking poll
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}\n"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 // Same, for the TMA-producer and MMA-issuer warps: between polls the warp sleeps.  A bare try_wait loop
 // re-issues ~2 instructions every ~40 cycles; measured in the attention kernel (ncu source page), the two
 // waiting warps executed 13 % of all warp-instructions of the SM and took issue slots from the softmax warps
