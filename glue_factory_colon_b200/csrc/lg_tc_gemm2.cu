@@ -54,7 +54,7 @@ struct Lay {
                                                                         //  rotary prefetch) then bias | gamma | beta
   static constexpr int OFF_STATS = OFF_PAR + 3 * BN * 4;                // [2][8 slots][128 rows] float2
   static constexpr int OFF_BAR = OFF_STATS + (KBIG ? 2 * 8 * 128 * 8 : 0);
-  static constexpr int SMEM = OFF_BAR + 256;
+  static constexpr int SMEM = OFF_BAR + 448;  // up to 50 mbarriers (pair HEADS kernel: 4 stages, 32 input barriers) + the TMEM slot
 };
 
 struct Maps {
@@ -584,12 +584,13 @@ __device__ __forceinline__ bool pair_skipped(const Args& g, int mt2) {
   return tile_skipped(g, 2 * mt2) && tile_skipped(g, 2 * mt2 + 1);
 }
 
-template <bool KBIG>
-__global__ void __launch_bounds__(320, 1)
+template <int MODE, bool KBIG>
+__global__ void __launch_bounds__(MODE == MODE_HEADS ? 576 : 320, 1)
 tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
   using L = Lay<KBIG>;
   constexpr int NSTAGE = L::NSTAGE;
   constexpr int BN2 = 256;  // columns of the pair's tile = accumulator columns per CTA
+  constexpr int NEW = MODE == MODE_HEADS ? 16 : 8;  // epilogue warps (HEADS was epilogue-bound with 8: issuer waited 56 % for TMEM)
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW = smem;
@@ -602,8 +603,8 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
   uint64_t* tempty = tfull + 2;          // [2] leader only: 16 epilogue warps of the pair
   uint64_t* w_full = tempty + 2;
   uint64_t* peer_w = w_full + 1;
-  uint64_t* in_bar = peer_w + 1;         // [8] one per epilogue warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_bar + 8);
+  uint64_t* in_bar = peer_w + 1;         // [2 * NEW] two per epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_bar + 2 * NEW);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_rank();  // 0 = leader
@@ -621,6 +622,8 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
     tc::prefetch_tmap(&maps.a1);
     tc::prefetch_tmap(&maps.w);
     tc::prefetch_tmap(&maps.out0);
+    tc::prefetch_tmap(&maps.out1);
+    tc::prefetch_tmap(&maps.out2);
     tc::prefetch_tmap(&maps.in);
     for (int i = 0; i < NSTAGE; ++i) {
       tc::mbar_init(&full[i], 1);
@@ -629,9 +632,9 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
     }
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&tfull[i], 1);
-      tc::mbar_init(&tempty[i], 16);
+      tc::mbar_init(&tempty[i], 2 * NEW);
     }
-    for (int i = 0; i < 8; ++i) tc::mbar_init(&in_bar[i], 1);
+    for (int i = 0; i < 2 * NEW; ++i) tc::mbar_init(&in_bar[i], 1);
     tc::mbar_init(w_full, 1);
     tc::mbar_init(peer_w, 1);
     tc::fence_barrier_init();
@@ -738,12 +741,110 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
     // ------------------------------------------------------------------ epilogue (8 warps): own 128 rows x 256 columns
     const int ew = warp - 2;
     const int quarter = warp & 3;
-    const int half = ew >> 2;
-    const int c_warp = half * 64;
-    uint8_t* stg_out = smem + L::OFF_SOUT + ew * STG;
-    uint8_t* stg_in = smem + L::OFF_SIN + ew * STG;
-    const uint32_t my_row_off = (uint32_t)lane * 128u;
-    const uint32_t sw = (uint32_t)(lane & 7);
+    const int half = ew >> 2;       // ROW: 64-column half; HEADS: 32-column slice cq (0..3) of a 128-column block
+    const int c_warp = half * (MODE == MODE_HEADS ? 32 : 64);
+    constexpr int STGW = MODE == MODE_HEADS ? 2048 : STG;  // staging tile of a warp: 32 rows x 64 B or x 128 B
+    uint8_t* stg_out = smem + L::OFF_SOUT + ew * STGW;
+    uint8_t* stg_in = smem + L::OFF_SIN + ew * STGW;
+    const uint32_t my_row_off = (uint32_t)lane * (MODE == MODE_HEADS ? 64u : 128u);
+    const uint32_t sw = MODE == MODE_HEADS ? (uint32_t)((lane >> 1) & 3) : (uint32_t)(lane & 7);
+    if constexpr (MODE == MODE_HEADS) {
+      // head-major outputs [S,4,Lp,64]; a warp owns 32 tokens x 32 columns (half a head) of each 128-column block:
+      // 2 KB staging tiles with a 64-byte swizzle, 32 x 32 TMA boxes.  Optional rotary on the first n_rot parts; the
+      // (cos, sin) pairs of the warp's 16 frequencies for the NEXT super-tile are fetched while this one is processed.
+      const bool use_rot = g.has_in != 0 && (pair_col0 >> 8) < g.n_rot;  // (a pair's 256 columns are one part)
+      const int part = pair_col0 >> 8;
+      const CUtensorMap* out_map = part == 0 ? &maps.out0 : (part == 1 ? &maps.out1 : &maps.out2);
+      const float sc = g.scale[part];
+      const int col_in_head = (half & 1) * 32;  // column of this slice inside its 64-wide head row
+      auto next_tile = [&](int mt) {
+        for (mt += m_step; mt < g.m_tiles && pair_skipped(g, mt); mt += m_step) {}
+        return mt;
+      };
+      int acc = 0, iter = 0;
+      uint32_t acc_phase = 0;
+      if (use_rot && lane == 0) {
+        int mt0 = m_first;
+        if (mt0 < g.m_tiles && pair_skipped(g, mt0)) mt0 = next_tile(mt0);
+        if (mt0 < g.m_tiles) {
+          tc::mbar_arrive_expect_tx(&in_bar[ew], STGW);
+          tc::tma_load_2d(stg_in, &maps.in, &in_bar[ew], col_in_head, mt0 * 2 * BM + (int)crank * BM + quarter * 32);
+        }
+      }
+      for (int mt = m_first; mt < g.m_tiles; mt += m_step) {
+        if (pair_skipped(g, mt)) continue;
+        const int r0 = mt * 2 * BM + (int)crank * BM;       // first row of this CTA's 128-row half (inside one sequence)
+        const bool store_rows = !tile_skipped(g, 2 * mt + (int)crank);
+        const int seq = r0 / g.Lp, l0 = r0 - seq * g.Lp;
+        if (use_rot && lane == 0) {
+          const int mn = next_tile(mt);
+          if (mn < g.m_tiles) {  // buffer (iter+1)&1 was read during the previous super-tile
+            const int nb_ = (iter + 1) & 1;
+            tc::mbar_arrive_expect_tx(&in_bar[nb_ * NEW + ew], STGW);
+            tc::tma_load_2d(stg_in + nb_ * NEW * STGW, &maps.in, &in_bar[nb_ * NEW + ew], col_in_head,
+                            mn * 2 * BM + (int)crank * BM + quarter * 32);
+          }
+        }
+        tc::mbar_wait(&tfull[acc], acc_phase);
+        tc::fence_after_sync();
+        uint32_t in[16];
+        if (use_rot) {
+          tc::mbar_wait(&in_bar[(iter & 1) * NEW + ew], (iter >> 1) & 1);
+          const uint8_t* tin = stg_in + (iter & 1) * NEW * STGW;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 t = *reinterpret_cast<const uint4*>(tin + my_row_off + ((j ^ sw) << 4));
+            in[4 * j] = t.x; in[4 * j + 1] = t.y; in[4 * j + 2] = t.z; in[4 * j + 3] = t.w;
+          }
+        }
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) {
+          const int cw = cb * BN + c_warp;               // first column of this warp within the pair's 256
+          const int head = ((pair_col0 + cw) >> 6) & 3;
+          uint32_t v[32];
+          tc::tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN2 + cw, v);
+          tc::tmem_ld_wait();
+          if (cb == 1) {
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) {
+              if (crank == 0) tc::mbar_arrive(&tempty[acc]);
+              else mbar_arrive_remote(&tempty[acc], 0);
+            }
+          }
+          uint32_t pk[16];
+          if (use_rot) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float a = __uint_as_float(v[2 * j]) + s_par[cw + 2 * j];
+              const float b = __uint_as_float(v[2 * j + 1]) + s_par[cw + 2 * j + 1];
+              const __half2 cs = *reinterpret_cast<const __half2*>(&in[j]);
+              const float c = __low2float(cs) * sc, s_ = __high2float(cs) * sc;
+              pk[j] = tc::pack_bf16(a * c - b * s_, b * c + a * s_);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              pk[j] = tc::pack_bf16((__uint_as_float(v[2 * j]) + s_par[cw + 2 * j]) * sc,
+                                    (__uint_as_float(v[2 * j + 1]) + s_par[cw + 2 * j + 1]) * sc);
+          }
+          if (lane == 0) bulk_wait_read0();  // previous store has finished reading stg_out
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(stg_out + my_row_off + ((j ^ sw) << 4)) =
+                make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          tc::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && store_rows) {
+            tma_store_2d(out_map, stg_out, col_in_head, (seq * LG_HEADS + head) * g.Lp + l0 + quarter * 32);
+            bulk_commit();
+          }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        ++iter;
+      }
+    } else {
     const float sc = g.scale[0];
     const bool use_in = g.has_in != 0;
     int acc = 0;
@@ -818,6 +919,7 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
     }
     if (lane == 0) bulk_wait0();
   }
@@ -1172,10 +1274,10 @@ int launch(const Maps& maps, Args g, int n_blocks, cudaStream_t st) {
 }
 
 
-template <bool KBIG>
+template <int MODE, bool KBIG>
 int launch_pair_row(const Maps& maps, Args g, int N, cudaStream_t st) {
   using L = Lay<KBIG>;
-  auto kern = tc_pair_row_kernel<KBIG>;
+  auto kern = tc_pair_row_kernel<MODE, KBIG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM);
   if (e != cudaSuccess) return (int)e;
   int dev = 0, sms = 148;
@@ -1184,7 +1286,7 @@ int launch_pair_row(const Maps& maps, Args g, int N, cudaStream_t st) {
   g.n_groups = N / 256;
   g.m_tiles = g.m_tiles / 2;  // 256-row super-tiles
   cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(320);
+  cfg.blockDim = dim3(MODE == MODE_HEADS ? 576 : 320);
   cfg.dynamicSmemBytes = L::SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1312,7 +1414,8 @@ int lg_tc_linear_v2(int epilogue, const __nv_bfloat16* A0, const __nv_bfloat16* 
   const int n_blocks = N / BN;
   // bit 1: CTA-pair kernel for the LayerNorm layer (default on: 150 vs 225 us at T = 262144);
   // bit 0: CTA-pair kernel for the K = 512 ROW layer (default off: that layer already runs at 88 % of HBM peak, 93 us both ways)
-  static const int pair_mode = getenv("LGB200_GEMM_PAIR") ? atoi(getenv("LGB200_GEMM_PAIR")) : 2;
+  // bit 2: CTA-pair kernel for the HEADS layers (QKV, cross projections)
+  static const int pair_mode = getenv("LGB200_GEMM_PAIR") ? atoi(getenv("LGB200_GEMM_PAIR")) : 6;
   if (ln && (pair_mode & 2) && T % 256 == 0) {  // CTA-pair kernel: each CTA loads 64-row boxes of A
     Maps pm = maps;
     if ((rc = make_map(&pm.a0, A0, K0, T, 64))) return rc;
@@ -1325,6 +1428,28 @@ int lg_tc_linear_v2(int epilogue, const __nv_bfloat16* A0, const __nv_bfloat16* 
     return launch_pair_ln(pm, g, st);
   }
   if (ln) return launch<MODE_LN, 4, true>(maps, g, n_blocks, st);
+  if (epilogue == LGB200_EPI_HEADS && (pair_mode & 4) && T % 256 == 0 && epi.Lp % 128 == 0) {
+    Maps pm = maps;  // CTA-pair kernel: 128-row A boxes, one pair per 256-column group (cluster of 2, no multicast);
+                     // outputs and rotary rows in 32-row x 32-column boxes with a 64-byte swizzle (16 epilogue warps)
+    if ((rc = make_map(&pm.a0, A0, K0, T, BM))) return rc;
+    pm.a1 = pm.a0;
+    {
+      const uint64_t rows = (uint64_t)T * LG_HEADS;
+      const uint64_t d[2] = {64, rows}, sb[1] = {128};
+      const uint32_t bx[2] = {32, 32};
+      for (int p = 0; p < N / 256; ++p) {
+        CUtensorMap* m = p == 0 ? &pm.out0 : (p == 1 ? &pm.out1 : &pm.out2);
+        if ((rc = lg_make_tmap_bf16_sw(m, epi.outp[p], 2, d, sb, bx, 64))) return rc;
+      }
+      if (N / 256 < 2) pm.out1 = pm.out0;
+      if (N / 256 < 3) pm.out2 = pm.out0;
+      if (epi.n_rot > 0) {
+        const uint64_t dr[2] = {64, (uint64_t)T};
+        if ((rc = lg_make_tmap_bf16_sw(&pm.in, rot16, 2, dr, sb, bx, 64))) return rc;
+      }
+    }
+    return launch_pair_row<MODE_HEADS, false>(pm, g, N, st);
+  }
   if (epilogue == LGB200_EPI_HEADS) return launch<MODE_HEADS, 2, false>(maps, g, n_blocks, st);
   if (kbig && (pair_mode & 1) && T % 256 == 0) {  // CTA-pair kernel: the A boxes are 128 rows (no multicast inside a pair)
     Maps pm = maps;
@@ -1334,7 +1459,7 @@ int lg_tc_linear_v2(int epilogue, const __nv_bfloat16* A0, const __nv_bfloat16* 
     } else {
       pm.a1 = pm.a0;
     }
-    return launch_pair_row<true>(pm, g, N, st);
+    return launch_pair_row<MODE_ROW, true>(pm, g, N, st);
   }
   if (kbig) return launch<MODE_ROW, 2, true>(maps, g, n_blocks, st);
   return launch<MODE_ROW, 2, false>(maps, g, n_blocks, st);

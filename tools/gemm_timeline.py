@@ -37,6 +37,8 @@ run("FFN1 LN  K512 N512", EPI_LN_GELU, 512, 512, A1=y, K0=256, out16=hid, gamma=
 o = torch.empty(T, 256, device="cuda", dtype=torch.bfloat16)
 run("FFN2 ROW K512 N256", EPI_ROWMAJOR, 256, 512, A0=hid, resid16=o, out16=o)
 run("out  ROW K256 N256", EPI_ROWMAJOR, 256, 256, out16=o)
+q2 = [torch.empty(T * 256, device="cuda", dtype=torch.bfloat16) for _ in range(2)]
+run("cross HEADS K256 N512", EPI_HEADS, 512, 256, n_rot=0, outp=(q2[0], q2[1], None))
 q = [torch.empty(T * 256, device="cuda", dtype=torch.bfloat16) for _ in range(3)]
 rot16 = torch.randn(T, 64, device="cuda").to(torch.float16)
 run("QKV HEADS K256 N768", EPI_HEADS, 768, 256, rot16=rot16, n_rot=2, outp=q)
