@@ -167,8 +167,11 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": min(warm, 1), "ms_per_step": 1e3 * el / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{PAIRS_PER_GPU} pairs x {KPTS} kpts x 256-d, 9 layers, random-init (configs[1])",
-                   "note": "CPU port of the reference (oracle/), host cores only"},
+        "config": {"workload": f"{args.pairs} pairs/GPU x {KPTS} kpts x 256-d descriptors, 9 layers, random-init, "
+                               f"{args.precision} (BASELINE configs[1])",
+                   "pairs_per_gpu": args.pairs, "kpts": KPTS,
+                   "note": "this arm: CPU port of the reference (oracle/) in fp32 on the host cores, one pair per step "
+                           "(bounded sample of the same workload)"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
