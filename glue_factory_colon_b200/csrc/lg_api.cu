@@ -76,9 +76,15 @@ extern "C" int lgb200_attention(int precision, const void* Q, const void* K, con
   if (precision == LGB200_F32)
     return lg_simt_attention((const float*)Q, (const float*)K, (const float*)V, S, Lp, lens, kv_xor,
                              (float*)ctx, st);
-  if (precision == LGB200_BF16)
+  if (precision == LGB200_BF16) {
+    // LGB200_ATTN2=1 selects the two-query-tile kernel with ordered softmax groups (lg_tc_attn2.cu)
+    static const int attn2 = getenv("LGB200_ATTN2") ? atoi(getenv("LGB200_ATTN2")) : 0;
+    if (attn2)
+      return lg_tc_attention2((const __nv_bfloat16*)Q, (const __nv_bfloat16*)K, (const __nv_bfloat16*)V, S, Lp,
+                              lens, kv_xor, (__nv_bfloat16*)ctx, st);
     return lg_tc_attention((const __nv_bfloat16*)Q, (const __nv_bfloat16*)K, (const __nv_bfloat16*)V, S,
                            Lp, lens, kv_xor, (__nv_bfloat16*)ctx, st);
+  }
   return LGB200_ERR_PRECISION;
 }
 
