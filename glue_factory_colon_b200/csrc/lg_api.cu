@@ -108,7 +108,7 @@ extern "C" int lgb200_assign_scores(int precision, const void* md, const float* 
   cudaStream_t st = lg_stream(stream);
   if (precision == LGB200_F32) {
     if (best_ws) return LGB200_ERR_PRECISION;  // the fused argmax exists in the tcgen05 kernel only
-    return lg_simt_assign_scores((const float*)md, z, lse, B, Lp, lens, R, C, scores, st);
+    return lg_simt_assign_scores((const float*)md, z, lse, B, Lp, lens, R, C, scores, nullptr, st);
   }
   if (precision == LGB200_BF16)
     return lg_tc_assign_scores((const __nv_bfloat16*)md, z, lse, B, Lp, lens, R, C, scores, best_ws, st);

@@ -9,7 +9,7 @@ int lg_simt_attention(const float* Q, const float* K, const float* V, int S, int
                       int kv_xor, float* ctx, cudaStream_t st);
 int lg_simt_assign_lse(const float* md, int S, int Lp, const int32_t* lens, float* lse, cudaStream_t st);
 int lg_simt_assign_scores(const float* md, const float* z, const float* lse, int B, int Lp,
-                          const int32_t* lens, int R, int C, float* scores, cudaStream_t st);
+                          const int32_t* lens, int R, int C, float* scores, float* sim_out, cudaStream_t st);
 
 // bf16 tcgen05 path (lg_tc_*.cu)
 int lg_tc_linear(int epilogue, const __nv_bfloat16* A0, const __nv_bfloat16* A1, int K0,

@@ -336,7 +336,10 @@ __global__ void __launch_bounds__(256) simt_assign_scores_kernel(const float* __
                                                                  const float* __restrict__ z,
                                                                  const float* __restrict__ lse, int Lp,
                                                                  const int32_t* __restrict__ lens, int R,
-                                                                 int C, float* __restrict__ scores) {
+                                                                 int C, float* __restrict__ scores,
+                                                                 float* __restrict__ sim_out) {
+  // z == nullptr: nearest-neighbour matcher mode (no matchability terms, dustbins stay 0,
+  // nearest_neighbor_matcher.py:73-74); sim_out (nullable): the raw similarity [B, R-1, C-1] (:64)
   __shared__ SimtSmem sm;
   const int b = blockIdx.z, m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
   const int s0 = 2 * b, s1 = 2 * b + 1;
@@ -358,9 +361,11 @@ __global__ void __launch_bounds__(256) simt_assign_scores_kernel(const float* __
     const int c = n0 + tx * 4 + j;
     cz[j] = cl[j] = cneg[j] = 0.f;
     if (c < nb) {
-      const float zz = z[(size_t)s1 * Lp + c];
-      cz[j] = lg_logsigmoid(zz);
-      cneg[j] = lg_logsigmoid(-zz);
+      if (z) {
+        const float zz = z[(size_t)s1 * Lp + c];
+        cz[j] = lg_logsigmoid(zz);
+        cneg[j] = lg_logsigmoid(-zz);
+      }
       cl[j] = lse[(size_t)s1 * Lp + c];
     }
   }
@@ -370,9 +375,11 @@ __global__ void __launch_bounds__(256) simt_assign_scores_kernel(const float* __
     if (r >= R) continue;
     float rz = 0.f, rl = 0.f, rneg = 0.f;
     if (r < na) {
-      const float zz = z[(size_t)s0 * Lp + r];
-      rz = lg_logsigmoid(zz);
-      rneg = lg_logsigmoid(-zz);
+      if (z) {
+        const float zz = z[(size_t)s0 * Lp + r];
+        rz = lg_logsigmoid(zz);
+        rneg = lg_logsigmoid(-zz);
+      }
       rl = lse[(size_t)s0 * Lp + r];
     }
 #pragma unroll
@@ -384,6 +391,8 @@ __global__ void __launch_bounds__(256) simt_assign_scores_kernel(const float* __
       else if (r < na && c == C - 1) v = rneg;
       else if (r == R - 1 && c < nb) v = cneg[j];
       out[(size_t)r * C + c] = v;
+      if (sim_out && r < R - 1 && c < C - 1)
+        sim_out[((size_t)b * (R - 1) + r) * (C - 1) + c] = (r < na && c < nb) ? acc[i][j] : 0.f;
     }
   }
 }
@@ -396,9 +405,9 @@ int lg_simt_assign_lse(const float* md, int S, int Lp, const int32_t* lens, floa
 }
 
 int lg_simt_assign_scores(const float* md, const float* z, const float* lse, int B, int Lp,
-                          const int32_t* lens, int R, int C, float* scores, cudaStream_t st) {
+                          const int32_t* lens, int R, int C, float* scores, float* sim_out, cudaStream_t st) {
   dim3 grid((C + SG_BN - 1) / SG_BN, (R + SG_BM - 1) / SG_BM, B);
-  simt_assign_scores_kernel<<<grid, 256, 0, st>>>(md, z, lse, Lp, lens, R, C, scores);
+  simt_assign_scores_kernel<<<grid, 256, 0, st>>>(md, z, lse, Lp, lens, R, C, scores, sim_out);
   LG_LAUNCH_CHECK();
   return LGB200_OK;
 }

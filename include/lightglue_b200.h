@@ -170,6 +170,23 @@ int lgb200_filter_matches(const float* scores, int B, int R, int C, const int32_
                           int N0, int N1, int64_t* m0, int64_t* m1, float* ms0, float* ms1,
                           void* workspace, int workspace_has_best, void* stream);
 
+/* ---- nearest-neighbour matcher ----------------------------------------------------------
+ * Replaces NearestNeighborMatcher._forward, gluefactory/models/matchers/nearest_neighbor_matcher.py:63-83
+ * (fp32).  d [S,Lp,256] = descriptors packed like the LightGlue activations (rows >= count and columns
+ * >= the descriptor dimension zero), lse from lgb200_assign_lse(LGB200_F32, d, ...).
+ *   lgb200_nn_scores: similarity [B,R-1,C-1] (nullable) = <d0[i], d1[j]> (:64) and log_assignment [B,R,C] =
+ *          log_softmax(sim, rows) + log_softmax(sim, columns) on the valid block, zeros elsewhere incl. the
+ *          dustbin row / column (:72-74).
+ *   lgb200_nn_match: find_nn (:15-31) for both images -- nearest neighbour by similarity, rejected if
+ *          2(1-s1) > ratio^2 * 2(1-s2) (ratio_thresh > 0, more than one candidate) or 2(1-s1) > distance_thresh^2
+ *          (distance_thresh > 0); lowest index among equal similarities -- then mutual_check (:34-43) if
+ *          `mutual`; scores = (match > -1).  similarity [B,N,M]; workspace: 8 * B * (N + M) bytes. */
+int lgb200_nn_scores(const float* d, const float* lse, int B, int Lp, const int32_t* lens, int R, int C,
+                     float* similarity, float* log_assignment, void* stream);
+int lgb200_nn_match(const float* similarity, int B, int N, int M, const int32_t* lens, float ratio_thresh,
+                    float distance_thresh, int mutual, int64_t* workspace, int64_t* m0, int64_t* m1,
+                    float* ms0, float* ms1, void* stream);
+
 /* ---- adaptive depth (early exit) ---------------------------------------------------------
  * Replaces check_if_stop, lightglue.py:569-580.  conf [S,Lp] = sigmoid token
  * confidences; pair b stops iff 1 - count(conf < thr)/total[b] > depth_conf

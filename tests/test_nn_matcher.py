@@ -1,0 +1,81 @@
+"""Nearest-neighbour matcher drop-in: oracle vs reference goldens on CPU, CUDA path vs oracle."""
+import pytest
+import torch
+
+from helpers import ROOT
+from oracle import nn_oracle
+
+from glue_factory_colon_b200.synthetic import make_pairs, to_device
+
+GOLD = ROOT / "tests" / "golden" / "nn_matcher.pt"
+
+
+def _cases():
+    return torch.load(GOLD, map_location="cpu", weights_only=True)
+
+
+def test_oracle_reproduces_the_reference_goldens():
+    for c in _cases():
+        data = make_pairs(**c["data_kwargs"])
+        res = nn_oracle.forward(c["conf"], data)
+        for k in ("matches0", "matches1", "matching_scores0", "matching_scores1"):
+            assert torch.equal(res[k], c["out"][k]), (c["name"], k)
+        torch.testing.assert_close(res["similarity"], c["out"]["similarity"], atol=1e-6, rtol=0)
+        torch.testing.assert_close(res["log_assignment"], c["out"]["log_assignment"], atol=1e-5, rtol=0)
+        assert (c["out"]["matches0"] > -1).any()
+
+
+def test_plugin_discovery_and_conf():
+    from glue_factory_colon_b200 import nearest_neighbor_matcher as mod
+
+    m = mod.__main_model__({"ratio_thresh": 0.9, "name": "whatever", "loss": "N_pair"})
+    assert m.conf.ratio_thresh == 0.9 and m.conf.mutual_check is True
+    assert [k for k, _ in m.named_parameters()] == ["temperature"]
+    with pytest.raises(NotImplementedError):
+        m.loss({}, {})
+    with pytest.raises(Exception):  # no CPU path
+        m(make_pairs(1, 8, 8))
+
+
+@pytest.mark.gpu
+def test_cuda_path_matches_reference_goldens_and_oracle():
+    from glue_factory_colon_b200.nearest_neighbor_matcher import NearestNeighborMatcher
+
+    for c in _cases():
+        data = make_pairs(**c["data_kwargs"])
+        out = NearestNeighborMatcher(c["conf"]).cuda()(to_device(data, "cuda"))
+        out = {k: v.cpu() for k, v in out.items()}
+        torch.testing.assert_close(out["similarity"], c["out"]["similarity"], atol=2e-6, rtol=0)
+        torch.testing.assert_close(out["log_assignment"], c["out"]["log_assignment"], atol=2e-5, rtol=0)
+        # index logic bit-exact on the kernel's own similarity matrix ...
+        res = nn_oracle.forward(c["conf"], data, sim=out["similarity"])
+        for k in ("matches0", "matches1", "matching_scores0", "matching_scores1"):
+            assert torch.equal(out[k], res[k]), (c["name"], k)
+        # ... and equal to the reference's matches on these fixtures (no near-ties at 1e-6)
+        assert torch.equal(out["matches0"], c["out"]["matches0"]) and torch.equal(out["matches1"], c["out"]["matches1"])
+
+
+@pytest.mark.gpu
+def test_cuda_path_ties_counts_and_empty_side():
+    from glue_factory_colon_b200.nearest_neighbor_matcher import NearestNeighborMatcher
+
+    # exact ties: duplicated descriptors -> the lowest index wins in both directions
+    data = make_pairs(B=1, n0=40, n1=50, seed=31)
+    data["descriptors1"][0, 7] = data["descriptors1"][0, 3]
+    data["descriptors0"][0, 9] = data["descriptors0"][0, 2]
+    out = NearestNeighborMatcher({"mutual_check": False}).cuda()(to_device(data, "cuda"))
+    sim = out["similarity"][0].cpu()
+    assert torch.equal(out["matches0"][0].cpu(), torch.stack([(r == r.max()).nonzero()[0, 0] for r in sim]))
+    assert torch.equal(out["matches1"][0].cpu(), torch.stack([(c == c.max()).nonzero()[0, 0] for c in sim.t()]))
+    # per-pair counts of a padded batch == the un-padded run
+    d2 = make_pairs(B=2, n0=60, n1=70, seed=32)
+    dd = to_device(d2, "cuda")
+    dd["num_keypoints0"], dd["num_keypoints1"] = torch.tensor([60, 33]), torch.tensor([70, 41])
+    out = NearestNeighborMatcher({"ratio_thresh": 0.95}).cuda()(dd)
+    one = {"descriptors0": d2["descriptors0"][1:2, :33].cuda(), "descriptors1": d2["descriptors1"][1:2, :41].cuda()}
+    ref = NearestNeighborMatcher({"ratio_thresh": 0.95}).cuda()(one)
+    assert torch.equal(out["matches0"][1, :33], ref["matches0"][0]) and (out["matches0"][1, 33:] == -1).all()
+    assert torch.equal(out["matches1"][1, :41], ref["matches1"][0]) and (out["matches1"][1, 41:] == -1).all()
+    # empty side (find_nn with no candidates)
+    e = NearestNeighborMatcher({}).cuda()({"descriptors0": torch.zeros(1, 0, 256).cuda(), "descriptors1": torch.randn(1, 5, 256).cuda()})
+    assert e["matches1"].tolist() == [[-1] * 5] and e["log_assignment"].shape == (1, 1, 6)
