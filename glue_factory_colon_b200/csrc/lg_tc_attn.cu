@@ -39,7 +39,10 @@ __device__ unsigned int g_attn_sm_slot[1024];
 #define LG_ATTN_MSUB 1  // 1: the row-max subtraction s - m_ref is folded into the QK^T MMA (a fifth K=16 slice)
 #endif
 #ifndef LG_ATTN_POLY16
-#define LG_ATTN_POLY16 3  // LG_ATTN_POLY16 of every 16 exponentials are evaluated by polynomial on the FMA pipe (0..8)
+#define LG_ATTN_POLY16 4  // LG_ATTN_POLY16 of every 16 exponentials are evaluated by polynomial on the FMA pipe (0..8)
+#endif
+#ifndef LG_ATTN_POLY_DEG
+#define LG_ATTN_POLY_DEG 3
 #endif
 #define LG_POLY_HERE(i) ((((i) * LG_ATTN_POLY16) % 8) < LG_ATTN_POLY16)
 
@@ -52,7 +55,9 @@ constexpr int KST = 3, VST = 2;            // K / V ring depth
 constexpr int XT_BYTES = 128 * 16 * 2;     // 4 KB: 128 rows x 16 bf16 (one K=16 MMA slice), 32-byte swizzle
 constexpr int AT_XOFF = TILE_BYTES * (1 + KST + VST);             // Q_ext | K_ext (LG_ATTN_MSUB)
 constexpr int AT_BAROFF = AT_XOFF + (LG_ATTN_MSUB ? 2 * XT_BYTES : 0);
-constexpr int AT_SMEM = AT_BAROFF + 192 + 6 * 128 * 4;  // + barriers + max/sum exchange
+constexpr int AT_NBAR = 16;                // mbarriers per pass (15 used)
+constexpr int AT_BARBYTES = 2 * AT_NBAR * 8 + 64;  // two barrier sets (pass 0 / restart) + tmem slot + panic flag
+constexpr int AT_SMEM = AT_BAROFF + AT_BARBYTES + 14 * 128 * 4;  // + barriers + max/sum exchange [6][128] + tile sums [8][128]
 
 constexpr uint32_t TM_S = 0, TM_P = 128, TM_O = 192, TM_COLS = 256;
 
@@ -69,13 +74,26 @@ __device__ __forceinline__ float ex2(float x) {
 // In this kernel at S=128, Lp=2048, with the subtraction folded into the MMA (LG_ATTN_MSUB), polynomial share of
 // 0 / 1 / 2 / 3 / 4 / 5 / 6 / 8 sixteenths: 0.728 / 0.705 / 0.693 / 0.681 / 0.690 / 0.703 / 0.731 / 0.764 ms -- the
 // polynomial costs 8 issue slots against 1 for MUFU, and the loop is bound by issue slots as much as by MUFU.
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
 __device__ __forceinline__ float ex2_poly(float x) {
+  // (valid for x < 127.5: the exponent patch below wraps silently above; the deferred-maximum mode, where a score may
+  // exceed the reference by any amount, keeps the maximum of the polynomial lanes' inputs and checks it per tile)
   x = fmaxf(x, -126.f);
   const float t = x + 12582912.f;
   const float f = x - (t - 12582912.f);
+#if LG_ATTN_POLY_DEG == 2  // max rel. err 1.7e-3 (a bf16 half-ulp is 1.95e-3)
+  float p = fmaf(f, 0.23842894f, 0.70344801f);
+  p = fmaf(p, f, 1.00044314f);
+#else
   float p = fmaf(f, 0.05500889f, 0.24221097f);
   p = fmaf(p, f, 0.69328294f);
   p = fmaf(p, f, 1.0f);
+#endif
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
@@ -83,7 +101,7 @@ template <int CL>
 __global__ void __launch_bounds__(320, 2)
 tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, int Lp, const int32_t* __restrict__ lens,
-                    int kv_xor, __nv_bfloat16* __restrict__ ctx, int dbg_arg, unsigned stagger_ns) {
+                    int kv_xor, __nv_bfloat16* __restrict__ ctx, int dbg_arg, unsigned stagger_ns, int start_mode) {
   // Debug modes (skeleton runs, no-MUFU run, clock64 timeline) exist only when the file is compiled with
   // -DLG_ATTN_DEBUG; in the product build `dbg` is the constant 0 and every debug branch folds away
   // (leaving them as run-time branches cost ~50 BRA per 64 exponentials in the unrolled loop).
@@ -126,30 +144,27 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* sV = smem + (1 + KST) * TILE_BYTES;  // VST stages
   uint8_t* sQx = smem + AT_XOFF;             // [128 queries][16] bf16: columns 0,1 = -m_ref(row) as hi, lo; rest 0
   uint8_t* sKx = sQx + XT_BYTES;             // [128 keys][16] bf16: 1, 1 at the start of each 16-byte chunk
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_BAROFF);
-  uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;             // [KST]
-  uint64_t* k_empty = k_full + KST;        // [KST]
-  uint64_t* v_full = k_empty + KST;        // [VST]
-  uint64_t* v_empty = v_full + VST;        // [VST]
-  uint64_t* s_full = v_empty + VST;
-  uint64_t* s_free = s_full + 1;
-  uint64_t* p_ready = s_free + 1;
-  uint64_t* pv_done = p_ready + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
-  float* s_xch = reinterpret_cast<float*>(smem + AT_BAROFF + 192);  // [6][128]
+  uint64_t* bars_base = reinterpret_cast<uint64_t*>(smem + AT_BAROFF);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_base + 2 * AT_NBAR);
+  volatile int* panic = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  float* s_xch = reinterpret_cast<float*>(smem + AT_BAROFF + AT_BARBYTES);  // [6][128]
+  float* s_sum = s_xch + 6 * 128;  // [4 tiles][2 halves][128]: row sums per tile (deferred mode)
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmQ);
     tc::prefetch_tmap(&tmK);
     tc::prefetch_tmap(&tmV);
-    tc::mbar_init(q_full, 1);
-    for (int i = 0; i < KST; ++i) { tc::mbar_init(&k_full[i], 1); tc::mbar_init(&k_empty[i], CL); }
-    for (int i = 0; i < VST; ++i) { tc::mbar_init(&v_full[i], 1); tc::mbar_init(&v_empty[i], CL); }
-    tc::mbar_init(s_full, 1);
-    tc::mbar_init(s_free, 8);
-    tc::mbar_init(p_ready, 8);
-    tc::mbar_init(pv_done, 1);
+    for (int set = 0; set < 2; ++set) {  // second set: the restart in exact mode (see `panic`) starts on fresh barriers
+      uint64_t* b = bars_base + set * AT_NBAR;
+      tc::mbar_init(b + 0, 1);                                                                   // q_full
+      for (int i = 0; i < KST; ++i) { tc::mbar_init(b + 1 + i, 1); tc::mbar_init(b + 1 + KST + i, CL); }
+      for (int i = 0; i < VST; ++i) { tc::mbar_init(b + 1 + 2 * KST + i, 1); tc::mbar_init(b + 1 + 2 * KST + VST + i, CL); }
+      tc::mbar_init(b + 1 + 2 * KST + 2 * VST + 0, 1);  // s_full
+      tc::mbar_init(b + 1 + 2 * KST + 2 * VST + 1, 8);  // s_free
+      tc::mbar_init(b + 1 + 2 * KST + 2 * VST + 2, 8);  // p_ready
+      tc::mbar_init(b + 1 + 2 * KST + 2 * VST + 3, 1);  // pv_done
+    }
+    *panic = 0;
     tc::fence_barrier_init();
   }
 #if LG_ATTN_MSUB
@@ -162,6 +177,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (threadIdx.x < 256) {
     reinterpret_cast<uint4*>(sQx)[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
     reinterpret_cast<uint4*>(sKx)[threadIdx.x] = make_uint4(0x3f803f80u, 0u, 0u, 0u);  // two leading ones
+    reinterpret_cast<uint4*>(s_sum)[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);         // [8][128] floats
   }
   tc::fence_proxy_async();
 #endif
@@ -176,6 +192,26 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (CL > 1) tc::cluster_sync();  // peers' barriers exist before anyone multicasts into them
   tc::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+
+  // Pass 0 runs with the DEFERRED row maximum (mode 0): after the first tile the softmax threads exponentiate a score
+  // tile as soon as it is in registers, against the reference the tile was produced with, and look at the tile's row
+  // sum afterwards; the reference moves (one tile later) when that sum exceeds 2^24.  A sum above 2^70 (or inf / NaN)
+  // means the scores jumped by more than the fp32 range can absorb: the CTA sets `panic`, finishes the schedule and
+  // runs the whole work item again in the exact mode (mode 1: maximum before the exponentials, every tile).
+  // (Clusters with K/V multicast always run in mode 1: a restart would have to be agreed across the cluster.)
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+  const int mode = (CL > 1) ? 1 : (start_mode | pass);
+  uint64_t* bars = bars_base + pass * AT_NBAR;
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;             // [KST]
+  uint64_t* k_empty = k_full + KST;        // [KST]
+  uint64_t* v_full = k_empty + KST;        // [VST]
+  uint64_t* v_empty = v_full + VST;        // [VST]
+  uint64_t* s_full = v_empty + VST;
+  uint64_t* s_free = s_full + 1;
+  uint64_t* p_ready = s_free + 1;
+  uint64_t* pv_done = p_ready + 1;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -272,11 +308,34 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int half = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    float m_ref = -INFINITY, l_part = 0.f;
+    // m_ref: the reference the running sum, O and (through Q_ext) the arriving score tiles are expressed in; both
+    // threads of a row hold identical copies.
+    // Deferred mode: the softmax warps are a serial chain per tile (score load -> exponentials -> P store) and every
+    // instruction in it costs ~0.3 % of the kernel, so the bookkeeping is a dozen instructions inside the unrolled loop's
+    // basic block: this thread's row sum of tile j-1 is published to shared memory (no barrier; before the p_ready(j)
+    // arrive), both halves of tile j-3 are read back with one 8-byte load (the reader observed pv_done(j-2) in tile j-1,
+    // the publisher's p_ready(j-2) arrive follows its store), and one compare + one warp vote after the loop decide
+    // whether tile j+1 takes the rare path, where the reference moves up by floor(log2(sum)) -- unless it moved less than
+    // four tiles ago (the sums still on their way were taken against the old reference) -- or, above 2^70 / inf / NaN,
+    // the `bad` bit is set.  The polynomial lanes, whose exponent patch would wrap silently for inputs above 127, feed
+    // a 3-input maximum that is checked once per tile.
+    float m_ref = 0.f, l_part = 0.f, sum_m1 = 0.f, joint_next = 0.f;
+    bool bad = false, move_next = false, any_next = false;
+    int last_move = -4;
+    float* const sum_row = s_sum + r * 2;  // [slot][row][half]
+#define LG_DEFERRED_BOOKKEEPING()                                                                                  \
+    do { /* unconditional and branch-free: stays inside the unrolled loop's basic block; tiles < 0 read zeros */   \
+      sum_row[((j + 3) & 3) * 256 + half] = sum_m1;                                                  /* tile j-1 */ \
+      const float2 both = *reinterpret_cast<const float2*>(sum_row + ((j + 1) & 3) * 256);           /* tile j-3 */ \
+      joint_next = both.x + both.y;                                                                                \
+      move_next = !(joint_next <= 0x1p24f);                                                                        \
+    } while (0)
     const bool rec = (dbg_in & 16) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0;
 #define STAMP(k) do { if (rec && j < 16) g_attn_times[(j * 16) + (k)] = clock64(); } while (0)
     for (int j = 0; j < n_tiles; ++j) {
       STAMP(0);
+      bool move = move_next, any_move = any_next;  // deferred mode: decided in the previous tile
+      const float joint = joint_next;
       tc::mbar_wait(s_full, j & 1);
       tc::fence_after_sync();
       STAMP(1);
@@ -285,12 +344,6 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tc::tmem_ld32(tmem + lane_base + TM_S + half * 64 + 32, sv + 32);
       tc::tmem_ld_wait();
       STAMP(2);
-#if !LG_ATTN_MSUB
-      tc::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(s_free);
-#endif
-      STAMP(3);
       const int valid = nk - j * AT_BN - half * 64;  // valid keys among this thread's 64 columns
       if (valid < 64) {
 #pragma unroll
@@ -298,98 +351,104 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           if (i >= valid) sv[i] = 0xff800000u;  // -inf
         }
       }
-      float mxs[4];
+      // Exact mode and first tile: this tile's row maximum (relative to m_ref; 0 on the first tile) decides, the
+      // reference moves when it exceeds 8 (factor 256).
+      float up = 0.f;
+      if (mode != 0 || j == 0) {  // uniform over the CTA
+        float mxs[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) mxs[i] = __uint_as_float(sv[i]);
+        for (int i = 0; i < 4; ++i) mxs[i] = __uint_as_float(sv[i]);
 #pragma unroll
-      for (int i = 4; i < 64; ++i) mxs[i & 3] = fmaxf(mxs[i & 3], __uint_as_float(sv[i]));
-      float mx = fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3]));
-      s_xch[((j & 1) * 2 + half) * 128 + r] = mx;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-      mx = fmaxf(mx, s_xch[((j & 1) * 2 + (half ^ 1)) * 128 + r]);
+#ifdef LG_ATTN_NO_MAX3
+        for (int i = 4; i < 64; ++i) mxs[i & 3] = fmaxf(mxs[i & 3], __uint_as_float(sv[i]));
+#else
+        for (int i = 4; i < 64; i += 2)  // FMNMX3: one issue slot for two elements
+          mxs[(i >> 1) & 3] = max3(mxs[(i >> 1) & 3], __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+#endif
+        float mx = fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3]));
+        s_xch[((j & 1) * 2 + half) * 128 + r] = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        mx = fmaxf(mx, s_xch[((j & 1) * 2 + (half ^ 1)) * 128 + r]);
+        move = j == 0 || mx > 8.f;
+        up = mx;
+        any_move = __any_sync(0xffffffffu, move);  // rare after the first tile
+      }
       STAMP(4);
-      float rsum[4] = {0.f, 0.f, 0.f, 0.f};
-      uint32_t pk[32];
-#if LG_ATTN_MSUB
-      // scores arrive relative to m_ref (0 on the first tile).  Move the reference only on the first tile and when
-      // the maximum grew by more than 8 (factor 256); the new reference is rounded to bf16 so that the MMA subtracts
-      // exactly what this thread accounts for.
-      float delta = 0.f;
-      const bool move = j == 0 || mx > 8.f;
-      if (move) {
-        const float base = j == 0 ? 0.f : m_ref;
-        const float m_want = base + mx;
-        const __nv_bfloat16 hi = __float2bfloat16_rn(m_want);
-        const __nv_bfloat16 lo = __float2bfloat16_rn(m_want - __bfloat162float(hi));
-        const float m_abs = __bfloat162float(hi) + __bfloat162float(lo);
-        delta = m_abs - base;
-        m_ref = m_abs;
-        if (half == 0) {  // row r of Q_ext: 32-byte rows, (-hi, -lo) in the first two elements of the row
-          const uint32_t bits = ((uint32_t)(*reinterpret_cast<const unsigned short*>(&hi)) |
-                                 ((uint32_t)(*reinterpret_cast<const unsigned short*>(&lo)) << 16)) ^ 0x80008000u;
-          *reinterpret_cast<uint32_t*>(sQx + r * 32) = bits;
+      float delta = 0.f, alpha = 1.f;
+      if (any_move) {
+        // The new reference is rounded to hi + lo bf16 so that the MMA subtracts exactly what this thread accounts
+        // for; this tile was produced with the old one, so the difference is subtracted below.
+        if (!(mode != 0 || j == 0) && move) {
+          if (!(joint <= 0x1p70f)) { bad = true; move = false; }  // garbage ahead: the work item will be repeated
+          else if (j - last_move < 4) move = false;
+          else up = (float)((int)(__float_as_uint(joint) >> 23) - 127);
+        }
+        if (move) {
+          last_move = j;
+          const float m_want = m_ref + up;
+          const __nv_bfloat16 hi = __float2bfloat16_rn(m_want);
+          const __nv_bfloat16 lo = __float2bfloat16_rn(m_want - __bfloat162float(hi));
+          const float m_abs = __bfloat162float(hi) + __bfloat162float(lo);
+          delta = m_abs - m_ref;
+          m_ref = m_abs;
+          if (half == 0) {  // row r of Q_ext: 32-byte rows, (-hi, -lo) in the first two elements of the row
+            const uint32_t bits = ((uint32_t)(*reinterpret_cast<const unsigned short*>(&hi)) |
+                                   ((uint32_t)(*reinterpret_cast<const unsigned short*>(&lo)) << 16)) ^ 0x80008000u;
+            *reinterpret_cast<uint32_t*>(sQx + r * 32) = bits;
+          }
         }
         tc::fence_proxy_async();  // generic-proxy write -> visible to the next QK^T (async proxy)
+        alpha = j == 0 ? 0.f : ex2(-delta);
       }
-      const float alpha = j == 0 ? 0.f : ex2(-delta);  // 1 when unchanged
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(s_free);  // S is in registers and Q_ext is up to date: QK^T(j+1) may go
-      const bool any_move = __any_sync(0xffffffffu, move);
-      if (any_move) {  // rare: this tile was produced with the old reference
+      STAMP(3);
+      float tile_sum, pmax = -INFINITY;  // pmax: largest input of a polynomial lane
+      uint32_t pk[32];
+      if (any_move) {
+        LG_DEFERRED_BOOKKEEPING();
+        float rsum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           float p0 = __uint_as_float(sv[2 * i]) - delta, p1 = __uint_as_float(sv[2 * i + 1]) - delta;
           p0 = ex2(p0);
+          if (LG_POLY_HERE(i)) pmax = fmaxf(pmax, p1);
           p1 = LG_POLY_HERE(i) ? ex2_poly(p1) : ex2(p1);
           rsum[i & 3] += p0 + p1;
           pk[i] = tc::pack_bf16(p0, p1);
         }
+        tile_sum = (rsum[0] + rsum[1]) + (rsum[2] + rsum[3]);
       } else {
-#ifndef LG_ATTN_NO_SUM2  // packed f32x2 row sum: one issue slot per pair instead of two (0.682 -> 0.675 ms)
+        // packed f32x2 row sum: one issue slot per pair instead of two (0.682 -> 0.675 ms)
+        LG_DEFERRED_BOOKKEEPING();
+        float pend = -INFINITY;
+        bool have_pend = false;  // (compile-time after unrolling)
         float2 rs2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           float p0 = ex2(__uint_as_float(sv[2 * i])), p1 = __uint_as_float(sv[2 * i + 1]);
+          if (LG_POLY_HERE(i)) {  // two polynomial inputs per FMNMX3
+            if (have_pend) { pmax = max3(pmax, pend, p1); have_pend = false; }
+            else { pend = p1; have_pend = true; }
+          }
           p1 = LG_POLY_HERE(i) ? ex2_poly(p1) : ex2(p1);
           rs2[i & 1] = __fadd2_rn(rs2[i & 1], make_float2(p0, p1));
           pk[i] = tc::pack_bf16(p0, p1);
         }
-        rsum[0] = rs2[0].x; rsum[1] = rs2[0].y; rsum[2] = rs2[1].x; rsum[3] = rs2[1].y;
-#else
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float p0 = ex2(__uint_as_float(sv[2 * i])), p1 = __uint_as_float(sv[2 * i + 1]);
-          p1 = LG_POLY_HERE(i) ? ex2_poly(p1) : ex2(p1);
-          rsum[i & 3] += p0 + p1;
-          pk[i] = tc::pack_bf16(p0, p1);
-        }
-#endif
+        if (have_pend) pmax = fmaxf(pmax, pend);
+        tile_sum = (rs2[0].x + rs2[0].y) + (rs2[1].x + rs2[1].y);
       }
-      const bool need_rescale = move;
-#else
-      // lazy rescale: keep the reference max unless it grows by more than 8 (factor 256)
-      float m_new = m_ref;
-      if (mx > m_ref + 8.f) m_new = mx;
-      const float alpha = ex2(m_ref - m_new);  // 1 when unchanged, 0 on the first tile
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float p0 = __uint_as_float(sv[2 * i]) - m_new, p1 = __uint_as_float(sv[2 * i + 1]) - m_new;
-        p0 = ex2(p0);
-        p1 = LG_POLY_HERE(i) ? ex2_poly(p1) : ex2(p1);
-        rsum[i & 3] += p0 + p1;
-        pk[i] = tc::pack_bf16(p0, p1);
-      }
-      const bool need_rescale = m_new != m_ref;
-      m_ref = m_new;
-#endif
-      l_part = l_part * alpha + ((rsum[0] + rsum[1]) + (rsum[2] + rsum[3]));
+      bad = bad || !(pmax <= 126.f);
+      l_part = l_part * alpha + tile_sum;
+      any_next = __any_sync(0xffffffffu, move_next);  // (exact mode: sums <= 128, never set)
+      sum_m1 = tile_sum;
       STAMP(5);
       if (j > 0) {
         tc::mbar_wait(pv_done, (j - 1) & 1);  // PV(j-1) retired: P is free, O is up to date
         tc::fence_after_sync();
         STAMP(6);
-        if (__any_sync(0xffffffffu, need_rescale)) {  // same rows in both half-warps -> same decision
+        if (any_move) {  // same rows in both half-warps -> same decision
           uint32_t o[32];
           tc::tmem_ld32(tmem + lane_base + TM_O + half * 32, o);
           tc::tmem_ld_wait();
@@ -408,8 +467,21 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     // combine the two partial row sums, normalise this thread's 32 output columns
     s_xch[(4 + half) * 128 + r] = l_part;
+    if (mode == 0) sum_row[((n_tiles - 1) & 3) * 256 + half] = sum_m1;
     asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
     const float l_sum = l_part + s_xch[(4 + (half ^ 1)) * 128 + r];
+    if (mode == 0) {  // the last three tiles' row sums have not been looked at yet
+      bool ok = !bad;
+#pragma unroll
+      for (int t = 1; t <= 3; ++t) {
+        if (n_tiles >= t) {
+          const float2 both = *reinterpret_cast<const float2*>(sum_row + ((n_tiles - t) & 3) * 256);
+          const float jt = both.x + both.y;
+          ok = ok && (jt <= 0x1p70f);
+        }
+      }
+      if (!ok) *panic = 1;
+    }
     tc::mbar_wait(pv_done, (n_tiles - 1) & 1);
     tc::fence_after_sync();
     const float inv = l_sum > 0.f ? 1.f / l_sum : 0.f;
@@ -431,6 +503,16 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
   tc::fence_before_sync();
   __syncthreads();
+  if (mode != 0 || *panic == 0) break;
+  // restart in the exact mode: every TMA load and MMA of pass 0 has been consumed (the softmax warps waited for the
+  // last P.V); fresh barrier set, Q_ext back to zero, O is overwritten by the first P.V (accumulate flag)
+  tc::fence_after_sync();
+  if (threadIdx.x < 256) reinterpret_cast<uint4*>(sQx)[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  }  // pass
   if (CL > 1) tc::cluster_sync();  // nobody retires while a peer may still multicast into its smem
   if (warp == 1) {
     tc::fence_after_sync();
@@ -467,7 +549,8 @@ static int launch_attention(const __nv_bfloat16* Q, const __nv_bfloat16* K, cons
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   static const unsigned stagger = getenv("LGB200_ATTN_STAGGER_NS") ? (unsigned)atoi(getenv("LGB200_ATTN_STAGGER_NS")) : 0u;  // (mattered before the instruction diet; 0 .. 1800 ns now within 1.5 %)
-  e = cudaLaunchKernelEx(&cfg, kern, tq, tk, tv, Lp, lens, kv_xor, ctx, dbg, stagger);
+  static const int start_mode = getenv("LGB200_ATTN_EXACT_MAX") ? atoi(getenv("LGB200_ATTN_EXACT_MAX")) : 0;  // 1: maximum before the exponentials on every tile (r1 behaviour)
+  e = cudaLaunchKernelEx(&cfg, kern, tq, tk, tv, Lp, lens, kv_xor, ctx, dbg, stagger, start_mode);
   if (e != cudaSuccess) return (int)e;
   LG_LAUNCH_CHECK();
   return LGB200_OK;

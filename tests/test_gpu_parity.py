@@ -289,6 +289,35 @@ def test_attention_bf16_large_and_drifting_logits(scale):
         torch.testing.assert_close(ctx[s, :n].float(), ref, atol=3e-2, rtol=3e-2)
 
 
+@pytest.mark.parametrize("key", [384, 385, 1000], ids=["mufu-lane", "poly-lane", "late"])
+@pytest.mark.parametrize("jump", [40.0, 240.0], ids=["jump40", "jump240"])
+def test_attention_bf16_outlier_key_after_first_tile(key, jump):
+    """Deferred-maximum mode of the bf16 kernel: after the first tile the exponentials run against the reference the
+    tile was produced with.  A key far above everything seen so far (jump40: absorbed, the reference moves one tile
+    later; jump240: beyond the fp32 range -> the CTA repeats its work item in the exact mode) must still give the
+    fp32 softmax, whether it sits in a MUFU lane or in a polynomial lane of the exponential loop."""
+    lib = _abi.load()
+    torch.manual_seed(11)
+    S, Lp = 2, 1152
+    lens = torch.tensor([1152, 1100], dtype=torch.int32, device=DEV)
+    u = torch.nn.functional.normalize(torch.randn(64, device=DEV), dim=0)
+    q = torch.randn(S, 4, Lp, 64, device=DEV) * 0.5 + 3.0 * u
+    k = torch.randn(S, 4, Lp, 64, device=DEV) * 0.5
+    k[:, :, key] = (jump / 3.0) * u
+    q[:, :, 5::7] -= 3.0 * u  # some rows do not see the outlier: their CTA mates do
+    q, k = q.to(torch.bfloat16), k.to(torch.bfloat16)
+    v = torch.randn(S, 4, Lp, 64, device=DEV).to(torch.bfloat16)
+    ctx = torch.zeros(S, Lp, 256, device=DEV, dtype=torch.bfloat16)
+    rc = lib.lgb200_attention(_abi.BF16, ptr(q), ptr(k), ptr(v), S, Lp, ptr(lens), 0, ptr(ctx), _stream())
+    assert rc == 0, lib.lgb200_error_string(rc)
+    for s in range(S):
+        n = int(lens[s])
+        sc = q[s, :, :n].double() @ k[s, :, :n].double().transpose(-1, -2) * math.log(2.0)
+        ref = (torch.softmax(sc, -1) @ v[s, :, :n].double()).permute(1, 0, 2).reshape(n, 256).float()
+        assert torch.isfinite(ctx[s, :n].float()).all()
+        torch.testing.assert_close(ctx[s, :n].float(), ref, atol=3e-2, rtol=3e-2)
+
+
 def test_attention_empty_keys_give_zeros():
     lib = _abi.load()
     S, Lp = 2, 128
