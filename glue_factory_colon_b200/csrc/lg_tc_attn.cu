@@ -57,7 +57,8 @@ constexpr int AT_XOFF = TILE_BYTES * (1 + KST + VST);             // Q_ext | K_e
 constexpr int AT_BAROFF = AT_XOFF + (LG_ATTN_MSUB ? 2 * XT_BYTES : 0);
 constexpr int AT_NBAR = 16;                // mbarriers per pass (15 used)
 constexpr int AT_BARBYTES = 2 * AT_NBAR * 8 + 64;  // two barrier sets (pass 0 / restart) + tmem slot + panic flag
-constexpr int AT_SMEM = AT_BAROFF + AT_BARBYTES + 14 * 128 * 4;  // + barriers + max/sum exchange [6][128] + tile sums [8][128]
+// + barriers + exchange ring [4 slots][128 rows][NP parts] fp32 (tile sums; maxima in the exact mode; final row sums)
+constexpr int at_smem(int np) { return AT_BAROFF + AT_BARBYTES + 4 * 128 * np * 4; }
 
 constexpr uint32_t TM_S = 0, TM_P = 128, TM_O = 192, TM_COLS = 256;
 
@@ -97,8 +98,9 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
-template <int CL>
-__global__ void __launch_bounds__(320, 2)
+// NP = softmax threads per query row (2: 8 softmax warps, 64 key columns each; 4: 16 warps, 32 columns each)
+template <int CL, int NP>
+__global__ void __launch_bounds__(64 + 128 * NP, 2)
 tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, int Lp, const int32_t* __restrict__ lens,
                     int kv_xor, __nv_bfloat16* __restrict__ ctx, int dbg_arg, unsigned stagger_ns, int start_mode) {
@@ -147,8 +149,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* bars_base = reinterpret_cast<uint64_t*>(smem + AT_BAROFF);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_base + 2 * AT_NBAR);
   volatile int* panic = reinterpret_cast<volatile int*>(tmem_slot + 1);
-  float* s_xch = reinterpret_cast<float*>(smem + AT_BAROFF + AT_BARBYTES);  // [6][128]
-  float* s_sum = s_xch + 6 * 128;  // [4 tiles][2 halves][128]: row sums per tile (deferred mode)
+  float* s_sum = reinterpret_cast<float*>(smem + AT_BAROFF + AT_BARBYTES);  // [4 slots][128 rows][NP parts]
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmQ);
@@ -160,8 +161,8 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       for (int i = 0; i < KST; ++i) { tc::mbar_init(b + 1 + i, 1); tc::mbar_init(b + 1 + KST + i, CL); }
       for (int i = 0; i < VST; ++i) { tc::mbar_init(b + 1 + 2 * KST + i, 1); tc::mbar_init(b + 1 + 2 * KST + VST + i, CL); }
       tc::mbar_init(b + 1 + 2 * KST + 2 * VST + 0, 1);  // s_full
-      tc::mbar_init(b + 1 + 2 * KST + 2 * VST + 1, 8);  // s_free
-      tc::mbar_init(b + 1 + 2 * KST + 2 * VST + 2, 8);  // p_ready
+      tc::mbar_init(b + 1 + 2 * KST + 2 * VST + 1, 4 * NP);  // s_free
+      tc::mbar_init(b + 1 + 2 * KST + 2 * VST + 2, 4 * NP);  // p_ready
       tc::mbar_init(b + 1 + 2 * KST + 2 * VST + 3, 1);  // pv_done
     }
     *panic = 0;
@@ -177,8 +178,8 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (threadIdx.x < 256) {
     reinterpret_cast<uint4*>(sQx)[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
     reinterpret_cast<uint4*>(sKx)[threadIdx.x] = make_uint4(0x3f803f80u, 0u, 0u, 0u);  // two leading ones
-    reinterpret_cast<uint4*>(s_sum)[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);         // [8][128] floats
   }
+  for (int i = threadIdx.x; i < 4 * 128 * NP / 4; i += blockDim.x) reinterpret_cast<uint4*>(s_sum)[i] = make_uint4(0u, 0u, 0u, 0u);
   tc::fence_proxy_async();
 #endif
   if (warp == 1) tc::tmem_alloc(tmem_slot, TM_COLS);
@@ -301,11 +302,12 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       MSTAMP(5);
     }
   } else {
-    // softmax: 8 warps, two threads per query row.  Warp (quarter, half) owns TMEM lanes
-    // quarter*32.. and key columns half*64..+64 of the score tile; the two threads of a row
-    // exchange their partial row maximum through shared memory (named barrier per quarter).
+    // softmax: 4 * NP warps, NP threads per query row.  Warp (quarter, part) owns TMEM lanes quarter*32.. and key
+    // columns part*COLS..+COLS of the score tile; the threads of a row talk through the shared-memory ring.
+    constexpr int COLS = AT_BN / NP;   // score columns per thread
+    constexpr int OC = LG_DH / NP;     // output columns per thread
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int part = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     // m_ref: the reference the running sum, O and (through Q_ext) the arriving score tiles are expressed in; both
@@ -322,12 +324,20 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     float m_ref = 0.f, l_part = 0.f, sum_m1 = 0.f, joint_next = 0.f;
     bool bad = false, move_next = false, any_next = false;
     int last_move = -4;
-    float* const sum_row = s_sum + r * 2;  // [slot][row][half]
+    float* const sum_row = s_sum + r * NP;  // [slot][row][part]
+    auto row_total = [&](int slot) -> float {  // all parts of this row in a slot, summed in a fixed order
+      if constexpr (NP == 2) {
+        const float2 v = *reinterpret_cast<const float2*>(sum_row + slot * (128 * NP));
+        return v.x + v.y;
+      } else {
+        const float4 v = *reinterpret_cast<const float4*>(sum_row + slot * (128 * NP));
+        return (v.x + v.y) + (v.z + v.w);
+      }
+    };
 #define LG_DEFERRED_BOOKKEEPING()                                                                                  \
     do { /* unconditional and branch-free: stays inside the unrolled loop's basic block; tiles < 0 read zeros */   \
-      sum_row[((j + 3) & 3) * 256 + half] = sum_m1;                                                  /* tile j-1 */ \
-      const float2 both = *reinterpret_cast<const float2*>(sum_row + ((j + 1) & 3) * 256);           /* tile j-3 */ \
-      joint_next = both.x + both.y;                                                                                \
+      sum_row[((j + 3) & 3) * (128 * NP) + part] = sum_m1;                                           /* tile j-1 */ \
+      joint_next = row_total((j + 1) & 3);                                                           /* tile j-3 */ \
       move_next = !(joint_next <= 0x1p24f);                                                                        \
     } while (0)
     const bool rec = (dbg_in & 16) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0;
@@ -339,15 +349,15 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tc::mbar_wait(s_full, j & 1);
       tc::fence_after_sync();
       STAMP(1);
-      uint32_t sv[64];
-      tc::tmem_ld32(tmem + lane_base + TM_S + half * 64, sv);
-      tc::tmem_ld32(tmem + lane_base + TM_S + half * 64 + 32, sv + 32);
+      uint32_t sv[COLS];
+#pragma unroll
+      for (int c = 0; c < COLS; c += 32) tc::tmem_ld32(tmem + lane_base + TM_S + part * COLS + c, sv + c);
       tc::tmem_ld_wait();
       STAMP(2);
-      const int valid = nk - j * AT_BN - half * 64;  // valid keys among this thread's 64 columns
-      if (valid < 64) {
+      const int valid = nk - j * AT_BN - part * COLS;  // valid keys among this thread's columns
+      if (valid < COLS) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) {
+        for (int i = 0; i < COLS; ++i) {
           if (i >= valid) sv[i] = 0xff800000u;  // -inf
         }
       }
@@ -359,16 +369,19 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
         for (int i = 0; i < 4; ++i) mxs[i] = __uint_as_float(sv[i]);
 #pragma unroll
-#ifdef LG_ATTN_NO_MAX3
-        for (int i = 4; i < 64; ++i) mxs[i & 3] = fmaxf(mxs[i & 3], __uint_as_float(sv[i]));
-#else
-        for (int i = 4; i < 64; i += 2)  // FMNMX3: one issue slot for two elements
-          mxs[(i >> 1) & 3] = max3(mxs[(i >> 1) & 3], __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
-#endif
+        for (int i = 4; i < COLS; ++i) mxs[i & 3] = fmaxf(mxs[i & 3], __uint_as_float(sv[i]));
         float mx = fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3]));
-        s_xch[((j & 1) * 2 + half) * 128 + r] = mx;
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-        mx = fmaxf(mx, s_xch[((j & 1) * 2 + (half ^ 1)) * 128 + r]);
+        // exchange through ring slot j & 1: in the deferred mode (first tile only) slot 0 is next written by the
+        // publishers of tile 0's sums, each into its own part, after everyone has read the maxima
+        sum_row[(j & 1) * (128 * NP) + part] = mx;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "n"(32 * NP) : "memory");
+        if constexpr (NP == 2) {
+          const float2 v = *reinterpret_cast<const float2*>(sum_row + (j & 1) * (128 * NP));
+          mx = fmaxf(v.x, v.y);
+        } else {
+          const float4 v = *reinterpret_cast<const float4*>(sum_row + (j & 1) * (128 * NP));
+          mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+        }
         move = j == 0 || mx > 8.f;
         up = mx;
         any_move = __any_sync(0xffffffffu, move);  // rare after the first tile
@@ -391,7 +404,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const float m_abs = __bfloat162float(hi) + __bfloat162float(lo);
           delta = m_abs - m_ref;
           m_ref = m_abs;
-          if (half == 0) {  // row r of Q_ext: 32-byte rows, (-hi, -lo) in the first two elements of the row
+          if (part == 0) {  // row r of Q_ext: 32-byte rows, (-hi, -lo) in the first two elements of the row
             const uint32_t bits = ((uint32_t)(*reinterpret_cast<const unsigned short*>(&hi)) |
                                    ((uint32_t)(*reinterpret_cast<const unsigned short*>(&lo)) << 16)) ^ 0x80008000u;
             *reinterpret_cast<uint32_t*>(sQx + r * 32) = bits;
@@ -405,12 +418,12 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (lane == 0) tc::mbar_arrive(s_free);  // S is in registers and Q_ext is up to date: QK^T(j+1) may go
       STAMP(3);
       float tile_sum, pmax = -INFINITY;  // pmax: largest input of a polynomial lane
-      uint32_t pk[32];
+      uint32_t pk[COLS / 2];
       if (any_move) {
         LG_DEFERRED_BOOKKEEPING();
         float rsum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < COLS / 2; ++i) {
           float p0 = __uint_as_float(sv[2 * i]) - delta, p1 = __uint_as_float(sv[2 * i + 1]) - delta;
           p0 = ex2(p0);
           if (LG_POLY_HERE(i)) pmax = fmaxf(pmax, p1);
@@ -426,7 +439,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         bool have_pend = false;  // (compile-time after unrolling)
         float2 rs2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < COLS / 2; ++i) {
           float p0 = ex2(__uint_as_float(sv[2 * i])), p1 = __uint_as_float(sv[2 * i + 1]);
           if (LG_POLY_HERE(i)) {  // two polynomial inputs per FMNMX3
             if (have_pend) { pmax = max3(pmax, pend, p1); have_pend = false; }
@@ -449,15 +462,18 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tc::fence_after_sync();
         STAMP(6);
         if (any_move) {  // same rows in both half-warps -> same decision
-          uint32_t o[32];
-          tc::tmem_ld32(tmem + lane_base + TM_O + half * 32, o);
+          uint32_t o[OC];
+          if constexpr (OC == 32) tc::tmem_ld32(tmem + lane_base + TM_O + part * OC, o);
+          else tc::tmem_ld16(tmem + lane_base + TM_O + part * OC, o);
           tc::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tc::tmem_st32(tmem + lane_base + TM_O + half * 32, o);
+          for (int i = 0; i < OC; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          if constexpr (OC == 32) tc::tmem_st32(tmem + lane_base + TM_O + part * OC, o);
+          else tc::tmem_st16(tmem + lane_base + TM_O + part * OC, o);
         }
       }
-      tc::tmem_st32(tmem + lane_base + TM_P + half * 32, pk);
+      if constexpr (NP == 2) tc::tmem_st32(tmem + lane_base + TM_P + part * (COLS / 2), pk);
+      else tc::tmem_st16(tmem + lane_base + TM_P + part * (COLS / 2), pk);
       tc::tmem_st_wait();
       STAMP(7);
       tc::fence_before_sync();
@@ -465,33 +481,32 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (lane == 0) tc::mbar_arrive(p_ready);
       STAMP(8);
     }
-    // combine the two partial row sums, normalise this thread's 32 output columns
-    s_xch[(4 + half) * 128 + r] = l_part;
-    if (mode == 0) sum_row[((n_tiles - 1) & 3) * 256 + half] = sum_m1;
-    asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-    const float l_sum = l_part + s_xch[(4 + (half ^ 1)) * 128 + r];
+    // combine the partial row sums (ring slot n_tiles & 3 is the one no pending tile sum lives in; the exact mode, whose
+    // maxima use slots 0 and 1, gets slot 2), normalise this thread's output columns
+    const int fin_slot = mode == 0 ? (n_tiles & 3) : 2;
+    sum_row[fin_slot * (128 * NP) + part] = l_part;
+    if (mode == 0) sum_row[((n_tiles - 1) & 3) * (128 * NP) + part] = sum_m1;
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "n"(32 * NP) : "memory");
+    const float l_sum = row_total(fin_slot);
     if (mode == 0) {  // the last three tiles' row sums have not been looked at yet
       bool ok = !bad;
 #pragma unroll
       for (int t = 1; t <= 3; ++t) {
-        if (n_tiles >= t) {
-          const float2 both = *reinterpret_cast<const float2*>(sum_row + ((n_tiles - t) & 3) * 256);
-          const float jt = both.x + both.y;
-          ok = ok && (jt <= 0x1p70f);
-        }
+        if (n_tiles >= t) ok = ok && (row_total((n_tiles - t) & 3) <= 0x1p70f);
       }
       if (!ok) *panic = 1;
     }
     tc::mbar_wait(pv_done, (n_tiles - 1) & 1);
     tc::fence_after_sync();
     const float inv = l_sum > 0.f ? 1.f / l_sum : 0.f;
-    uint32_t o[32];
-    tc::tmem_ld32(tmem + lane_base + TM_O + half * 32, o);
+    uint32_t o[OC];
+    if constexpr (OC == 32) tc::tmem_ld32(tmem + lane_base + TM_O + part * OC, o);
+    else tc::tmem_ld16(tmem + lane_base + TM_O + part * OC, o);
     tc::tmem_ld_wait();
     if (q0 + r < nq) {
-      uint4* dst = reinterpret_cast<uint4*>(ctx + ((size_t)s * Lp + q0 + r) * LG_D + h * LG_DH + half * 32);
+      uint4* dst = reinterpret_cast<uint4*>(ctx + ((size_t)s * Lp + q0 + r) * LG_D + h * LG_DH + part * OC);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < OC / 8; ++i) {
         uint4 w;
         w.x = tc::pack_bf16(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
         w.y = tc::pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
@@ -522,7 +537,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
 }  // namespace
 
-template <int CL>
+template <int CL, int NP>
 static int launch_attention(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* V, int S, int Lp,
                             const int32_t* lens, int kv_xor, __nv_bfloat16* ctx, int dbg, cudaStream_t st) {
   CUtensorMap tq, tk, tv;
@@ -532,13 +547,13 @@ static int launch_attention(const __nv_bfloat16* Q, const __nv_bfloat16* K, cons
   if ((rc = lg_make_tmap_bf16(&tq, Q, 2, d, sb, box))) return rc;
   if ((rc = lg_make_tmap_bf16(&tk, K, 2, d, sb, box_kv))) return rc;
   if ((rc = lg_make_tmap_bf16(&tv, V, 2, d, sb, box_kv))) return rc;
-  auto kern = tc_attention_kernel<CL>;
-  const int smem = (dbg & 15) == 3 ? 120 * 1024 : AT_SMEM;  // dbg 3: one CTA per SM
+  auto kern = tc_attention_kernel<CL, NP>;
+  const int smem = (dbg & 15) == 3 ? 120 * 1024 : at_smem(NP);  // dbg 3: one CTA per SM
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(Lp / AT_BM, LG_HEADS, S);
-  cfg.blockDim = dim3(320);
+  cfg.blockDim = dim3(64 + 128 * NP);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -565,9 +580,11 @@ int lg_tc_attention(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_b
   // softmax/MUFU side, not by L2->SM traffic, so K/V multicast stays opt-in (LGB200_ATTN_CL=2|4).
   int cl = 1;
   if (force_cl == 1 || force_cl == 2 || force_cl == 4) cl = (qt % force_cl == 0) ? force_cl : 1;
-  if (cl == 4) return launch_attention<4>(Q, K, V, S, Lp, lens, kv_xor, ctx, dbg, st);
-  if (cl == 2) return launch_attention<2>(Q, K, V, S, Lp, lens, kv_xor, ctx, dbg, st);
-  return launch_attention<1>(Q, K, V, S, Lp, lens, kv_xor, ctx, dbg, st);
+  static const int np = getenv("LGB200_ATTN_NP") ? atoi(getenv("LGB200_ATTN_NP")) : 2;  // softmax threads per query row
+  if (cl == 4) return launch_attention<4, 2>(Q, K, V, S, Lp, lens, kv_xor, ctx, dbg, st);
+  if (cl == 2) return launch_attention<2, 2>(Q, K, V, S, Lp, lens, kv_xor, ctx, dbg, st);
+  if (np == 4) return launch_attention<1, 4>(Q, K, V, S, Lp, lens, kv_xor, ctx, dbg, st);
+  return launch_attention<1, 2>(Q, K, V, S, Lp, lens, kv_xor, ctx, dbg, st);
 }
 
 extern "C" int lgb200_debug_attn_times(long long* host_out, int n) {
