@@ -186,10 +186,153 @@ class LightGlue(nn.Module):
     def compile(self, mode="reduce-overhead"):  # lightglue.py:410-420: nothing to compile
         return self
 
+    # ---- loss (forward values) ------------------------------------------
+
+    def _log_assignment_of(self, lib, prec, d0, d1, layer: int, token_layer: Optional[int] = None):
+        """MatchAssignment `layer` applied to descriptors d0 [B,m,256] / d1 [B,n,256] (lightglue.py:279-288 as called
+        from loss_params, :589-595): the same kernels as the forward's assignment stage.  Returns scores [B,m+1,n+1]
+        and, if asked, the token-confidence logits of `token_layer` on the same descriptors (lightglue.py:83-84)."""
+        bf = prec == BF16
+        dev = d0.device
+        B, m, _ = d0.shape
+        n = d1.shape[1]
+        W = self._pack(prec, dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        S = 2 * B
+        Lp = max(128, ((max(m, n) + 127) // 128) * 128)
+        T = S * Lp
+        f32 = dict(device=dev, dtype=torch.float32)
+        adt = dict(device=dev, dtype=torch.bfloat16 if bf else torch.float32)
+        lens = None
+        if m != Lp or n != Lp:
+            lens = torch.tensor([m, n] * B, device=dev, dtype=torch.int32)
+        x = torch.zeros(T, 256, **adt)
+        md = torch.zeros(T, 256, **adt)
+        for img, dsc, cnt in ((0, d0, m), (1, d1, n)):
+            dsc = dsc.to(torch.float32).contiguous()
+            x32_, x16_ = (None, x) if bf else (x, None)
+            check(lib.lgb200_pack_rows(ptr(dsc), B, cnt, 256, img, Lp, ptr(x32_), ptr(x16_), st), "pack_rows")
+        a = W["assign"][layer]
+        o32, o16 = (None, md) if bf else (md, None)
+        check(
+            lib.lgb200_linear(
+                prec, EPI_ROWMAJOR, ptr(x), None, 256, ptr(a["fp_w"]), ptr(a["fp_b"]), T, 256, 256, ptr(lens), Lp,
+                0.25, 1.0, 1.0, None, None, ptr(o32), ptr(o16), None, None, 0, None, None, None, None, None, st,
+            ),
+            "lgb200_linear",
+        )
+        z = torch.zeros(T, **f32)
+        lse = torch.zeros(T, **f32)
+        check(lib.lgb200_rowdot(prec, ptr(x), ptr(a["m_w"]), ptr(a["m_b"]), S, Lp, ptr(lens), 0, ptr(z), st), "rowdot")
+        check(lib.lgb200_assign_lse(prec, ptr(md), S, Lp, ptr(lens), ptr(lse), st), "assign_lse")
+        scores = torch.empty(B, m + 1, n + 1, **f32)
+        check(lib.lgb200_assign_scores(prec, ptr(md), ptr(z), ptr(lse), B, Lp, ptr(lens), m + 1, n + 1, ptr(scores),
+                                       None, st), "assign_scores")
+        logits = None
+        if token_layer is not None:
+            tk = W["token"][token_layer]
+            lg_ = torch.zeros(T, **f32)
+            check(lib.lgb200_rowdot(prec, ptr(x), ptr(tk["w"]), ptr(tk["b"]), S, Lp, ptr(lens), 0, ptr(lg_), st), "rowdot")
+            lv = lg_.view(B, 2, Lp)
+            logits = (lv[:, 0, :m], lv[:, 1, :n])
+        return scores, logits
+
+    @staticmethod
+    def _reduce(lib, la, gt, st):
+        """lgb200_loss_reduce on one log-assignment matrix: per-row positive sums / counts / exp sums and the
+        row / column arg-maxima including the dustbins."""
+        B, R, C = la.shape
+        dev = la.device
+        rows = torch.zeros(3, B, R - 1, device=dev, dtype=torch.float32)
+        row_arg = torch.zeros(B, R - 1, device=dev, dtype=torch.int32)
+        col_arg = torch.zeros(B, C - 1, device=dev, dtype=torch.int32)
+        check(lib.lgb200_loss_reduce(ptr(la), B, R, C, ptr(gt), ptr(rows[0]), ptr(rows[1]), ptr(rows[2]), ptr(row_arg),
+                                     ptr(col_arg), st), "loss_reduce")
+        return rows[0].sum(1), rows[1].sum(1), rows[2], row_arg, col_arg
+
+    @torch.no_grad()
     def loss(self, pred, data):
-        # TwoViewPipeline.loss skips components raising NotImplementedError
-        # (reference two_view_pipeline.py:417-429).  Training is outside this path.
-        raise NotImplementedError("training loss is not part of the B200 inference hot path")
+        """LightGlue.loss (lightglue.py:588-637) -> (losses, metrics) with the reference's keys, FORWARD VALUES ONLY:
+        the B200 kernels have no backward pass, so the returned tensors carry no autograd graph (use them for
+        validation, `do_evaluation` in the reference's train.py:100-170; optimisation needs the reference module).
+        The dense [B,M+1,N+1] work -- MatchAssignment of every collected layer, the NLL sums of weight_loss
+        (models/utils/losses.py:6-26), row_norm and the arg-maxima of TokenConfidence.loss (:82-95) -- runs in the
+        library's kernels; what is left here is arithmetic on [B] and [B,N] vectors."""
+        lib = _abi.load()
+        conf = self.conf
+        r0, r1 = pred["ref_descriptors0"], pred["ref_descriptors1"]
+        if not r0.is_cuda:
+            raise _abi.LightGlueB200Error("glue_factory_colon_b200.LightGlue.loss runs on CUDA tensors only")
+        dev = r0.device
+        B, N, m, _ = r0.shape
+        n = r1.shape[2]
+        prec = self._precision()
+        st = torch.cuda.current_stream(dev).cuda_stream
+        L = conf.n_layers
+        gt = data["gt_assignment"].to(dev).to(torch.bool).contiguous()
+        assert gt.shape == (B, m, n), "gt_assignment must be [B, M, N]"
+        gm0, gm1 = data["gt_matches0"].to(dev), data["gt_matches1"].to(dev)
+        neg0, neg1 = (gm0 == -1).float(), (gm1 == -1).float()
+        num_neg0, num_neg1 = neg0.sum(-1).clamp(min=1.0), neg1.sum(-1).clamp(min=1.0)
+        bal = float(conf.loss.nll_balancing)
+
+        def nll_of(la):  # weight_loss + NLLLoss.forward (losses.py:6-26, :44-60)
+            pos_sum, pos_cnt, row_exp, row_arg, col_arg = self._reduce(lib, la, gt, st)
+            num_pos = pos_cnt.clamp(min=1.0)
+            nll_pos = -pos_sum / num_pos
+            nll_neg = (-(la[:, :m, n] * neg0).sum(-1) - (la[:, m, :n] * neg1).sum(-1)) / (num_neg0 + num_neg1)
+            nll = bal * nll_pos + (1 - bal) * nll_neg
+            return nll, nll_pos, nll_neg, num_pos, (row_exp, row_arg, col_arg)
+
+        la_last, _ = self._log_assignment_of(lib, prec, r0[:, -1], r1[:, -1], L - 1)
+        nll, nll_pos, nll_neg, num_pos, _ = nll_of(la_last)
+        losses = {
+            "total": nll, "last": nll.clone(), "assignment_nll": nll, "nll_pos": nll_pos, "nll_neg": nll_neg,
+            "num_matchable": num_pos, "num_unmatchable": (num_neg0 + num_neg1) / 2.0,
+        }
+        if self.training:
+            losses["confidence"] = torch.zeros_like(nll)
+        la_pred = pred["log_assignment"].to(torch.float32).contiguous()
+        _, _, row_exp_f, row_arg_f, col_arg_f = self._reduce(lib, la_pred, None, st)
+        losses["row_norm"] = row_exp_f.mean(1)  # lightglue.py:606
+        bce = torch.nn.functional.binary_cross_entropy_with_logits
+        sum_w = 1.0
+        for i in range(N - 1):
+            la_i, (lg0, lg1) = self._log_assignment_of(lib, prec, r0[:, i], r1[:, i], i, token_layer=i)
+            nll_i, _, _, _, (_, row_arg_i, col_arg_i) = nll_of(la_i)
+            g = float(conf.loss.gamma)
+            w = g ** (N - i - 1) if g > 0.0 else i + 1
+            sum_w += w
+            losses["total"] = losses["total"] + nll_i * w
+            c0, c1 = (row_arg_f == row_arg_i).float(), (col_arg_f == col_arg_i).float()
+            conf_i = (bce(lg0, c0, reduction="none").mean(-1) + bce(lg1, c1, reduction="none").mean(-1)) / 2.0
+            losses["confidence"] = losses["confidence"] + conf_i / (N - 1)
+        losses["total"] = losses["total"] / sum_w
+        if self.training:
+            losses["total"] = losses["total"] + losses["confidence"]
+        metrics = {} if self.training else self._matcher_metrics(pred, {"gt_matches0": gm0})
+        return losses, metrics
+
+    @staticmethod
+    def _matcher_metrics(pred, data):
+        """Recall / precision / accuracy / ranking AP of matches0 against gt_matches0, same definitions as the
+        reference's matcher_metrics (gluefactory/models/utils/metrics.py:5-57); [B,N] vector arithmetic."""
+        mt, gt, sc = pred["matches0"], data["gt_matches0"], pred["matching_scores0"]
+        same = (mt == gt).float()
+        in_recall, in_acc = (gt > -1).float(), (gt >= -1).float()
+        in_prec = ((mt > -1) & (gt >= -1)).float()
+        eps = 1e-8
+        order = torch.argsort(-sc)
+        tp, pm, rm = same.gather(-1, order), in_prec.gather(-1, order), in_recall.gather(-1, order)
+        prec_curve = torch.cumsum(tp * pm, -1) / (eps + torch.cumsum(pm, -1))
+        rec_curve = torch.cumsum(tp * rm, -1) / (eps + rm.sum(-1, keepdim=True))
+        ap = ((rec_curve[..., 1:] - rec_curve[..., :-1]) * prec_curve[:, None, -1]).sum(-1)
+        return {
+            "match_recall": (same * in_recall).sum(1) / (eps + in_recall.sum(1)),
+            "match_precision": (same * in_prec).sum(1) / (eps + in_prec.sum(1)),
+            "accuracy": (same * in_acc).sum(1) / (eps + in_acc.sum(1)),
+            "average_precision": ap,
+        }
 
     # ---- weight packing ------------------------------------------------------------------
 
@@ -402,6 +545,7 @@ class LightGlue(nn.Module):
 
         q_scale = LOG2E / math.sqrt(64.0)
         c_scale = math.sqrt(q_scale)
+        collected0, collected1 = [], []  # training mode: every layer's descriptors (lightglue.py:495-497)
         for i in range(L):
             w = W["layers"][i]
             la = lens_act
@@ -423,6 +567,10 @@ class LightGlue(nn.Module):
             linear(EPI_LN_GELU, x, w["cf0_w"], w["cf0_b"], 512, 512, A1=ctx if bf else msg, K0=256, gamma=w["cln_g"],
                    beta=w["cln_b"], out=hid, lens_=la)
             linear(EPI_ROWMAJOR, hid, w["cf3_w"], w["cf3_b"], 256, 512, resid=x, out=x, lens_=la)
+            if self.training:
+                xl = x.view(B, 2, Lp, 256)
+                collected0.append(xl[:, 0, :m].clone())
+                collected1.append(xl[:, 1, :n].clone())
             if i == L - 1 or not adaptive:
                 continue
             thr = thresholds[i]
@@ -501,6 +649,8 @@ class LightGlue(nn.Module):
             prune0 = torch.full((B, m), float(L), **f32)
             prune1 = torch.full((B, n), float(L), **f32)
             ref0, ref1 = xv[:, 0:1, :m], xv[:, 1:2, :n]
+        if self.training:  # [B, n_layers, N, 256] (lightglue.py:546-547)
+            ref0, ref1 = torch.stack(collected0, 1), torch.stack(collected1, 1)
         return {
             "matches0": m0,
             "matches1": m1,

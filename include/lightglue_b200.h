@@ -187,6 +187,19 @@ int lgb200_nn_match(const float* similarity, int B, int N, int M, const int32_t*
                     float distance_thresh, int mutual, int64_t* workspace, int64_t* m0, int64_t* m1,
                     float* ms0, float* ms1, void* stream);
 
+/* ---- loss-side reductions (forward values only) -------------------
+ * Replaces the dense [B,R,C] reductions behind LightGlue.loss, lightglue.py:588-637:
+ *   NLLLoss / weight_loss, gluefactory/models/utils/losses.py:6-26 -- row_pos[b,i] = sum_j la[b,i,j] *
+ *          gt[b,i,j] and row_cnt[b,i] = sum_j gt[b,i,j] over the inner block (i < R-1, j < C-1);
+ *   losses["row_norm"], lightglue.py:606 -- row_exp[b,i] = sum_{j<C} exp(la[b,i,j]);
+ *   TokenConfidence.loss, lightglue.py:86-91 -- row_arg[b,i] = argmax_{j<C} la[b,i,j] for i < R-1 and
+ *          col_arg[b,j] = argmax_{i<R} la[b,i,j] for j < C-1 (torch.max: lowest index among equal values).
+ * gt_assignment is the reference's bool tensor data["gt_assignment"] [B,R-1,C-1] (one byte per entry).
+ * Any output pointer may be NULL; per-row results are written without atomics (bit-reproducible). */
+int lgb200_loss_reduce(const float* log_assignment, int B, int R, int C, const uint8_t* gt_assignment,
+                       float* row_pos, float* row_cnt, float* row_exp, int32_t* row_arg, int32_t* col_arg,
+                       void* stream);
+
 /* ---- adaptive depth (early exit) ---------------------------------------------------------
  * Replaces check_if_stop, lightglue.py:569-580.  conf [S,Lp] = sigmoid token
  * confidences; pair b stops iff 1 - count(conf < thr)/total[b] > depth_conf
