@@ -114,3 +114,14 @@ extern "C" int lgb200_assign_scores(int precision, const void* md, const float* 
     return lg_tc_assign_scores((const __nv_bfloat16*)md, z, lse, B, Lp, lens, R, C, scores, best_ws, st);
   return LGB200_ERR_PRECISION;
 }
+
+extern "C" int lgb200_assign_loss(int precision, const void* md, const float* z, const float* lse, int B, int Lp,
+                                  const int32_t* lens, int R, int C, const uint8_t* gt_assignment, float* row_pos,
+                                  float* row_cnt, float* row_exp, int32_t* row_arg, int32_t* col_arg, void* workspace,
+                                  void* stream) {
+  if (!md || !z || !lse || !gt_assignment || !row_pos || !row_cnt || !row_exp || !workspace) return LGB200_ERR_NULL;
+  if (B <= 0 || Lp <= 0 || Lp % 128 || R < 1 || C < 1 || R - 1 > Lp || C - 1 > Lp) return LGB200_ERR_SHAPE;
+  if (precision != LGB200_BF16) return LGB200_ERR_PRECISION;  // fp32: lgb200_assign_scores + lgb200_loss_reduce
+  return lg_tc_assign_loss((const __nv_bfloat16*)md, z, lse, B, Lp, lens, R, C, gt_assignment, row_pos, row_cnt,
+                           row_exp, row_arg, col_arg, workspace, lg_stream(stream));
+}

@@ -26,3 +26,6 @@ int lg_tc_assign_lse(const __nv_bfloat16* md, int S, int Lp, const int32_t* lens
                      cudaStream_t st);
 int lg_tc_assign_scores(const __nv_bfloat16* md, const float* z, const float* lse, int B, int Lp,
                         const int32_t* lens, int R, int C, float* scores, void* best_ws, cudaStream_t st);
+int lg_tc_assign_loss(const __nv_bfloat16* md, const float* z, const float* lse, int B, int Lp, const int32_t* lens,
+                      int R, int C, const uint8_t* gt, float* row_pos, float* row_cnt, float* row_exp,
+                      int32_t* row_arg, int32_t* col_arg, void* best_ws, cudaStream_t st);

@@ -44,12 +44,24 @@ __device__ __forceinline__ void amax_merge(float& va, int& ia, float vb, int ib)
 // 1.075 GB at 0.88 TB/s (1.30 ms at 64 pairs x 2048).  Now 8 warps, each owning 32 rows x 64 columns of a tile,
 // finished values staged transposed in shared memory, an unrolled store loop (32 independent 128-byte row
 // segments in flight per warp) and the column constants prefetched one chunk ahead: 0.63 ms (1.9 TB/s).
-template <bool SCORES>
+// LOSS (third mode): pass 2 without the store -- the finished values feed, per row, the sums
+// sum_j la*gt, sum_j gt and sum_j exp(la) (weight_loss / row_norm of LightGlue.loss) and the two arg-maxima
+// (TokenConfidence.loss); the N x M matrix of an intermediate layer is never written at all.
+struct AsLoss {
+  const uint8_t* gt;  // [B, R-1, C-1] bool
+  float* row_pos;     // [B, R-1] each, zero-initialised: the two column halves of a row add into them (a + b is
+  float* row_cnt;     // commutative, so the result does not depend on which half arrives first)
+  float* row_exp;
+};
+
+template <int MODE>
 __global__ void __launch_bounds__(AS_THREADS, 1)
 tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t* __restrict__ lens,
                  const float* __restrict__ z, const float* __restrict__ lse_in, float* __restrict__ lse_out,
                  int R, int C, float* __restrict__ scores, unsigned long long* __restrict__ best0,
-                 unsigned long long* __restrict__ best1) {
+                 unsigned long long* __restrict__ best1, AsLoss ls) {
+  constexpr bool SCORES = MODE != 0;  // passes 2 (scores written) and 3 (loss reductions)
+  constexpr bool LOSS = MODE == 2;
   // SCORES: blockIdx.y = pair b, rows from sequence 2b.  LSE: blockIdx.y = sequence s.
   const int s = SCORES ? 2 * blockIdx.y : blockIdx.y;
   const int so = s ^ 1;
@@ -148,6 +160,8 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t
     float* xc = xp + AS_XP;      // this chunk's 32 column constants
     float rbest = -INFINITY;     // fused filter_matches: running row argmax over this warp's columns
     int ridx = 0;
+    float a_pos = 0.f, a_cnt = 0.f, a_exp = 0.f;  // LOSS: this thread's row, this warp's columns
+    const bool gt16 = LOSS && ((C - 1) % 16 == 0) && ((reinterpret_cast<uintptr_t>(ls.gt) & 15) == 0);
     float pf_z = 0.f, pf_lse = 0.f;  // prefetched z / lse of the next 32-column chunk (lane = column)
     if (SCORES && half * 64 + lane < nk) {
       pf_z = z[(size_t)so * Lp + half * 64 + lane];
@@ -218,9 +232,35 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t
 #pragma unroll
             for (int i = 0; i < 32; ++i) amax_merge(rbest, ridx, val[i], cb + i);
           }
+          if constexpr (LOSS) {
+            if (row < nq) {
+              const uint8_t* g = ls.gt + ((size_t)blockIdx.y * (R - 1) + row) * (C - 1) + cb;
+              uint32_t gw[8];  // 32 ground-truth bytes of this row
+              if (gt16 && cb + 32 <= nk) {
+                const uint4 g0 = reinterpret_cast<const uint4*>(g)[0], g1 = reinterpret_cast<const uint4*>(g)[1];
+                gw[0] = g0.x; gw[1] = g0.y; gw[2] = g0.z; gw[3] = g0.w;
+                gw[4] = g1.x; gw[5] = g1.y; gw[6] = g1.z; gw[7] = g1.w;
+              } else {
+#pragma unroll
+                for (int w = 0; w < 8; ++w) {
+                  gw[w] = 0;
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    if (cb + 4 * w + k < nk) gw[w] |= (uint32_t)g[4 * w + k] << (8 * k);
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                if (cb + i < nk) {  // (columns past the end carry -inf)
+                  a_exp += __expf(val[i]);
+                  if ((gw[i >> 2] >> (8 * (i & 3))) & 0xffu) { a_pos += val[i]; a_cnt += 1.f; }
+                }
+              }
+            }
+          }
           __syncwarp();
           // column phase (thread = column): every warp store is one contiguous 128-byte row segment
-          float* out = scores + ((size_t)blockIdx.y * R + m0 + quarter * 32) * C + col;
+          float* out = LOSS ? nullptr : scores + ((size_t)blockIdx.y * R + m0 + quarter * 32) * C + col;
           const int rows_here = min(32, nq - (m0 + quarter * 32));
           if (col < nk) {
             float cbest = -INFINITY;
@@ -230,7 +270,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t
 #pragma unroll
               for (int rr = 0; rr < 32; ++rr) {
                 cv[rr] = xp[rr * 33 + lane];
-                out[(size_t)rr * C] = cv[rr];
+                if constexpr (!LOSS) out[(size_t)rr * C] = cv[rr];
               }
               if (best1) {
 #pragma unroll
@@ -239,7 +279,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t
             } else {
               for (int rr = 0; rr < rows_here; ++rr) {
                 const float val = xp[rr * 33 + lane];
-                out[(size_t)rr * C] = val;
+                if constexpr (!LOSS) out[(size_t)rr * C] = val;
                 if (val > cbest || (val != val && cbest == cbest)) { cbest = val; cidx = rr; }
               }
             }
@@ -265,6 +305,14 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t
       // both column halves of a row race on one packed (value, ~index) word: 64-bit max keeps the larger value
       // and, among equal values, the lower index (best0 is zeroed by the caller)
       if (best0 && row < nq) atomicMax(best0 + (size_t)blockIdx.y * R + row, fm_pack(rbest, ridx));
+      if constexpr (LOSS) {
+        if (row < nq) {
+          const size_t o = (size_t)blockIdx.y * (R - 1) + row;
+          atomicAdd(ls.row_pos + o, a_pos);
+          atomicAdd(ls.row_cnt + o, a_cnt);
+          atomicAdd(ls.row_exp + o, a_exp);
+        }
+      }
     }
   }
   tc::fence_before_sync();
@@ -272,6 +320,30 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t
   if (warp == 1) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem, 256);
+  }
+}
+
+// LOSS: arg-maxima including the dustbins from the packed inner maxima, and the dustbin column's share of row_exp.
+// torch.max tie rule: the dustbin has the highest index, so it wins only if strictly larger (or the first NaN).
+__global__ void assign_loss_finish_kernel(const float* __restrict__ z, int Lp, int R, int C,
+                                          const unsigned long long* __restrict__ best0,
+                                          const unsigned long long* __restrict__ best1, float* __restrict__ row_exp,
+                                          int32_t* __restrict__ row_arg, int32_t* __restrict__ col_arg) {
+  const int b = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < R - 1) {
+    const float dz = lg_logsigmoid(-z[(size_t)(2 * b) * Lp + t]);
+    const unsigned long long p = best0[(size_t)b * R + t];
+    const float v = fm_value(p);
+    const bool inner = C > 1 && p != 0ull && !(dz > v || (dz != dz && v == v));
+    if (row_arg) row_arg[(size_t)b * (R - 1) + t] = inner ? fm_index(p) : C - 1;
+    if (row_exp) row_exp[(size_t)b * (R - 1) + t] += __expf(dz);
+  }
+  if (t < C - 1 && col_arg) {
+    const float dz = lg_logsigmoid(-z[(size_t)(2 * b + 1) * Lp + t]);
+    const unsigned long long p = best1[(size_t)b * C + t];
+    const float v = fm_value(p);
+    const bool inner = R > 1 && p != 0ull && !(dz > v || (dz != dz && v == v));
+    col_arg[(size_t)b * (C - 1) + t] = inner ? fm_index(p) : R - 1;
   }
 }
 
@@ -305,11 +377,11 @@ int lg_tc_assign_lse(const __nv_bfloat16* md, int S, int Lp, const int32_t* lens
   CUtensorMap tm;
   int rc = make_md_map(&tm, md, S, Lp);
   if (rc) return rc;
-  cudaError_t e = cudaFuncSetAttribute(tc_assign_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AS_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(tc_assign_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AS_SMEM);
   if (e != cudaSuccess) return (int)e;
   dim3 grid(Lp / 128, S);
-  tc_assign_kernel<false><<<grid, AS_THREADS, AS_SMEM, st>>>(tm, Lp, lens, nullptr, nullptr, lse, 0, 0, nullptr, nullptr,
-                                                      nullptr);
+  tc_assign_kernel<0><<<grid, AS_THREADS, AS_SMEM, st>>>(tm, Lp, lens, nullptr, nullptr, lse, 0, 0, nullptr, nullptr,
+                                                          nullptr, AsLoss{});
   LG_LAUNCH_CHECK();
   return LGB200_OK;
 }
@@ -319,7 +391,7 @@ int lg_tc_assign_scores(const __nv_bfloat16* md, const float* z, const float* ls
   CUtensorMap tm;
   int rc = make_md_map(&tm, md, 2 * B, Lp);
   if (rc) return rc;
-  cudaError_t e = cudaFuncSetAttribute(tc_assign_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AS_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(tc_assign_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AS_SMEM);
   if (e != cudaSuccess) return (int)e;
   assign_border_kernel<<<dim3(R, B), 128, 0, st>>>(z, Lp, lens, R, C, scores);
   LG_LAUNCH_CHECK();
@@ -331,7 +403,38 @@ int lg_tc_assign_scores(const __nv_bfloat16* md, const float* z, const float* ls
   }
   if (R > 1 && C > 1) {
     dim3 grid((R - 1 + 127) / 128, B);
-    tc_assign_kernel<true><<<grid, AS_THREADS, AS_SMEM, st>>>(tm, Lp, lens, z, lse, nullptr, R, C, scores, best0, best1);
+    tc_assign_kernel<1><<<grid, AS_THREADS, AS_SMEM, st>>>(tm, Lp, lens, z, lse, nullptr, R, C, scores, best0, best1,
+                                                            AsLoss{});
+    LG_LAUNCH_CHECK();
+  }
+  return LGB200_OK;
+}
+
+int lg_tc_assign_loss(const __nv_bfloat16* md, const float* z, const float* lse, int B, int Lp, const int32_t* lens,
+                      int R, int C, const uint8_t* gt, float* row_pos, float* row_cnt, float* row_exp,
+                      int32_t* row_arg, int32_t* col_arg, void* best_ws, cudaStream_t st) {
+  CUtensorMap tm;
+  int rc = make_md_map(&tm, md, 2 * B, Lp);
+  if (rc) return rc;
+  cudaError_t e = cudaFuncSetAttribute(tc_assign_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AS_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  unsigned long long* best0 = reinterpret_cast<unsigned long long*>(best_ws);
+  unsigned long long* best1 = best0 + (size_t)B * R;
+  if ((e = cudaMemsetAsync(best_ws, 0, sizeof(unsigned long long) * (size_t)B * (R + C), st)) != cudaSuccess) return (int)e;
+  const size_t nrow = sizeof(float) * (size_t)B * (R - 1);
+  if ((e = cudaMemsetAsync(row_pos, 0, nrow, st)) != cudaSuccess) return (int)e;
+  if ((e = cudaMemsetAsync(row_cnt, 0, nrow, st)) != cudaSuccess) return (int)e;
+  if ((e = cudaMemsetAsync(row_exp, 0, nrow, st)) != cudaSuccess) return (int)e;
+  if (R > 1 && C > 1) {
+    dim3 grid((R - 1 + 127) / 128, B);
+    tc_assign_kernel<2><<<grid, AS_THREADS, AS_SMEM, st>>>(tm, Lp, lens, z, lse, nullptr, R, C, nullptr, best0, best1,
+                                                            AsLoss{gt, row_pos, row_cnt, row_exp});
+    LG_LAUNCH_CHECK();
+  }
+  const int nmax = (R > C ? R : C) - 1;
+  if (nmax > 0) {
+    assign_loss_finish_kernel<<<dim3((nmax + 255) / 256, B), 256, 0, st>>>(z, Lp, R, C, best0, best1, row_exp, row_arg,
+                                                                          col_arg);
     LG_LAUNCH_CHECK();
   }
   return LGB200_OK;

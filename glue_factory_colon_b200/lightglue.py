@@ -188,10 +188,12 @@ class LightGlue(nn.Module):
 
     # ---- loss (forward values) ------------------------------------------
 
-    def _log_assignment_of(self, lib, prec, d0, d1, layer: int, token_layer: Optional[int] = None):
+    def _log_assignment_of(self, lib, prec, d0, d1, layer: int, gt, token_layer: Optional[int] = None):
         """MatchAssignment `layer` applied to descriptors d0 [B,m,256] / d1 [B,n,256] (lightglue.py:279-288 as called
-        from loss_params, :589-595): the same kernels as the forward's assignment stage.  Returns scores [B,m+1,n+1]
-        and, if asked, the token-confidence logits of `token_layer` on the same descriptors (lightglue.py:83-84)."""
+        from loss_params, :589-595) and the loss reductions on its output.  fp32: the forward's assignment kernels
+        write scores [B,m+1,n+1], lgb200_loss_reduce reads them.  bf16: lgb200_assign_loss, the tcgen05 pass 2 with the
+        reductions in its epilogue -- the matrix is never written.  Returns (pos_sum, pos_cnt, row_exp, row_arg,
+        col_arg, dustbin column la[:, :m, n], dustbin row la[:, m, :n], token logits of `token_layer` or None)."""
         bf = prec == BF16
         dev = d0.device
         B, m, _ = d0.shape
@@ -225,9 +227,24 @@ class LightGlue(nn.Module):
         lse = torch.zeros(T, **f32)
         check(lib.lgb200_rowdot(prec, ptr(x), ptr(a["m_w"]), ptr(a["m_b"]), S, Lp, ptr(lens), 0, ptr(z), st), "rowdot")
         check(lib.lgb200_assign_lse(prec, ptr(md), S, Lp, ptr(lens), ptr(lse), st), "assign_lse")
-        scores = torch.empty(B, m + 1, n + 1, **f32)
-        check(lib.lgb200_assign_scores(prec, ptr(md), ptr(z), ptr(lse), B, Lp, ptr(lens), m + 1, n + 1, ptr(scores),
-                                       None, st), "assign_scores")
+        R, C = m + 1, n + 1
+        if bf:
+            rows = torch.empty(3, B, m, **f32)
+            row_arg = torch.empty(B, m, device=dev, dtype=torch.int32)
+            col_arg = torch.empty(B, n, device=dev, dtype=torch.int32)
+            ws = torch.empty(B * (R + C), device=dev, dtype=torch.int64)
+            check(lib.lgb200_assign_loss(prec, ptr(md), ptr(z), ptr(lse), B, Lp, ptr(lens), R, C, ptr(gt), ptr(rows[0]),
+                                         ptr(rows[1]), ptr(rows[2]), ptr(row_arg), ptr(col_arg), ptr(ws), st), "assign_loss")
+            pos_sum, pos_cnt, row_exp = rows[0].sum(1), rows[1].sum(1), rows[2]
+            zv = z.view(B, 2, Lp)
+            ls = torch.nn.functional.logsigmoid
+            dust0, dust1 = ls(-zv[:, 0, :m]), ls(-zv[:, 1, :n])  # lightglue.py:266-267
+        else:
+            scores = torch.empty(B, R, C, **f32)
+            check(lib.lgb200_assign_scores(prec, ptr(md), ptr(z), ptr(lse), B, Lp, ptr(lens), R, C, ptr(scores), None, st),
+                  "assign_scores")
+            pos_sum, pos_cnt, row_exp, row_arg, col_arg = self._reduce(lib, scores, gt, st)
+            dust0, dust1 = scores[:, :m, n], scores[:, m, :n]
         logits = None
         if token_layer is not None:
             tk = W["token"][token_layer]
@@ -235,7 +252,7 @@ class LightGlue(nn.Module):
             check(lib.lgb200_rowdot(prec, ptr(x), ptr(tk["w"]), ptr(tk["b"]), S, Lp, ptr(lens), 0, ptr(lg_), st), "rowdot")
             lv = lg_.view(B, 2, Lp)
             logits = (lv[:, 0, :m], lv[:, 1, :n])
-        return scores, logits
+        return pos_sum, pos_cnt, row_exp, row_arg, col_arg, dust0, dust1, logits
 
     @staticmethod
     def _reduce(lib, la, gt, st):
@@ -276,16 +293,16 @@ class LightGlue(nn.Module):
         num_neg0, num_neg1 = neg0.sum(-1).clamp(min=1.0), neg1.sum(-1).clamp(min=1.0)
         bal = float(conf.loss.nll_balancing)
 
-        def nll_of(la):  # weight_loss + NLLLoss.forward (losses.py:6-26, :44-60)
-            pos_sum, pos_cnt, row_exp, row_arg, col_arg = self._reduce(lib, la, gt, st)
+        def nll_of(layer_idx, mod, token_layer=None):  # weight_loss + NLLLoss.forward (losses.py:6-26, :44-60)
+            pos_sum, pos_cnt, _, row_arg, col_arg, dust0, dust1, logits = self._log_assignment_of(
+                lib, prec, r0[:, layer_idx], r1[:, layer_idx], mod, gt, token_layer)
             num_pos = pos_cnt.clamp(min=1.0)
             nll_pos = -pos_sum / num_pos
-            nll_neg = (-(la[:, :m, n] * neg0).sum(-1) - (la[:, m, :n] * neg1).sum(-1)) / (num_neg0 + num_neg1)
+            nll_neg = (-(dust0 * neg0).sum(-1) - (dust1 * neg1).sum(-1)) / (num_neg0 + num_neg1)
             nll = bal * nll_pos + (1 - bal) * nll_neg
-            return nll, nll_pos, nll_neg, num_pos, (row_exp, row_arg, col_arg)
+            return nll, nll_pos, nll_neg, num_pos, row_arg, col_arg, logits
 
-        la_last, _ = self._log_assignment_of(lib, prec, r0[:, -1], r1[:, -1], L - 1)
-        nll, nll_pos, nll_neg, num_pos, _ = nll_of(la_last)
+        nll, nll_pos, nll_neg, num_pos, _, _, _ = nll_of(-1, L - 1)
         losses = {
             "total": nll, "last": nll.clone(), "assignment_nll": nll, "nll_pos": nll_pos, "nll_neg": nll_neg,
             "num_matchable": num_pos, "num_unmatchable": (num_neg0 + num_neg1) / 2.0,
@@ -298,8 +315,7 @@ class LightGlue(nn.Module):
         bce = torch.nn.functional.binary_cross_entropy_with_logits
         sum_w = 1.0
         for i in range(N - 1):
-            la_i, (lg0, lg1) = self._log_assignment_of(lib, prec, r0[:, i], r1[:, i], i, token_layer=i)
-            nll_i, _, _, _, (_, row_arg_i, col_arg_i) = nll_of(la_i)
+            nll_i, _, _, _, row_arg_i, col_arg_i, (lg0, lg1) = nll_of(i, i, token_layer=i)
             g = float(conf.loss.gamma)
             w = g ** (N - i - 1) if g > 0.0 else i + 1
             sum_w += w

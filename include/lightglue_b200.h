@@ -200,6 +200,17 @@ int lgb200_loss_reduce(const float* log_assignment, int B, int R, int C, const u
                        float* row_pos, float* row_cnt, float* row_exp, int32_t* row_arg, int32_t* col_arg,
                        void* stream);
 
+/* Fused form for LGB200_BF16 (tcgen05): MatchAssignment pass 2 of lgb200_assign_scores with the reductions above in
+ * its epilogue instead of the store -- the [B,R,C] matrix of a layer that only the loss looks at (every layer but
+ * the last in training mode, lightglue.py:607-608) is never written.  Same outputs as lgb200_loss_reduce on the
+ * matrix lgb200_assign_scores would have produced; md / z / lse as for lgb200_assign_scores; lens entries must be
+ * R-1 / C-1 (or lens NULL when R-1 == C-1 == Lp).  workspace: 8 * B * (R + C) bytes.  LGB200_F32 is refused
+ * (LGB200_ERR_PRECISION): the fp32 parity mode materialises and calls lgb200_loss_reduce. */
+int lgb200_assign_loss(int precision, const void* md, const float* z, const float* lse, int B, int Lp,
+                       const int32_t* lens, int R, int C, const uint8_t* gt_assignment, float* row_pos,
+                       float* row_cnt, float* row_exp, int32_t* row_arg, int32_t* col_arg, void* workspace,
+                       void* stream);
+
 /* ---- adaptive depth (early exit) ---------------------------------------------------------
  * Replaces check_if_stop, lightglue.py:569-580.  conf [S,Lp] = sigmoid token
  * confidences; pair b stops iff 1 - count(conf < thr)/total[b] > depth_conf

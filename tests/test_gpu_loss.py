@@ -92,3 +92,47 @@ def test_forward_and_loss_bf16_within_the_bf16_envelope(golden_dir):
     for k in ("total", "last", "nll_pos", "nll_neg", "confidence", "row_norm"):
         torch.testing.assert_close(losses[k].cpu(), fx["losses"][k].float(), atol=0.05, rtol=0.02, msg=lambda m: f"{k}: {m}")
     assert torch.equal(losses["num_matchable"].cpu(), fx["losses"]["num_matchable"])
+
+
+@pytest.mark.parametrize("m,n", [(256, 256), (200, 179), (384, 130)], ids=["full", "ragged", "wide"])
+def test_fused_assign_loss_equals_scores_plus_reduce(m, n):
+    """lgb200_assign_loss (tcgen05 pass 2 with the loss reductions in its epilogue, nothing N x M written) against
+    lgb200_assign_scores + lgb200_loss_reduce on the same operands: arg-maxima identical, sums to fp32 rounding."""
+    lib = _abi.load()
+    g = torch.Generator().manual_seed(m + n)
+    B = 3
+    Lp = ((max(m, n) + 127) // 128) * 128
+    S = 2 * B
+    md = torch.zeros(S, Lp, 256, dtype=torch.bfloat16, device=DEV)
+    md[0::2, :m] = (torch.randn(B, m, 256, generator=g) * 0.35).to(DEV).to(torch.bfloat16)
+    md[1::2, :n] = (torch.randn(B, n, 256, generator=g) * 0.35).to(DEV).to(torch.bfloat16)
+    z = (torch.randn(S, Lp, generator=g) * 2).to(DEV)
+    z[0, 3] = 30.0   # dustbin-dominated and matchable-dominated rows / columns
+    z[1, 5] = -30.0
+    lens = None if m == Lp and n == Lp else torch.tensor([m, n] * B, dtype=torch.int32, device=DEV)
+    lse = torch.zeros(S, Lp, device=DEV)
+    assert lib.lgb200_assign_lse(_abi.BF16, ptr(md), S, Lp, ptr(lens), ptr(lse), _stream()) == 0
+    R, C = m + 1, n + 1
+    gt = (torch.rand(B, m, n, generator=g) < 0.01).to(DEV)
+    sc = torch.empty(B, R, C, device=DEV)
+    assert lib.lgb200_assign_scores(_abi.BF16, ptr(md), ptr(z), ptr(lse), B, Lp, ptr(lens), R, C, ptr(sc), None, _stream()) == 0
+    ref_rows = torch.zeros(3, B, m, device=DEV)
+    ref_ra = torch.zeros(B, m, device=DEV, dtype=torch.int32)
+    ref_ca = torch.zeros(B, n, device=DEV, dtype=torch.int32)
+    assert lib.lgb200_loss_reduce(ptr(sc), B, R, C, ptr(gt), ptr(ref_rows[0]), ptr(ref_rows[1]), ptr(ref_rows[2]), ptr(ref_ra),
+                                  ptr(ref_ca), _stream()) == 0
+    rows = torch.full((3, B, m), 7.0, device=DEV)
+    ra = torch.zeros(B, m, device=DEV, dtype=torch.int32)
+    ca = torch.zeros(B, n, device=DEV, dtype=torch.int32)
+    ws = torch.empty(B * (R + C), device=DEV, dtype=torch.int64)
+    rc = lib.lgb200_assign_loss(_abi.BF16, ptr(md), ptr(z), ptr(lse), B, Lp, ptr(lens), R, C, ptr(gt), ptr(rows[0]), ptr(rows[1]),
+                                ptr(rows[2]), ptr(ra), ptr(ca), ptr(ws), _stream())
+    assert rc == 0, lib.lgb200_error_string(rc)
+    assert torch.equal(rows[1], ref_rows[1])
+    torch.testing.assert_close(rows[0], ref_rows[0], atol=1e-4, rtol=1e-5)
+    torch.testing.assert_close(rows[2], ref_rows[2], atol=1e-5, rtol=1e-4)
+    assert torch.equal(ra, ref_ra) and torch.equal(ca, ref_ca)
+    assert (ra == n).any() and (ra < n).any()
+    # fp32 is refused: the parity mode materialises the matrix
+    assert lib.lgb200_assign_loss(_abi.F32, ptr(md), ptr(z), ptr(lse), B, Lp, ptr(lens), R, C, ptr(gt), ptr(rows[0]), ptr(rows[1]),
+                                  ptr(rows[2]), ptr(ra), ptr(ca), ptr(ws), _stream()) == -3
