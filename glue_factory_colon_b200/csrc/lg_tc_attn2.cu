@@ -41,7 +41,8 @@ constexpr int OFF_K = 2 * TILE_BYTES;
 constexpr int OFF_V = OFF_K + KST * TILE_BYTES;
 constexpr int OFF_X = OFF_V + VST * TILE_BYTES;  // Q_ext A | Q_ext B | K_ext
 constexpr int OFF_BAR = OFF_X + 3 * XT_BYTES;
-constexpr int A2_SMEM = OFF_BAR + 256;
+constexpr int A2_NBAR = 32;                 // mbarriers per pass (25 used)
+constexpr int A2_SMEM = OFF_BAR + 2 * A2_NBAR * 8 + 64;  // two barrier sets (pass 0 / exact-mode restart) + tmem slot + panic flag
 constexpr int A2_THREADS = 18 * 32;
 constexpr uint32_t TM_S = 0, TM_P = 256, TM_O = 384;
 
@@ -50,7 +51,12 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float ex2_poly(float x) {
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float ex2_poly(float x) {  // valid for x < 127.5 (the deferred mode checks the inputs' maximum)
   x = fmaxf(x, -126.f);
   const float t = x + 12582912.f;
   const float f = x - (t - 12582912.f);
@@ -63,7 +69,7 @@ __device__ __forceinline__ float ex2_poly(float x) {
 __global__ void __launch_bounds__(A2_THREADS, 1)
 tc_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, int Lp, const int32_t* __restrict__ lens, int kv_xor,
-                     __nv_bfloat16* __restrict__ ctx) {
+                     __nv_bfloat16* __restrict__ ctx, int start_mode) {
   const int s = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 2 * BM;
   const int nq = lens ? lens[s] : Lp;
   if (q0 >= nq) return;
@@ -90,33 +96,29 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint8_t* sV = smem + OFF_V;
   uint8_t* sQx = smem + OFF_X;             // [2][128][16] bf16
   uint8_t* sKx = sQx + 2 * XT_BYTES;       // [128][16] bf16
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;             // [KST]
-  uint64_t* k_empty = k_full + KST;        // [KST]
-  uint64_t* v_full = k_empty + KST;        // [VST]
-  uint64_t* v_empty = v_full + VST;        // [VST]
-  uint64_t* s_full = v_empty + VST;        // [2]
-  uint64_t* s_free = s_full + 2;           // [2]
-  uint64_t* p_ready = s_free + 2;          // [2]
-  uint64_t* pv_done = p_ready + 2;         // [2]
-  uint64_t* turn = pv_done + 2;            // [2] turn[x]: group x may exponentiate
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(turn + 2);
+  uint64_t* bars_base = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_base + 2 * A2_NBAR);
+  volatile int* panic = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmQ);
     tc::prefetch_tmap(&tmK);
     tc::prefetch_tmap(&tmV);
-    tc::mbar_init(q_full, 1);
-    for (int i = 0; i < KST; ++i) { tc::mbar_init(&k_full[i], 1); tc::mbar_init(&k_empty[i], 1); }
-    for (int i = 0; i < VST; ++i) { tc::mbar_init(&v_full[i], 1); tc::mbar_init(&v_empty[i], 1); }
-    for (int x = 0; x < 2; ++x) {
-      tc::mbar_init(&s_full[x], 1);
-      tc::mbar_init(&s_free[x], 8);
-      tc::mbar_init(&p_ready[x], 8);
-      tc::mbar_init(&pv_done[x], 1);
-      tc::mbar_init(&turn[x], 8);
+    for (int set = 0; set < 2; ++set) {  // second set: the exact-mode restart (see `panic`) starts on fresh barriers
+      uint64_t* b = bars_base + set * A2_NBAR;
+      tc::mbar_init(b, 1);
+      for (int i = 0; i < KST; ++i) { tc::mbar_init(b + 1 + i, 1); tc::mbar_init(b + 1 + KST + i, 1); }
+      for (int i = 0; i < VST; ++i) { tc::mbar_init(b + 1 + 2 * KST + i, 1); tc::mbar_init(b + 1 + 2 * KST + VST + i, 1); }
+      uint64_t* g = b + 1 + 2 * KST + 2 * VST;
+      for (int x = 0; x < 2; ++x) {
+        tc::mbar_init(g + x, 1);      // s_full
+        tc::mbar_init(g + 2 + x, 8);  // s_free
+        tc::mbar_init(g + 4 + x, 8);  // p_ready
+        tc::mbar_init(g + 6 + x, 1);  // pv_done
+        tc::mbar_init(g + 8 + x, 8);  // turn
+      }
     }
+    *panic = 0;
     tc::fence_barrier_init();
   }
   for (int i = threadIdx.x; i < 512; i += blockDim.x) reinterpret_cast<uint4*>(sQx)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -127,6 +129,26 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+
+  // Pass 0: deferred row maximum (mode 0, see lg_tc_attn.cu): after the first tile the exponentials run against the
+  // reference the tile was produced with; the quad-reduced row sum of a tile, formed in the tile's tail, moves the
+  // reference at the next tile when it exceeds 2^24.  Above 2^70 / inf / NaN (or a polynomial-lane input above 126)
+  // the CTA sets `panic`, finishes its schedule and repeats the work item in the exact mode (mode 1) on fresh barriers.
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+  const int mode = start_mode | pass;
+  uint64_t* bars = bars_base + pass * A2_NBAR;
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;             // [KST]
+  uint64_t* k_empty = k_full + KST;        // [KST]
+  uint64_t* v_full = k_empty + KST;        // [VST]
+  uint64_t* v_empty = v_full + VST;        // [VST]
+  uint64_t* s_full = v_empty + VST;        // [2]
+  uint64_t* s_free = s_full + 2;           // [2]
+  uint64_t* p_ready = s_free + 2;          // [2]
+  uint64_t* pv_done = p_ready + 2;         // [2]
+  uint64_t* turn = pv_done + 2;            // [2] turn[x]: group x may exponentiate
+  (void)turn;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -213,7 +235,10 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     uint64_t* my_p_ready = &p_ready[x];
     uint64_t* my_pv_done = &pv_done[x];
     float m_lo = 0.f, m_hi = 0.f, l_lo = 0.f, l_hi = 0.f;
+    float jn_lo = 0.f, jn_hi = 0.f;  // deferred mode: the rows' sums over the previous tile (whole quad)
+    bool bad = false, mvn_lo = false, mvn_hi = false, any_next = false;
     for (int j = 0; j < n_tiles; ++j) {
+      bool mv_lo = mvn_lo, mv_hi = mvn_hi, any_move = any_next;  // deferred mode: decided in the previous tile's tail
       tc::mbar_wait(my_s_full, j & 1);
       tc::fence_after_sync();
       uint32_t sv[64];  // [32h + 4k + e]: key column 64h + 8k + 2*c4 + (e & 1), row (e < 2 ? lo : hi)
@@ -228,8 +253,9 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           if (col >= valid) sv[i] = 0xff800000u;  // -inf
         }
       }
-      float mx_lo, mx_hi;
-      {
+      const bool exact_tile = mode != 0 || j == 0;  // uniform over the CTA
+      float up_lo = 0.f, up_hi = 0.f;
+      if (exact_tile) {
         float a0 = __uint_as_float(sv[0]), a1 = __uint_as_float(sv[1]), b0 = __uint_as_float(sv[2]), b1 = __uint_as_float(sv[3]);
 #pragma unroll
         for (int q = 1; q < 16; ++q) {
@@ -238,18 +264,21 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           b0 = fmaxf(b0, __uint_as_float(sv[4 * q + 2]));
           b1 = fmaxf(b1, __uint_as_float(sv[4 * q + 3]));
         }
-        mx_lo = fmaxf(a0, a1);
-        mx_hi = fmaxf(b0, b1);
+        float mx_lo = fmaxf(a0, a1), mx_hi = fmaxf(b0, b1);
         mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
         mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
         mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
         mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+        mv_lo = j == 0 || mx_lo > 8.f;
+        mv_hi = j == 0 || mx_hi > 8.f;
+        up_lo = mx_lo;
+        up_hi = mx_hi;
+        any_move = __any_sync(0xffffffffu, mv_lo || mv_hi);
       }
-      float d_lo = 0.f, d_hi = 0.f;
-      const bool mv_lo = j == 0 || mx_lo > 8.f, mv_hi = j == 0 || mx_hi > 8.f;
-      auto new_ref = [&](float& m, float mx, int row, bool writer) -> float {
-        const float base = j == 0 ? 0.f : m;
-        const float want = base + mx;
+      float d_lo = 0.f, d_hi = 0.f, al_lo = 1.f, al_hi = 1.f;
+      auto new_ref = [&](float& m, float up, int row, bool writer) -> float {
+        const float base = m;  // (0 before the first tile)
+        const float want = base + up;
         const __nv_bfloat16 hi = __float2bfloat16_rn(want);
         const __nv_bfloat16 lo = __float2bfloat16_rn(want - __bfloat162float(hi));
         const float m_abs = __bfloat162float(hi) + __bfloat162float(lo);
@@ -261,14 +290,20 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
         return m_abs - base;
       };
-      if (mv_lo) d_lo = new_ref(m_lo, mx_lo, r_lo, c4 == 0);
-      if (mv_hi) d_hi = new_ref(m_hi, mx_hi, r_hi, c4 == 1);
-      if (mv_lo || mv_hi) tc::fence_proxy_async();
-      const float al_lo = j == 0 ? 0.f : ex2(-d_lo), al_hi = j == 0 ? 0.f : ex2(-d_hi);
+      if (any_move) {  // rare after the first tile
+        if (!exact_tile) {  // the previous tile's row sum, taken against the current reference, says by how much
+          if (mv_lo) { if (!(jn_lo <= 0x1p70f)) { bad = true; mv_lo = false; } else up_lo = (float)((int)(__float_as_uint(jn_lo) >> 23) - 127); }
+          if (mv_hi) { if (!(jn_hi <= 0x1p70f)) { bad = true; mv_hi = false; } else up_hi = (float)((int)(__float_as_uint(jn_hi) >> 23) - 127); }
+        }
+        if (mv_lo) d_lo = new_ref(m_lo, up_lo, r_lo, c4 == 0);
+        if (mv_hi) d_hi = new_ref(m_hi, up_hi, r_hi, c4 == 1);
+        tc::fence_proxy_async();
+        al_lo = j == 0 ? 0.f : ex2(-d_lo);
+        al_hi = j == 0 ? 0.f : ex2(-d_hi);
+      }
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(my_s_free);  // S is in registers, Q_ext is up to date: QK^T(j+1) may go
-      const bool any_move = __any_sync(0xffffffffu, mv_lo || mv_hi);
 #if LG_ATTN2_ORDERED
       // my turn to exponentiate?  A(j) follows B(j-1), B(j) follows A(j)
       if (x == 0) { if (j > 0) tc::mbar_wait(&turn[0], (j - 1) & 1); }
@@ -279,11 +314,14 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #endif
       uint32_t pk[32];
       float2 s_lo = make_float2(0.f, 0.f), s_hi = make_float2(0.f, 0.f);
+      float pmax = -INFINITY;  // largest input of a polynomial lane
       if (any_move) {
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
           float p0 = ex2(__uint_as_float(sv[4 * q]) - d_lo), p1 = __uint_as_float(sv[4 * q + 1]) - d_lo;
           float p2 = ex2(__uint_as_float(sv[4 * q + 2]) - d_hi), p3 = __uint_as_float(sv[4 * q + 3]) - d_hi;
+          if (LG2_POLY_HERE(2 * q)) pmax = fmaxf(pmax, p1);
+          if (LG2_POLY_HERE(2 * q + 1)) pmax = fmaxf(pmax, p3);
           p1 = LG2_POLY_HERE(2 * q) ? ex2_poly(p1) : ex2(p1);
           p3 = LG2_POLY_HERE(2 * q + 1) ? ex2_poly(p3) : ex2(p3);
           s_lo = __fadd2_rn(s_lo, make_float2(p0, p1));
@@ -292,10 +330,18 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           pk[2 * q + 1] = tc::pack_bf16(p2, p3);
         }
       } else {
+        float pend = -INFINITY;
+        bool have_pend = false;  // (compile-time after unrolling)
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
           float p0 = ex2(__uint_as_float(sv[4 * q])), p1 = __uint_as_float(sv[4 * q + 1]);
           float p2 = ex2(__uint_as_float(sv[4 * q + 2])), p3 = __uint_as_float(sv[4 * q + 3]);
+          if (LG2_POLY_HERE(2 * q)) {
+            if (have_pend) { pmax = max3(pmax, pend, p1); have_pend = false; } else { pend = p1; have_pend = true; }
+          }
+          if (LG2_POLY_HERE(2 * q + 1)) {
+            if (have_pend) { pmax = max3(pmax, pend, p3); have_pend = false; } else { pend = p3; have_pend = true; }
+          }
           p1 = LG2_POLY_HERE(2 * q) ? ex2_poly(p1) : ex2(p1);
           p3 = LG2_POLY_HERE(2 * q + 1) ? ex2_poly(p3) : ex2(p3);
           s_lo = __fadd2_rn(s_lo, make_float2(p0, p1));
@@ -303,13 +349,16 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           pk[2 * q] = tc::pack_bf16(p0, p1);
           pk[2 * q + 1] = tc::pack_bf16(p2, p3);
         }
+        if (have_pend) pmax = fmaxf(pmax, pend);
       }
+      bad = bad || !(pmax <= 126.f);
 #if LG_ATTN2_ORDERED
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&turn[x ^ 1]);  // the other group may exponentiate now
 #endif
-      l_lo = l_lo * al_lo + (s_lo.x + s_lo.y);
-      l_hi = l_hi * al_hi + (s_hi.x + s_hi.y);
+      const float t_lo = s_lo.x + s_lo.y, t_hi = s_hi.x + s_hi.y;
+      l_lo = l_lo * al_lo + t_lo;
+      l_hi = l_hi * al_hi + t_hi;
       if (j > 0) {
         tc::mbar_wait(my_pv_done, (j - 1) & 1);  // PV(j-1) retired: P is free, O is up to date
         tc::fence_after_sync();
@@ -327,7 +376,17 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(my_p_ready);
+      // tail (overlaps the wait for the next score tile): the rows' sums over this tile, identical in the four
+      // threads of a quad (butterfly of commutative adds), decide whether the next tile moves the reference
+      jn_lo = t_lo + __shfl_xor_sync(0xffffffffu, t_lo, 1);
+      jn_hi = t_hi + __shfl_xor_sync(0xffffffffu, t_hi, 1);
+      jn_lo += __shfl_xor_sync(0xffffffffu, jn_lo, 2);
+      jn_hi += __shfl_xor_sync(0xffffffffu, jn_hi, 2);
+      mvn_lo = !(jn_lo <= 0x1p24f);
+      mvn_hi = !(jn_hi <= 0x1p24f);
+      any_next = mode == 0 && __any_sync(0xffffffffu, mvn_lo || mvn_hi);
     }
+    if (mode == 0 && (bad || !(jn_lo <= 0x1p70f) || !(jn_hi <= 0x1p70f))) *panic = 1;  // (last tile's sums included)
     l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
     l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
     l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
@@ -353,6 +412,15 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
   tc::fence_before_sync();
   __syncthreads();
+  if (mode != 0 || *panic == 0) break;
+  // restart in the exact mode: everything issued in pass 0 has been consumed (both groups waited for their last P.V)
+  tc::fence_after_sync();
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) reinterpret_cast<uint4*>(sQx)[i] = make_uint4(0u, 0u, 0u, 0u);
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  }  // pass
   if (warp == 1) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem, 512);
@@ -374,7 +442,8 @@ int lg_tc_attention2(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_
   cudaError_t e = cudaFuncSetAttribute(tc_attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM);
   if (e != cudaSuccess) return (int)e;
   dim3 grid((Lp + 2 * BM - 1) / (2 * BM), LG_HEADS, S);
-  tc_attention2_kernel<<<grid, A2_THREADS, A2_SMEM, st>>>(tq, tk, tv, Lp, lens, kv_xor, ctx);
+  static const int start_mode = getenv("LGB200_ATTN_EXACT_MAX") ? atoi(getenv("LGB200_ATTN_EXACT_MAX")) : 0;
+  tc_attention2_kernel<<<grid, A2_THREADS, A2_SMEM, st>>>(tq, tk, tv, Lp, lens, kv_xor, ctx, start_mode);
   LG_LAUNCH_CHECK();
   return LGB200_OK;
 }
