@@ -35,6 +35,9 @@ __device__ long long g_attn_times[2 * 16 * 16];
 // same time (MUFU 100 % busy for ~2000 cycles) and then all leave it idle for ~1000 (measured timeline).
 __device__ unsigned int g_attn_sm_slot[1024];
 
+#ifndef LG_DBG_Z
+#define LG_DBG_Z 0  // sequence index of the CTA whose clock64 timeline is recorded (debug builds)
+#endif
 #ifndef LG_ATTN_MSUB
 #define LG_ATTN_MSUB 1  // 1: the row-max subtraction s - m_ref is folded into the QK^T MMA (a fifth K=16 slice)
 #endif
@@ -113,6 +116,12 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   constexpr int dbg_in = 0;
 #endif
   const int dbg = dbg_in & 15;  // bit 4 of dbg_in enables the clock64 timeline
+#ifdef LG_ATTN_DEBUG
+#define XSTAMP(k) do { if ((dbg_in & 16) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == LG_DBG_Z && threadIdx.x == 64) g_attn_times[506 + (k)] = clock64(); } while (0)
+#else
+#define XSTAMP(k) do {} while (0)
+#endif
+  XSTAMP(0);
   // CL CTAs with consecutive query tiles of the same (sequence, head) form a cluster and share every
   // K/V tile: each loads 1/CL of it and TMA-multicasts it to the others.  (Measured: with one CTA per
   // K/V tile the kernel sat at ~5 TB/s of L2->SM traffic regardless of MUFU / pipelining changes.)
@@ -193,6 +202,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (CL > 1) tc::cluster_sync();  // peers' barriers exist before anyone multicasts into them
   tc::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  XSTAMP(1);
 
   // Pass 0 runs with the DEFERRED row maximum (mode 0): after the first tile the softmax threads exponentiate a score
   // tile as soon as it is in registers, against the reference the tile was produced with, and look at the tile's row
@@ -271,7 +281,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tc::mbar_wait(&k_full[0], 0);
     tc::fence_after_sync();
     issue_qk();
-    const bool recm = (dbg_in & 16) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+    const bool recm = (dbg_in & 16) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == LG_DBG_Z && lane == 0;
 #define MSTAMP(k) do { if (recm && j < 16) g_attn_times[256 + (j * 16) + (k)] = clock64(); } while (0)
     for (int j = 0; j < n_tiles; ++j) {
       MSTAMP(0);
@@ -340,7 +350,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       joint_next = row_total((j + 1) & 3);                                                           /* tile j-3 */ \
       move_next = !(joint_next <= 0x1p24f);                                                                        \
     } while (0)
-    const bool rec = (dbg_in & 16) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0;
+    const bool rec = (dbg_in & 16) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == LG_DBG_Z && warp == 2 && lane == 0;
 #define STAMP(k) do { if (rec && j < 16) g_attn_times[(j * 16) + (k)] = clock64(); } while (0)
     for (int j = 0; j < n_tiles; ++j) {
       STAMP(0);
@@ -481,6 +491,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (lane == 0) tc::mbar_arrive(p_ready);
       STAMP(8);
     }
+    XSTAMP(2);
     // combine the partial row sums (ring slot n_tiles & 3 is the one no pending tile sum lives in; the exact mode, whose
     // maxima use slots 0 and 1, gets slot 2), normalise this thread's output columns
     const int fin_slot = mode == 0 ? (n_tiles & 3) : 2;
@@ -516,8 +527,10 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
     }
   }
+  XSTAMP(3);
   tc::fence_before_sync();
   __syncthreads();
+  XSTAMP(4);
   if (mode != 0 || *panic == 0) break;
   // restart in the exact mode: every TMA load and MMA of pass 0 has been consumed (the softmax warps waited for the
   // last P.V); fresh barrier set, Q_ext back to zero, O is overwritten by the first P.V (accumulate flag)

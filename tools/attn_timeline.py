@@ -21,3 +21,7 @@ print("softmax warp (cycles rel. to step 2 start): cols = start, s_full woke, ld
 for j in range(2, 12): print(j, (t[0, j, :9] - t0).tolist())
 print("mma thread: iter start, k_full, s_free woke, qk issued, p_ready woke, pv issued")
 for j in range(2, 12): print(j, (t[1, j, :6] - t0).tolist())
+
+x = np.array(buf[506:512])
+print("CTA(0,0,0) thread 64: entry, setup done, softmax loop done, output stored, after final sync (cycles rel. to entry):", (x[:5] - x[0]).tolist())
+print("first softmax stamp rel. to entry:", int(t[0, 0, 0] - x[0]), " last p_ready arrive:", int(t[0, 15, 8] - x[0]))
