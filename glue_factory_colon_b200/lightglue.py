@@ -138,6 +138,10 @@ class LightGlue(nn.Module):
         # B200 extension: "fp32" (CUDA-core parity kernels), "bf16" (tcgen05 kernels),
         # "auto" = bf16 when conf.mp or torch autocast is active, else fp32.
         "precision": "auto",
+        # B200 extension: capture the whole forward of a fixed input signature in a CUDA graph and replay it (eval
+        # mode, no adaptive depth / width, no per-pair counts).  One pair at 2048 keypoints is ~90 launches of 5-20 us
+        # each: issued from Python the forward is host-bound, replayed from a graph it is not.
+        "cuda_graph": False,
     }
 
     required_data_keys = ["keypoints0", "keypoints1", "descriptors0", "descriptors1"]
@@ -165,6 +169,7 @@ class LightGlue(nn.Module):
         )
         self._packed: Dict = {}
         self._pack_key = None
+        self._graphs: Dict = {}
 
     # ---- reference-compatible helpers ------------------------------------------------
 
@@ -419,10 +424,54 @@ class LightGlue(nn.Module):
 
     # ---- forward ---------------------------------------------------------------------------
 
+    _GRAPH_INPUTS = ("keypoints0", "keypoints1", "descriptors0", "descriptors1", "scales0", "scales1", "oris0", "oris1")
+
     @torch.no_grad()
     def forward(self, data: dict) -> dict:
         for key in self.required_data_keys:
             assert key in data, f"Missing key {key} in data"
+        conf = self.conf
+        graphable = (
+            conf.cuda_graph and not self.training and conf.depth_confidence <= 0 and conf.width_confidence <= 0
+            and "num_keypoints0" not in data and "num_keypoints1" not in data and data["keypoints0"].is_cuda
+        )
+        if not graphable:
+            return self._forward_impl(data)
+        # ---- CUDA-graph path: static copies of the inputs, one captured forward per input signature ----
+        ins = {k: data[k] for k in self._GRAPH_INPUTS if isinstance(data.get(k), torch.Tensor)}
+        for v in ("view0", "view1"):
+            sz = data.get(v, {}).get("image_size") if v in data else None
+            if sz is not None:
+                ins[v] = sz if isinstance(sz, torch.Tensor) else torch.tensor(sz)
+        dev = data["keypoints0"].device
+        prec = self._precision()
+        self._pack(prec, dev)
+        sig = (prec, self._pack_key) + tuple((k, tuple(t.shape), t.dtype) for k, t in sorted(ins.items()))
+        entry = self._graphs.get(sig)
+        if entry is None:
+            static = {k: t.to(dev).clone() for k, t in ins.items()}
+
+            def as_data():
+                d = {k: t for k, t in static.items() if not k.startswith("view")}
+                d["view0"] = {"image_size": static["view0"]} if "view0" in static else {}
+                d["view1"] = {"image_size": static["view1"]} if "view1" in static else {}
+                return d
+
+            self._forward_impl(as_data())  # warm-up outside the capture: lazy initialisation, allocator pools
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._forward_impl(as_data())
+            if len(self._graphs) >= 8:  # a handful of signatures at most; drop the oldest
+                self._graphs.pop(next(iter(self._graphs)))
+            entry = self._graphs[sig] = (graph, static, out)
+        graph, static, out = entry
+        for k, t in ins.items():
+            static[k].copy_(t, non_blocking=True)
+        graph.replay()
+        return {k: v.clone() for k, v in out.items()}  # the graph's output buffers are overwritten by the next replay
+
+    def _forward_impl(self, data: dict) -> dict:
         lib = _abi.load()
         conf = self.conf
         kpts0, kpts1 = data["keypoints0"], data["keypoints1"]
@@ -488,7 +537,14 @@ class LightGlue(nn.Module):
         do_prune = conf.width_confidence > 0 and not self.training
         adaptive = do_early or do_prune
         use_lens = variable or adaptive or m != Lp or n != Lp
-        lens = torch.from_numpy(lens_host.reshape(-1).copy()).to(dev) if use_lens else None
+        if not use_lens:
+            lens = None
+        elif variable:
+            lens = torch.from_numpy(lens_host.reshape(-1).copy()).to(dev)
+        else:  # all pairs (m, n): filled on the device (no host copy, so the forward can be captured in a CUDA graph)
+            lens = torch.empty(S, **i32)
+            lens[0::2] = m
+            lens[1::2] = n
         lens_act = lens.clone() if adaptive else lens
 
         act = torch.bfloat16 if bf else torch.float32

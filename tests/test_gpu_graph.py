@@ -1,0 +1,40 @@
+"""CUDA-graph replay of the forward (conf.cuda_graph, a B200 extension): identical results to the eager launches."""
+import pytest
+import torch
+
+from glue_factory_colon_b200 import LightGlue
+from glue_factory_colon_b200.synthetic import make_pairs
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_graph_replay_equals_eager(precision):
+    torch.manual_seed(4)
+    eager = LightGlue({"precision": precision, "filter_threshold": 0.1}).eval().to(DEV)
+    graphed = LightGlue({"precision": precision, "filter_threshold": 0.1, "cuda_graph": True}).eval().to(DEV)
+    graphed.load_state_dict(eager.state_dict())
+    shapes = [(1, 300, 260, 41), (1, 300, 260, 42), (2, 256, 256, 43), (1, 300, 260, 44)]
+    for B, n0, n1, seed in shapes:  # same signature three times (one capture, two replays), another one in between
+        data = make_pairs(B, n0, n1, seed=seed, device=DEV)
+        want, got = eager(data), graphed(data)
+        assert set(want) == set(got)
+        for k in want:
+            assert got[k].shape == want[k].shape and got[k].dtype == want[k].dtype, k
+            assert torch.equal(got[k], want[k]), k
+    assert len(graphed._graphs) == 2
+    # results are copies: a later replay does not overwrite what was returned earlier
+    d1, d2 = make_pairs(1, 300, 260, seed=45, device=DEV), make_pairs(1, 300, 260, seed=46, device=DEV)
+    o1 = graphed(d1)
+    keep = o1["log_assignment"].clone()
+    graphed(d2)
+    assert torch.equal(o1["log_assignment"], keep)
+    # new weights -> new capture (the packed weights are part of the signature)
+    with torch.no_grad():
+        graphed.log_assignment[-1].matchability.bias.add_(0.5)
+        eager.log_assignment[-1].matchability.bias.add_(0.5)
+    assert torch.equal(graphed(d1)["log_assignment"], eager(d1)["log_assignment"])
+    # adaptive / training / per-pair counts fall back to eager launches
+    d3 = dict(d1, num_keypoints0=torch.tensor([250]), num_keypoints1=torch.tensor([260]))
+    assert torch.equal(graphed(d3)["matches0"], eager(d3)["matches0"])
