@@ -129,6 +129,11 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   constexpr int SLICE = AT_BN / CL;  // K/V rows this CTA loads per tile
   const uint32_t crank = CL > 1 ? tc::cluster_ctarank() : 0;
   const int s = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AT_BM;
+  // PDL: everything this kernel reads (lens, Q, K, V) comes from its predecessor, so the wait is the first thing it
+  // does; what overlaps is the launch itself.  Its own dependents (the FFN GEMM: barriers, TMEM, weight block) may
+  // start at once.
+  tc::pdl_wait();
+  tc::pdl_launch_dependents();
   const int nq = lens ? lens[s] : Lp;
   if ((int)(blockIdx.x - crank) * AT_BM >= nq) return;  // whole cluster is past the valid rows
   const int skv = s ^ kv_xor;
@@ -569,13 +574,14 @@ static int launch_attention(const __nv_bfloat16* Q, const __nv_bfloat16* K, cons
   cfg.blockDim = dim3(64 + 128 * NP);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  tc::lg_pdl_attr(&attr[1]);
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   static const unsigned stagger = getenv("LGB200_ATTN_STAGGER_NS") ? (unsigned)atoi(getenv("LGB200_ATTN_STAGGER_NS")) : 0u;  // (mattered before the instruction diet; 0 .. 1800 ns now within 1.5 %)
   static const int start_mode = getenv("LGB200_ATTN_EXACT_MAX") ? atoi(getenv("LGB200_ATTN_EXACT_MAX")) : 0;  // 1: maximum before the exponentials on every tile (r1 behaviour)
   e = cudaLaunchKernelEx(&cfg, kern, tq, tk, tv, Lp, lens, kv_xor, ctx, dbg, stagger, start_mode);

@@ -2,6 +2,7 @@
 // alloc/ld/st, commit) and the shared-memory / instruction descriptors they need.
 // Everything is inline PTX; no CUTLASS dependency.
 #pragma once
+#include <stdlib.h>
 #include <cuda.h>
 #include "lg_common.cuh"
 
@@ -176,6 +177,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start once every CTA of its predecessor has executed launch_dependents (or exited); it must not touch global memory
+// the predecessor writes (or reads memory it is about to overwrite) before its own griddepcontrol.wait, which returns
+// when the predecessor has completed and flushed.  Both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// host side: fills one launch attribute; LGB200_PDL=0 switches it off (the attribute slot is then a harmless repeat)
+inline bool lg_pdl_enabled() {
+  static const int on = getenv("LGB200_PDL") ? atoi(getenv("LGB200_PDL")) : 1;
+  return on != 0;
+}
+inline void lg_pdl_attr(cudaLaunchAttribute* a) {
+  a->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  a->val.programmaticStreamSerializationAllowed = lg_pdl_enabled() ? 1 : 0;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 

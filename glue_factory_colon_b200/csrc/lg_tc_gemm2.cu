@@ -241,6 +241,9 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
   if (CL > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: the next kernel in the stream may start its own prologue (barriers, TMEM, weight block) while this one runs;
+  // this kernel has read nothing of its predecessor's yet: weights, bias and LayerNorm parameters never change
+  tc::pdl_launch_dependents();
 
   // Producer and MMA warps run their loops with warp-uniform control flow (all 32 lanes wait on the
   // barriers, one elected lane issues the TMA / tcgen05 instruction): addresses and descriptors then
@@ -253,6 +256,7 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
       for (int kb = 0; kb < g.kb_total; ++kb) tc::tma_load_2d(sW + kb * WB_BYTES, &maps.w, w_full, kb * BK, n0);
     }
     __syncwarp();
+    tc::pdl_wait();  // activations (and lens) come from the predecessor; the weight block above does not
     int stage = 0;
     uint32_t phase = 0;
     for (int mt = m_first; mt < g.m_tiles; mt += m_step) {
@@ -277,6 +281,7 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
       }
     }
   } else if (warp == 1) {
+    tc::pdl_wait();  // (reads lens)
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = tc::idesc_bf16(BM, BN, 0);
     int stage = 0, acc = 0;
@@ -323,6 +328,7 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
     if (rec) { g_gemm_times[0] = w_acc; g_gemm_times[1] = w_full_c; g_gemm_times[2] = clock64() - t_begin; }
 #endif
   } else {
+    tc::pdl_wait();  // residual / rotary rows, lens and the output buffers belong to the predecessor until here
     // ------------------------------------------------------------------ epilogue (8 warps)
     const int ew = warp - 2;        // 0..7
     const int quarter = warp & 3;   // TMEM lane quarter accessible to this warp
@@ -646,6 +652,9 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
   cluster_sync_all();  // both CTAs' barriers and TMEM exist before any cross-CTA traffic
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: the next kernel in the stream may start its own prologue (barriers, TMEM, weight block) while this one runs;
+  // this kernel has read nothing of its predecessor's yet: weights, bias and LayerNorm parameters never change
+  tc::pdl_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (own 128 rows, own W block)
@@ -654,6 +663,7 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
       for (int kb = 0; kb < g.kb_total; ++kb) tc::tma_load_2d(sW + kb * WB_BYTES, &maps.w, w_full, kb * BK, n0);
     }
     __syncwarp();
+    tc::pdl_wait();  // activations (and lens) come from the predecessor; the weight block above does not
     int stage = 0;
     uint32_t phase = 0;
     for (int mt = m_first; mt < g.m_tiles; mt += m_step) {
@@ -676,6 +686,7 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
       }
     }
   } else if (warp == 1) {
+    tc::pdl_wait();  // (reads lens)
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     tc::mbar_wait(w_full, 0);
@@ -738,6 +749,7 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
       }
     }
   } else {
+    tc::pdl_wait();  // residual / rotary rows, lens and the output buffers belong to the predecessor until here
     // ------------------------------------------------------------------ epilogue (8 warps): own 128 rows x 256 columns
     const int ew = warp - 2;
     const int quarter = warp & 3;
@@ -1014,6 +1026,9 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
   cluster_sync_all();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: the next kernel in the stream may start its own prologue (barriers, TMEM, weight block) while this one runs;
+  // this kernel has read nothing of its predecessor's yet: weights, bias and LayerNorm parameters never change
+  tc::pdl_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer: half of this parity's A stage, multicast
@@ -1022,6 +1037,7 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
       for (int kb = 0; kb < g.kb_total; ++kb) tc::tma_load_2d(sW + kb * WB_BYTES, &maps.w, w_full, kb * BK, n0);
     }
     __syncwarp();
+    tc::pdl_wait();  // activations (and lens) come from the predecessor; the weight block above does not
     int stage = 0;
     uint32_t phase = 0;
     for (int mt = cid; mt < g.m_tiles; mt += ncl) {
@@ -1044,6 +1060,7 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
       }
     }
   } else if (warp == 1) {
+    tc::pdl_wait();  // (reads lens)
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     tc::mbar_wait(w_full, 0);
@@ -1107,6 +1124,7 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
       }
     }
   } else {
+    tc::pdl_wait();  // residual / rotary rows, lens and the output buffers belong to the predecessor until here
     // ------------------------------------------------------------------ epilogue (16 warps): own 128 rows x 256 columns
     // warp = (TMEM lane quarter, 32-column slice cq of each 128-column block).  With 8 warps (2 per SM sub-partition)
     // the epilogue was busy 6600 cycles per 256-row super-tile against ~3500 issue cycles of work.
@@ -1247,13 +1265,14 @@ int launch(const Maps& maps, Args g, int n_blocks, cudaStream_t st) {
   cfg.blockDim = dim3(320);
   cfg.dynamicSmemBytes = L::SMEM;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  tc::lg_pdl_attr(&attr[1]);
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   // persistent clusters with static striding: never launch more clusters than can be co-resident
   static int max_clusters = 0;
   if (max_clusters == 0) {
@@ -1289,13 +1308,14 @@ int launch_pair_row(const Maps& maps, Args g, int N, cudaStream_t st) {
   cfg.blockDim = dim3(MODE == MODE_HEADS ? 576 : 320);
   cfg.dynamicSmemBytes = L::SMEM;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  tc::lg_pdl_attr(&attr[1]);
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   static int max_clusters = 0;
   if (max_clusters == 0) {
     int n = 0;
@@ -1327,13 +1347,14 @@ int launch_pair_ln(const Maps& maps, Args g, cudaStream_t st) {
   cfg.blockDim = dim3(576);
   cfg.dynamicSmemBytes = LayPL::SMEM;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 4;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  tc::lg_pdl_attr(&attr[1]);
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   static int max_clusters = 0;
   if (max_clusters == 0) {
     int n = 0;
