@@ -25,6 +25,7 @@ SIGNATURES = {
     "lgb200_linear": [_i, _i, _p, _p, _i, _p, _p, _i, _i, _i, _p, _i, _f, _f, _f, _p, _p, _p, _p, _p, _p, _i,
                       _p, _p, _p, _p, _p, _p],
     "lgb200_attention": [_i, _p, _p, _p, _i, _i, _p, _i, _p, _p],
+    "lgb200_attention_ordered": [_i, _p, _p, _p, _i, _i, _p, _p, _i, _p, _p],
     "lgb200_rowdot": [_i, _p, _p, _p, _i, _i, _p, _i, _p, _p],
     "lgb200_assign_lse": [_i, _p, _i, _i, _p, _p, _p],
     "lgb200_assign_scores": [_i, _p, _p, _p, _i, _i, _p, _i, _i, _p, _p, _p],

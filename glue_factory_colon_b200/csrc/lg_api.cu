@@ -67,8 +67,17 @@ extern "C" int lgb200_linear(int precision, int epilogue, const void* A0, const 
   return LGB200_ERR_PRECISION;
 }
 
+extern "C" int lgb200_attention_ordered(int precision, const void* Q, const void* K, const void* V, int S, int Lp,
+                                        const int32_t* lens, const int32_t* order, int kv_xor, void* ctx,
+                                        void* stream);
 extern "C" int lgb200_attention(int precision, const void* Q, const void* K, const void* V, int S,
                                 int Lp, const int32_t* lens, int kv_xor, void* ctx, void* stream) {
+  return lgb200_attention_ordered(precision, Q, K, V, S, Lp, lens, nullptr, kv_xor, ctx, stream);
+}
+
+extern "C" int lgb200_attention_ordered(int precision, const void* Q, const void* K, const void* V, int S, int Lp,
+                                        const int32_t* lens, const int32_t* order, int kv_xor, void* ctx,
+                                        void* stream) {
   if (!Q || !K || !V || !ctx) return LGB200_ERR_NULL;
   if (S <= 0 || Lp <= 0 || Lp % 128 || (kv_xor != 0 && kv_xor != 1) || (kv_xor && (S & 1)))
     return LGB200_ERR_SHAPE;
@@ -83,7 +92,7 @@ extern "C" int lgb200_attention(int precision, const void* Q, const void* K, con
       return lg_tc_attention2((const __nv_bfloat16*)Q, (const __nv_bfloat16*)K, (const __nv_bfloat16*)V, S, Lp,
                               lens, kv_xor, (__nv_bfloat16*)ctx, st);
     return lg_tc_attention((const __nv_bfloat16*)Q, (const __nv_bfloat16*)K, (const __nv_bfloat16*)V, S,
-                           Lp, lens, kv_xor, (__nv_bfloat16*)ctx, st);
+                           Lp, lens, kv_xor, (__nv_bfloat16*)ctx, order, st);
   }
   return LGB200_ERR_PRECISION;
 }

@@ -19,7 +19,7 @@ int lg_tc_linear_v2(int epilogue, const __nv_bfloat16* A0, const __nv_bfloat16* 
                     const __nv_bfloat16* W, int T, int N, int K, const int32_t* lens, LgEpi epi,
                     const void* rot16, const __nv_bfloat16* resid16, cudaStream_t st);
 int lg_tc_attention(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* V, int S, int Lp,
-                    const int32_t* lens, int kv_xor, __nv_bfloat16* ctx, cudaStream_t st);
+                    const int32_t* lens, int kv_xor, __nv_bfloat16* ctx, const int32_t* order, cudaStream_t st);
 int lg_tc_attention2(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* V, int S, int Lp,
                      const int32_t* lens, int kv_xor, __nv_bfloat16* ctx, cudaStream_t st);
 int lg_tc_assign_lse(const __nv_bfloat16* md, int S, int Lp, const int32_t* lens, float* lse,

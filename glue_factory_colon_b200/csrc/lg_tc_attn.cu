@@ -106,7 +106,8 @@ template <int CL, int NP>
 __global__ void __launch_bounds__(64 + 128 * NP, 2)
 tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, int Lp, const int32_t* __restrict__ lens,
-                    int kv_xor, __nv_bfloat16* __restrict__ ctx, int dbg_arg, unsigned stagger_ns, int start_mode) {
+                    int kv_xor, __nv_bfloat16* __restrict__ ctx, int dbg_arg, unsigned stagger_ns, int start_mode,
+                    const int32_t* __restrict__ order) {
   // Debug modes (skeleton runs, no-MUFU run, clock64 timeline) exist only when the file is compiled with
   // -DLG_ATTN_DEBUG; in the product build `dbg` is the constant 0 and every debug branch folds away
   // (leaving them as run-time branches cost ~50 BRA per 64 exponentials in the unrolled loop).
@@ -128,12 +129,15 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
   constexpr int SLICE = AT_BN / CL;  // K/V rows this CTA loads per tile
   const uint32_t crank = CL > 1 ? tc::cluster_ctarank() : 0;
-  const int s = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AT_BM;
+  const int h = blockIdx.y, q0 = blockIdx.x * AT_BM;
   // PDL: everything this kernel reads (lens, Q, K, V) comes from its predecessor, so the wait is the first thing it
   // does; what overlaps is the launch itself.  Its own dependents (the FFN GEMM: barriers, TMEM, weight block) may
   // start at once.
   tc::pdl_wait();
   tc::pdl_launch_dependents();
+  // ragged batches: CTAs are handed out in blockIdx order, so the caller may pass the sequences sorted by key count,
+  // longest first (a CTA's duration is proportional to it) -- the kernel's tail is then made of the shortest items
+  const int s = order ? order[blockIdx.z] : (int)blockIdx.z;
   const int nq = lens ? lens[s] : Lp;
   if ((int)(blockIdx.x - crank) * AT_BM >= nq) return;  // whole cluster is past the valid rows
   const int skv = s ^ kv_xor;
@@ -557,7 +561,8 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
 template <int CL, int NP>
 static int launch_attention(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* V, int S, int Lp,
-                            const int32_t* lens, int kv_xor, __nv_bfloat16* ctx, int dbg, cudaStream_t st) {
+                            const int32_t* lens, int kv_xor, __nv_bfloat16* ctx, int dbg, const int32_t* order,
+                            cudaStream_t st) {
   CUtensorMap tq, tk, tv;
   const uint64_t d[2] = {64, (uint64_t)S * LG_HEADS * Lp}, sb[1] = {128};
   const uint32_t box[2] = {64, 128}, box_kv[2] = {64, 128 / CL};
@@ -584,14 +589,14 @@ static int launch_attention(const __nv_bfloat16* Q, const __nv_bfloat16* K, cons
   cfg.numAttrs = 2;
   static const unsigned stagger = getenv("LGB200_ATTN_STAGGER_NS") ? (unsigned)atoi(getenv("LGB200_ATTN_STAGGER_NS")) : 0u;  // (mattered before the instruction diet; 0 .. 1800 ns now within 1.5 %)
   static const int start_mode = getenv("LGB200_ATTN_EXACT_MAX") ? atoi(getenv("LGB200_ATTN_EXACT_MAX")) : 0;  // 1: maximum before the exponentials on every tile (r1 behaviour)
-  e = cudaLaunchKernelEx(&cfg, kern, tq, tk, tv, Lp, lens, kv_xor, ctx, dbg, stagger, start_mode);
+  e = cudaLaunchKernelEx(&cfg, kern, tq, tk, tv, Lp, lens, kv_xor, ctx, dbg, stagger, start_mode, order);
   if (e != cudaSuccess) return (int)e;
   LG_LAUNCH_CHECK();
   return LGB200_OK;
 }
 
 int lg_tc_attention(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* V, int S, int Lp,
-                    const int32_t* lens, int kv_xor, __nv_bfloat16* ctx, cudaStream_t st) {
+                    const int32_t* lens, int kv_xor, __nv_bfloat16* ctx, const int32_t* order, cudaStream_t st) {
   static const int dbg = getenv("LGB200_ATTN_DBG") ? atoi(getenv("LGB200_ATTN_DBG")) : 0;
   static const int force_cl = getenv("LGB200_ATTN_CL") ? atoi(getenv("LGB200_ATTN_CL")) : 0;
   const int qt = Lp / AT_BM;
@@ -600,10 +605,10 @@ int lg_tc_attention(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_b
   int cl = 1;
   if (force_cl == 1 || force_cl == 2 || force_cl == 4) cl = (qt % force_cl == 0) ? force_cl : 1;
   static const int np = getenv("LGB200_ATTN_NP") ? atoi(getenv("LGB200_ATTN_NP")) : 2;  // softmax threads per query row
-  if (cl == 4) return launch_attention<4, 2>(Q, K, V, S, Lp, lens, kv_xor, ctx, dbg, st);
-  if (cl == 2) return launch_attention<2, 2>(Q, K, V, S, Lp, lens, kv_xor, ctx, dbg, st);
-  if (np == 4) return launch_attention<1, 4>(Q, K, V, S, Lp, lens, kv_xor, ctx, dbg, st);
-  return launch_attention<1, 2>(Q, K, V, S, Lp, lens, kv_xor, ctx, dbg, st);
+  if (cl == 4) return launch_attention<4, 2>(Q, K, V, S, Lp, lens, kv_xor, ctx, dbg, nullptr, st);  // (clusters: x only)
+  if (cl == 2) return launch_attention<2, 2>(Q, K, V, S, Lp, lens, kv_xor, ctx, dbg, nullptr, st);
+  if (np == 4) return launch_attention<1, 4>(Q, K, V, S, Lp, lens, kv_xor, ctx, dbg, order, st);
+  return launch_attention<1, 2>(Q, K, V, S, Lp, lens, kv_xor, ctx, dbg, order, st);
 }
 
 extern "C" int lgb200_debug_attn_times(long long* host_out, int n) {

@@ -20,6 +20,7 @@ PyTorch fallback: CPU inputs raise.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -537,10 +538,19 @@ class LightGlue(nn.Module):
         do_prune = conf.width_confidence > 0 and not self.training
         adaptive = do_early or do_prune
         use_lens = variable or adaptive or m != Lp or n != Lp
+        order_self = order_cross = None
         if not use_lens:
             lens = None
         elif variable:
-            lens = torch.from_numpy(lens_host.reshape(-1).copy()).to(dev)
+            # one upload: lens | launch order of the self attention | of the cross attention (sequences sorted by key
+            # count, longest first: a ragged batch's attention kernels then end on their shortest work items)
+            flat = lens_host.reshape(-1)
+            o_self = np.argsort(-flat, kind="stable").astype(np.int32)
+            o_cross = np.argsort(-flat[np.arange(S) ^ 1], kind="stable").astype(np.int32)
+            up = torch.from_numpy(np.concatenate([flat, o_self, o_cross])).to(dev)
+            lens, order_self, order_cross = up[:S], up[S:2 * S], up[2 * S:]
+            if os.environ.get("LGB200_ATTN_ORDER", "1") == "0":  # A/B switch
+                order_self = order_cross = None
         else:  # all pairs (m, n): filled on the device (no host copy, so the forward can be captured in a CUDA graph)
             lens = torch.empty(S, **i32)
             lens[0::2] = m
@@ -624,7 +634,8 @@ class LightGlue(nn.Module):
             # self block (lightglue.py:151-164)
             linear(EPI_HEADS, x, w["qkv_w"], w["qkv_b"], 768, 256, scale=(q_scale, 1.0, 1.0), n_rot=2,
                    outp=(q, k, v), lens_=la)
-            check(lib.lgb200_attention(prec, ptr(q), ptr(k), ptr(v), S, Lp, ptr(la), 0, ptr(ctx), st), "attention")
+            check(lib.lgb200_attention_ordered(prec, ptr(q), ptr(k), ptr(v), S, Lp, ptr(la), ptr(order_self), 0, ptr(ctx),
+                                               st), "attention")
             if not bf:  # (bf16: out_proj is folded into sf0_w, see _pack)
                 linear(EPI_ROWMAJOR, ctx, w["so_w"], w["so_b"], 256, 256, out=msg, lens_=la)
             linear(EPI_LN_GELU, x, w["sf0_w"], w["sf0_b"], 512, 512, A1=ctx if bf else msg, K0=256, gamma=w["sln_g"],
@@ -633,7 +644,8 @@ class LightGlue(nn.Module):
             # cross block (lightglue.py:193-222)
             linear(EPI_HEADS, x, w["cqv_w"], w["cqv_b"], 512, 256, scale=(c_scale, 1.0, 1.0), n_rot=0,
                    outp=(q, v, None), lens_=la)
-            check(lib.lgb200_attention(prec, ptr(q), ptr(q), ptr(v), S, Lp, ptr(la), 1, ptr(ctx), st), "attention")
+            check(lib.lgb200_attention_ordered(prec, ptr(q), ptr(q), ptr(v), S, Lp, ptr(la), ptr(order_cross), 1, ptr(ctx),
+                                               st), "attention")
             if not bf:
                 linear(EPI_ROWMAJOR, ctx, w["co_w"], w["co_b"], 256, 256, out=msg, lens_=la)
             linear(EPI_LN_GELU, x, w["cf0_w"], w["cf0_b"], 512, 512, A1=ctx if bf else msg, K0=256, gamma=w["cln_g"],

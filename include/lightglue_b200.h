@@ -125,6 +125,13 @@ int lgb200_linear(int precision, int epilogue, const void* A0, const void* A1, i
 int lgb200_attention(int precision, const void* Q, const void* K, const void* V,
                      int S, int Lp, const int32_t* lens, int kv_xor,
                      void* ctx, void* stream);
+/* Same, with a launch order for ragged batches: order[S] (DEVICE int32, a permutation of 0..S-1, or NULL) lists the
+ * sequences in the order their query tiles are handed to the SMs.  Sorted by key count, longest first, the kernel's
+ * tail consists of the shortest work items (a CTA's duration is proportional to lens[s ^ kv_xor]).  The result does
+ * not depend on it; the fp32 kernels ignore it. */
+int lgb200_attention_ordered(int precision, const void* Q, const void* K, const void* V,
+                             int S, int Lp, const int32_t* lens, const int32_t* order, int kv_xor,
+                             void* ctx, void* stream);
 
 /* ---- per-token heads -----------------------------------------------------------
  * Replaces matchability / token-confidence Linear(256,1) (+ sigmoid),

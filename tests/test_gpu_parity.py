@@ -261,6 +261,12 @@ def test_attention(prec, kv_xor):
         ref = (torch.softmax(sc, -1) @ v[skv, :, :nk].float()).permute(1, 0, 2).reshape(nq, 256)
         tol = dict(atol=2e-2, rtol=2e-2) if bf else dict(atol=2e-5, rtol=1e-4)
         torch.testing.assert_close(ctx[s, :nq].float(), ref, **tol)
+    # a launch order (ragged batches: longest sequences first) changes which CTA works on what, not the result
+    order = torch.argsort(-lens[torch.arange(S, device=DEV) ^ kv_xor].long(), stable=True).to(torch.int32)
+    ctx2 = torch.zeros_like(ctx)
+    rc = lib.lgb200_attention_ordered(prec, ptr(q), ptr(k), ptr(v), S, Lp, ptr(lens), ptr(order), kv_xor, ptr(ctx2), _stream())
+    assert rc == 0, lib.lgb200_error_string(rc)
+    assert torch.equal(ctx2, ctx)
 
 
 @pytest.mark.parametrize("scale", [20.0, 300.0], ids=["logits~1e3", "logits~2e4"])
