@@ -49,6 +49,15 @@ __device__ unsigned int g_attn_sm_slot[1024];
 #endif
 #define LG_POLY_HERE(i) ((((i) * LG_ATTN_POLY16) % 8) < LG_ATTN_POLY16)
 
+// waits of the TMA-producer and MMA-issuer warps: polling with a 64 ns sleep in between (a bare try_wait loop takes
+// issue slots from the softmax warps of the same sub-partitions: 0.661 -> 0.650 ms with the deferred-maximum loop, which
+// is short enough to feel it; with the r1 loop it made no difference).  -DLG_ATTN_SPIN restores the spinning waits.
+#ifdef LG_ATTN_SPIN
+#define LG_PI_WAIT(...) tc::mbar_wait(__VA_ARGS__)
+#else
+#define LG_PI_WAIT(...) tc::mbar_wait_relaxed(__VA_ARGS__)
+#endif
+
 namespace {
 
 constexpr int AT_BM = 128;   // queries per CTA
@@ -243,11 +252,11 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int ks = j % KST, vs = j % VST;
         const int row = kvrow + j * AT_BN + (int)crank * SLICE;
         const int off = (int)crank * SLICE * 128;
-        tc::mbar_wait(&k_empty[ks], ((j / KST) & 1) ^ 1);  // every CTA of the cluster released the stage
+        LG_PI_WAIT(&k_empty[ks], ((j / KST) & 1) ^ 1);  // every CTA of the cluster released the stage
         tc::mbar_arrive_expect_tx(&k_full[ks], TILE_BYTES);
         if (CL > 1) tc::tma_load_2d_mc(sK + ks * TILE_BYTES + off, &tmK, &k_full[ks], 0, row, MC_MASK);
         else tc::tma_load_2d(sK + ks * TILE_BYTES, &tmK, &k_full[ks], 0, row);
-        tc::mbar_wait(&v_empty[vs], ((j / VST) & 1) ^ 1);
+        LG_PI_WAIT(&v_empty[vs], ((j / VST) & 1) ^ 1);
         tc::mbar_arrive_expect_tx(&v_full[vs], TILE_BYTES);
         if (CL > 1) tc::tma_load_2d_mc(sV + vs * TILE_BYTES + off, &tmV, &v_full[vs], 0, row, MC_MASK);
         else tc::tma_load_2d(sV + vs * TILE_BYTES, &tmV, &v_full[vs], 0, row);
@@ -286,8 +295,8 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       __syncwarp();
       if (++ks == KST) { ks = 0; kph ^= 1; }
     };
-    tc::mbar_wait(q_full, 0);
-    tc::mbar_wait(&k_full[0], 0);
+    LG_PI_WAIT(q_full, 0);
+    LG_PI_WAIT(&k_full[0], 0);
     tc::fence_after_sync();
     issue_qk();
     const bool recm = (dbg_in & 16) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == LG_DBG_Z && lane == 0;
@@ -295,16 +304,16 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int j = 0; j < n_tiles; ++j) {
       MSTAMP(0);
       if (j + 1 < n_tiles) {
-        tc::mbar_wait(&k_full[ks], kph);
+        LG_PI_WAIT(&k_full[ks], kph);
         MSTAMP(1);
-        tc::mbar_wait(s_free, j & 1);  // softmax holds S(j) in registers
+        LG_PI_WAIT(s_free, j & 1);  // softmax holds S(j) in registers
         tc::fence_after_sync();
         MSTAMP(2);
         issue_qk();
         MSTAMP(3);
       }
-      tc::mbar_wait(&v_full[vs], vph);
-      tc::mbar_wait(p_ready, j & 1);
+      LG_PI_WAIT(&v_full[vs], vph);
+      LG_PI_WAIT(p_ready, j & 1);
       tc::fence_after_sync();
       MSTAMP(4);
       const uint64_t dV = dV0 + (uint64_t)(vs * (TILE_BYTES >> 4));

@@ -171,6 +171,9 @@ class LightGlue(nn.Module):
         self._packed: Dict = {}
         self._pack_key = None
         self._graphs: Dict = {}
+        # measurement hook (bench.py): a list to which the forward appends (start, end) CUDA events around every
+        # self-attention launch, i.e. the dominant kernel timed inside the running step
+        self._attn_events = None
 
     # ---- reference-compatible helpers ------------------------------------------------
 
@@ -634,8 +637,14 @@ class LightGlue(nn.Module):
             # self block (lightglue.py:151-164)
             linear(EPI_HEADS, x, w["qkv_w"], w["qkv_b"], 768, 256, scale=(q_scale, 1.0, 1.0), n_rot=2,
                    outp=(q, k, v), lens_=la)
+            if self._attn_events is not None:
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
             check(lib.lgb200_attention_ordered(prec, ptr(q), ptr(k), ptr(v), S, Lp, ptr(la), ptr(order_self), 0, ptr(ctx),
                                                st), "attention")
+            if self._attn_events is not None:
+                ev1.record()
+                self._attn_events.append((ev0, ev1))
             if not bf:  # (bf16: out_proj is folded into sf0_w, see _pack)
                 linear(EPI_ROWMAJOR, ctx, w["so_w"], w["so_b"], 256, 256, out=msg, lens_=la)
             linear(EPI_LN_GELU, x, w["sf0_w"], w["sf0_b"], 512, 512, A1=ctx if bf else msg, K0=256, gamma=w["sln_g"],
