@@ -6,6 +6,7 @@ B200-class GPU the import of the product path raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "liblightglue_b200.so"
@@ -51,6 +52,8 @@ def load(path: Path = LIB_PATH):
     global _lib
     if _lib is not None:
         return _lib
+    if path == LIB_PATH and os.environ.get("LGB200_LIB"):  # development switch: A/B a variant build of the library
+        path = Path(os.environ["LGB200_LIB"]).resolve()
     if not Path(path).exists():
         raise LightGlueB200Error(
             f"{path} is missing: build it with `python -m glue_factory_colon_b200.build` "

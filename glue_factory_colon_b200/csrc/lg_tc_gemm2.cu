@@ -34,6 +34,15 @@
 //   [2] MMA warp total   [3] epilogue warp 0 waiting for tfull   [4] epilogue warp 0 total   [5] tiles   [6] epilogue stats wait
 __device__ long long g_gemm_times[16];
 
+// waits of the TMA-producer and MMA-issuer warps: -DLG_GEMM_RELAXED polls with a sleep in between instead of spinning
+// (measured on the whole step: 20.4-20.6 ms against 20.2-20.4 ms spinning, and one 48 ms outlier -- not adopted; the
+// attention kernel, whose softmax warps compete with the waiting warps for issue slots, does gain from it)
+#ifdef LG_GEMM_RELAXED
+#define LG_PI_WAIT(...) tc::mbar_wait_relaxed(__VA_ARGS__)
+#else
+#define LG_PI_WAIT(...) tc::mbar_wait(__VA_ARGS__)
+#endif
+
 namespace {
 
 constexpr int BM = 128, BK = 64, BN = 128;
@@ -263,7 +272,7 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
       if (tile_skipped(g, mt)) continue;
       const int row = mt * BM + crank * SLICE_ROWS;
       for (int kb = 0; kb < g.kb_total; ++kb) {
-        tc::mbar_wait(&empty[stage], phase ^ 1);  // all CL consumers released this stage
+        LG_PI_WAIT(&empty[stage], phase ^ 1);  // all CL consumers released this stage
         uint8_t* dst = sA + stage * A_STAGE + crank * (SLICE_ROWS * 128);
         const CUtensorMap* tm = kb < g.kb_a0 ? &maps.a0 : &maps.a1;
         const int kc = (kb < g.kb_a0 ? kb : kb - g.kb_a0) * BK;
@@ -286,7 +295,7 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
     constexpr uint32_t idesc = tc::idesc_bf16(BM, BN, 0);
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
-    tc::mbar_wait(w_full, 0);
+    LG_PI_WAIT(w_full, 0);
     const uint64_t dW0 = tc::smem_desc_sw128(tc::smem_u32(sW), 0, 1024);
     const uint64_t dA0 = tc::smem_desc_sw128(tc::smem_u32(sA), 0, 1024);
 #ifdef LG_GEMM_DEBUG
@@ -301,13 +310,13 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
     for (int mt = m_first; mt < g.m_tiles; mt += m_step) {
       if (tile_skipped(g, mt)) continue;
       GT0();
-      tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
+      LG_PI_WAIT(&tempty[acc], acc_phase ^ 1);
       GT1(w_acc);
       tc::fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * BN;
       for (int kb = 0; kb < g.kb_total; ++kb) {
         GT0();
-        tc::mbar_wait(&full[stage], phase);
+        LG_PI_WAIT(&full[stage], phase);
         GT1(w_full_c);
         tc::fence_after_sync();
         const uint64_t dA = dA0 + (uint64_t)(stage * (A_STAGE >> 4));
@@ -391,7 +400,7 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
       if (MODE == MODE_LN && ew == 0 && lane == 0)
         tc::mbar_arrive_expect_tx(&stats_bar[iter & 1], 2 * CL * 128 * 8);  // partials from every peer warp
       GT0();
-      tc::mbar_wait(&tfull[acc], acc_phase);
+      LG_PI_WAIT(&tfull[acc], acc_phase);
       GT1(e_wait);
       tc::fence_after_sync();
       uint32_t v[64];
@@ -421,7 +430,7 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
 #pragma unroll
         for (int p = 0; p < CL; ++p) st_async_f2(map_to_rank(slot, p), sum, sq, map_to_rank(bar, p));
         GT0();
-        tc::mbar_wait(&stats_bar[buf], (iter >> 1) & 1);
+        LG_PI_WAIT(&stats_bar[buf], (iter >> 1) & 1);
         GT1(e_stats);
         float ts = 0.f, tq = 0.f;
 #pragma unroll
@@ -446,10 +455,10 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
         if (use_in) {
           const uint8_t* tin = stg_in;
           if (PF) {
-            tc::mbar_wait(&in_bar[(iter & 1) * 8 + ew], (iter >> 1) & 1);
+            LG_PI_WAIT(&in_bar[(iter & 1) * 8 + ew], (iter >> 1) & 1);
             tin = stg_in + (iter & 1) * 8 * STG;
           } else {
-            tc::mbar_wait(&in_bar[ew], iter & 1);
+            LG_PI_WAIT(&in_bar[ew], iter & 1);
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -670,7 +679,7 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
       if (pair_skipped(g, mt)) continue;
       const int row = mt * 2 * BM + (int)crank * BM;
       for (int kb = 0; kb < g.kb_total; ++kb) {
-        tc::mbar_wait(&empty[stage], phase ^ 1);  // the pair's MMAs have read this stage (in both CTAs)
+        LG_PI_WAIT(&empty[stage], phase ^ 1);  // the pair's MMAs have read this stage (in both CTAs)
         const CUtensorMap* tm = kb < g.kb_a0 ? &maps.a0 : &maps.a1;
         const int kc = (kb < g.kb_a0 ? kb : kb - g.kb_a0) * BK;
         if (tc::elect_one()) {
@@ -689,7 +698,7 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
     tc::pdl_wait();  // (reads lens)
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
-    tc::mbar_wait(w_full, 0);
+    LG_PI_WAIT(w_full, 0);
     if (crank == 0) {
       // ---------------------------------------------------------------- MMA issuer (leader CTA)
       constexpr uint32_t idesc = tc::idesc_bf16(256, BN2, 0);
@@ -710,7 +719,7 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
         const uint32_t d_tmem = tmem_base + acc * BN2;
         for (int kb = 0; kb < g.kb_total; ++kb) {
           GT0();
-          tc::mbar_wait(&full[stage], phase);
+          LG_PI_WAIT(&full[stage], phase);
           GT1(w_full_c);
           GT0();
           mbar_wait_cluster(&peer_full[stage], phase);
@@ -741,7 +750,7 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
       for (int mt = m_first; mt < g.m_tiles; mt += m_step) {
         if (pair_skipped(g, mt)) continue;
         for (int kb = 0; kb < g.kb_total; ++kb) {
-          tc::mbar_wait(&full[stage], phase);
+          LG_PI_WAIT(&full[stage], phase);
           if (lane == 0) mbar_arrive_remote(&peer_full[stage], 0);
           __syncwarp();
           if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -797,11 +806,11 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
                             mn * 2 * BM + (int)crank * BM + quarter * 32);
           }
         }
-        tc::mbar_wait(&tfull[acc], acc_phase);
+        LG_PI_WAIT(&tfull[acc], acc_phase);
         tc::fence_after_sync();
         uint32_t in[16];
         if (use_rot) {
-          tc::mbar_wait(&in_bar[(iter & 1) * NEW + ew], (iter >> 1) & 1);
+          LG_PI_WAIT(&in_bar[(iter & 1) * NEW + ew], (iter >> 1) & 1);
           const uint8_t* tin = stg_in + (iter & 1) * NEW * STGW;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -875,7 +884,7 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
           tc::tma_load_2d(stg_in, &maps.in, &in_bar[ew], colg, row0);  // residual rows
         }
         if (cb == 0) {
-          tc::mbar_wait(&tfull[acc], acc_phase);
+          LG_PI_WAIT(&tfull[acc], acc_phase);
           tc::fence_after_sync();
         }
         uint32_t v[64];
@@ -894,7 +903,7 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
         uint32_t pk[32];
         uint32_t in[32];
         if (use_in) {
-          tc::mbar_wait(&in_bar[ew], n_in & 1);
+          LG_PI_WAIT(&in_bar[ew], n_in & 1);
           ++n_in;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -1044,7 +1053,7 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
       if (pair_skipped(g, mt)) continue;
       const int row = mt * 2 * BM + (int)parity * BM + (int)pair * 64;  // this CTA loads 64 of the 128 rows
       for (int kb = 0; kb < g.kb_total; ++kb) {
-        tc::mbar_wait(&empty[stage], phase ^ 1);
+        LG_PI_WAIT(&empty[stage], phase ^ 1);
         const CUtensorMap* tm = kb < g.kb_a0 ? &maps.a0 : &maps.a1;
         const int kc = (kb < g.kb_a0 ? kb : kb - g.kb_a0) * BK;
         if (tc::elect_one()) {
@@ -1063,7 +1072,7 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
     tc::pdl_wait();  // (reads lens)
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
-    tc::mbar_wait(w_full, 0);
+    LG_PI_WAIT(w_full, 0);
     if (parity == 0) {
       // ---------------------------------------------------------------- MMA issuer (leader of the pair)
       constexpr uint32_t idesc = tc::idesc_bf16(256, BN2, 0);
@@ -1085,7 +1094,7 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
         const uint32_t d_tmem = tmem_base + acc * BN2;
         for (int kb = 0; kb < g.kb_total; ++kb) {
           GT0();
-          tc::mbar_wait(&full[stage], phase);
+          LG_PI_WAIT(&full[stage], phase);
           GT1(w_full_c);
           GT0();
           mbar_wait_cluster(&peer_full[stage], phase);
@@ -1116,7 +1125,7 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
       for (int mt = cid; mt < g.m_tiles; mt += ncl) {
         if (pair_skipped(g, mt)) continue;
         for (int kb = 0; kb < g.kb_total; ++kb) {
-          tc::mbar_wait(&full[stage], phase);
+          LG_PI_WAIT(&full[stage], phase);
           if (lane == 0) mbar_arrive_remote(&peer_full[stage], crank - 1);
           __syncwarp();
           if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -1149,7 +1158,7 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
       const int buf = iter & 1;
       if (ew == 0 && lane == 0) tc::mbar_arrive_expect_tx(&stats_bar[buf], 2 * 128 * 8);  // one partial per row from each CTA
       GT0();
-      tc::mbar_wait(&tfull[acc], acc_phase);
+      LG_PI_WAIT(&tfull[acc], acc_phase);
       GT1(e_wait);
       tc::fence_after_sync();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN2 + cq * 32;
@@ -1184,7 +1193,7 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
         st_async_f2(map_to_rank(slot, partner), sum, sq, map_to_rank(bar, partner));
       }
       GT0();
-      tc::mbar_wait(&stats_bar[buf], (iter >> 1) & 1);
+      LG_PI_WAIT(&stats_bar[buf], (iter >> 1) & 1);
       GT1(e_stats);
       const float2 st0 = s_stats[(buf * 2 + 0) * 128 + r_in_tile], st1 = s_stats[(buf * 2 + 1) * 128 + r_in_tile];
       const float inv_n = 1.f / 512.f;
