@@ -28,17 +28,24 @@ def plan_batches(
     max_pairs: int = 64,
     max_tokens: int = 64 * 2 * 2048,
     bucket: int = 128,
+    by_size: bool = False,
 ) -> List[List[int]]:
-    """Greedy, order-preserving batching.  `counts[i] = (n0, n1)`.  A batch is closed when adding the next pair
+    """Greedy batching.  `counts[i] = (n0, n1)`.  A batch is closed when adding the next pair
     would exceed `max_pairs` or make the PADDED token count B * (N0p + N1p) exceed `max_tokens`
     (N0p / N1p = the batch maxima rounded up to `bucket`).  Every pair lands in exactly one batch; a single pair
-    larger than the token budget gets a batch of its own."""
+    larger than the token budget gets a batch of its own.  Order-preserving by default; `by_size` visits the pairs
+    largest first, so that a batch holds pairs of similar size: every kernel pads a batch to its largest pair, and
+    the attention cost of the padding grows with its square."""
     if max_pairs < 1 or bucket < 1:
         raise ValueError("max_pairs and bucket must be positive")
     batches: List[List[int]] = []
     cur: List[int] = []
     m0 = m1 = 0
-    for i, (n0, n1) in enumerate(counts):
+    visit = range(len(counts))
+    if by_size:
+        visit = sorted(visit, key=lambda i: (-max(counts[i]), -min(counts[i]), i))
+    for i in visit:
+        n0, n1 = counts[i]
         if n0 < 0 or n1 < 0:
             raise ValueError("negative keypoint count")
         c0, c1 = max(m0, _round_up(max(n0, 1), bucket)), max(m1, _round_up(max(n1, 1), bucket))
@@ -128,7 +135,8 @@ class BatchedPairMatcher:
     D2H_KEYS = ("matches0", "matches1", "matching_scores0", "matching_scores1")
 
     def __init__(self, matcher, max_pairs: int = 64, max_tokens: int = 64 * 2 * 2048, bucket: int = 128,
-                 device: Optional[torch.device] = None, return_log_assignment: bool = False, window: int = 256):
+                 device: Optional[torch.device] = None, return_log_assignment: bool = False, window: int = 256,
+                 sort_by_size: bool = True):
         self.matcher = matcher
         self.max_pairs, self.max_tokens, self.bucket = max_pairs, max_tokens, bucket
         self.device = torch.device(device) if device is not None else next(matcher.parameters()).device
@@ -136,6 +144,7 @@ class BatchedPairMatcher:
             raise RuntimeError("BatchedPairMatcher needs the matcher on a CUDA device (there is no CPU path)")
         self.return_log_assignment = return_log_assignment
         self.window = max(window, max_pairs)  # pairs pulled from the iterator before batches are planned
+        self.sort_by_size = sort_by_size      # batches of similar-sized pairs within a window (results stay in input order)
 
     # ------------------------------------------------------------------------------------------
     def _upload(self, host: dict, stream: torch.cuda.Stream):
@@ -206,7 +215,7 @@ class BatchedPairMatcher:
             if not chunk:
                 break
             counts = [(int(p["keypoints0"].shape[0]), int(p["keypoints1"].shape[0])) for p in chunk]
-            plan = plan_batches(counts, self.max_pairs, self.max_tokens, self.bucket)
+            plan = plan_batches(counts, self.max_pairs, self.max_tokens, self.bucket, by_size=self.sort_by_size)
             staged = None
             for bi, idx in enumerate(plan):
                 if staged is None:

@@ -33,6 +33,28 @@ def test_plan_batches_covers_every_pair_once_in_order_and_respects_budgets():
         plan_batches([(1, 1)], max_pairs=0)
 
 
+def test_plan_batches_by_size_groups_similar_pairs():
+    g = torch.Generator().manual_seed(1)
+    counts = [(int(a), int(b)) for a, b in torch.randint(200, 4097, (256, 2), generator=g)]
+
+    def padded_cost(plan):  # attention work of the padded batches: B * (N0p^2 + N1p^2 + 1.5 N0p N1p)
+        tot = 0
+        for b in plan:
+            n0 = max(-(-counts[i][0] // 128) * 128 for i in b)
+            n1 = max(-(-counts[i][1] // 128) * 128 for i in b)
+            tot += len(b) * (n0 * n0 + n1 * n1 + 1.5 * n0 * n1)
+        return tot
+
+    kw = dict(max_pairs=32, max_tokens=32 * 2 * 4096, bucket=128)
+    plain, sized = plan_batches(counts, **kw), plan_batches(counts, by_size=True, **kw)
+    assert sorted(i for b in sized for i in b) == list(range(256))  # every pair exactly once
+    for b in sized:
+        n0 = max(-(-counts[i][0] // 128) * 128 for i in b)
+        n1 = max(-(-counts[i][1] // 128) * 128 for i in b)
+        assert 1 <= len(b) <= 32 and (len(b) == 1 or len(b) * (n0 + n1) <= 32 * 2 * 4096)
+    assert padded_cost(sized) < 0.8 * padded_cost(plain)
+
+
 def test_collate_pads_with_zeros_and_records_counts():
     pairs = [_pair(100, 257, 1), _pair(300, 5, 2)]
     out = collate_pairs(pairs, bucket=128)
