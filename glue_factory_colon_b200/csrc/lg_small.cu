@@ -346,72 +346,104 @@ extern "C" int lgb200_prune_compact(const float* match, const float* conf, float
 // ---------------------------------------------------------------------------
 // filter_matches
 // ---------------------------------------------------------------------------
-// Pass A streams the score matrix once.  A CTA owns a strip of FM_ROWS rows and
-// 128 columns per step (each thread one float4 of one row); row maxima are
-// reduced with warp shuffles, column maxima with packed 64-bit atomicMax on
-// (ordered value << 32 | ~index), which also resolves ties to the lowest index.
+// Pass A streams the score matrix once (HBM-bound: N*M*4 bytes read, (N+M)*8 written).  A WARP owns FM_WROWS whole rows
+// and sweeps them in blocks of 128 columns, lane = column (every load instruction is one contiguous 128-byte row
+// segment; the row pitch of (M+1)*4 bytes rules out aligned vector loads), 32 independent loads in flight per lane.
+// Values are compared as order-preserving signed keys (NaN above everything, torch.max); with ascending visit order a
+// strictly-greater test keeps the LOWEST index among equal values.  Row maxima stay in registers for the whole sweep
+// (one shuffle reduction per row at the end, one plain store: no other warp sees the row); column maxima are
+// final for the warp's rows after each block and go out as packed 64-bit atomicMax on
+// (ordered value << 32 | ~index) -- N / FM_WROWS atomics per column, no shared memory, no block-wide barrier.
+// The first version (256-thread CTAs, 64-bit packed compares per element, two __syncthreads per block) read its
+// matrix at 1.0 TB/s.
 // Pass B does the mutual check, exp, threshold and scatter.
 
 // (fm_pack / fm_value / fm_index live in lg_common.cuh: the bf16 assignment kernel produces the same
 // packed maxima in its epilogue so that this pass can be skipped.)
 
-#define FM_ROWS 32
-__global__ void __launch_bounds__(256) fm_argmax_kernel(const float* __restrict__ scores, int R, int C,
-                                                        const int32_t* __restrict__ lens,
-                                                        unsigned long long* __restrict__ best0,
-                                                        unsigned long long* __restrict__ best1) {
-  const int b = blockIdx.y;
-  const int n0 = lens ? lens[2 * b] : R - 1, n1 = lens ? lens[2 * b + 1] : C - 1;
-  const int r0 = blockIdx.x * FM_ROWS;
-  if (r0 >= n0 || n1 <= 0) return;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;  // 8 warps, 4 rows each
-  const float* base = scores + (size_t)b * R * C;
-  unsigned long long* b0 = best0 + (size_t)b * R;
-  unsigned long long* b1 = best1 + (size_t)b * C;
-  __shared__ unsigned long long colbest[8][128];
-  unsigned long long rowbest[FM_ROWS / 8];
+#ifndef FM_WROWS
+#define FM_WROWS 16  // rows per warp (row maxima live in 2 x FM_WROWS registers)
+#define FM_GROUP 8   // rows loaded together: 32 independent 128-byte loads in flight per warp
+#define FM_MINB 8    // CTAs per SM the register allocation is held to (128 registers, 16 warps per SM)
+#endif
+#define FM_WARPS 2   // warps per CTA (independent of each other)
+
+// float -> signed int whose order is the float order, every NaN on top; key ^ 0x80000000 is fm_pack's key
+__device__ __forceinline__ int fm_key(float v) {
+  const int u = __float_as_int(v);
+  const int k = u ^ ((u >> 31) & 0x7fffffff);
+  return v != v ? 0x7fffffff : k;
+}
+__device__ __forceinline__ unsigned long long fm_pack_key(int key, int idx) {
+  return ((unsigned long long)((unsigned)key ^ 0x80000000u) << 32) | (unsigned)(0xffffffffu - (unsigned)idx);
+}
+
+// one block of 128 columns x this warp's 32 rows; FULL: no bounds checks
+template <bool FULL>
+__device__ __forceinline__ void fm_block(const float* __restrict__ p, int C, int rows, int cols, int r0, int c0, int lane,
+                                         int (&rk)[FM_WROWS], int (&ri)[FM_WROWS],
+                                         unsigned long long* __restrict__ b1) {
+  int ck[4], cr[4];
 #pragma unroll
-  for (int i = 0; i < FM_ROWS / 8; ++i) rowbest[i] = 0ull;
-  for (int c0 = 0; c0 < n1; c0 += 128) {
-    unsigned long long cb[4] = {0ull, 0ull, 0ull, 0ull};
+  for (int j = 0; j < 4; ++j) { ck[j] = (int)0x80000000; cr[j] = 0; }
+  const float* q = p + lane;  // walks down the rows group by group (32 hoisted row pointers would cost 64 registers)
 #pragma unroll
-    for (int i = 0; i < FM_ROWS / 8; ++i) {
-      const int r = r0 + wid * (FM_ROWS / 8) + i;
-      if (r < n0) {
-        const float* rowp = base + (size_t)r * C;
+  for (int g = 0; g < FM_WROWS / FM_GROUP; ++g) {
+    float v[FM_GROUP][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c = c0 + lane + 32 * j;  // coalesced 128-byte row segments
-          if (c < n1) {
-            const float v = rowp[c];
-            const unsigned long long pr = fm_pack(v, c), pc = fm_pack(v, r);
-            rowbest[i] = pr > rowbest[i] ? pr : rowbest[i];
-            cb[j] = pc > cb[j] ? pc : cb[j];
-          }
-        }
+    for (int i = 0; i < FM_GROUP; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = g * FM_GROUP + i, c = lane + 32 * j;
+        if (FULL || (r < rows && c < cols)) v[i][j] = __ldcs(q + i * C + 32 * j);
       }
-    }
+    q += FM_GROUP * C;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) colbest[wid][lane + 32 * j] = cb[j];
-    __syncthreads();
-    if (threadIdx.x < 128) {
-      unsigned long long m = colbest[0][threadIdx.x];
+    for (int i = 0; i < FM_GROUP; ++i)
 #pragma unroll
-      for (int w = 1; w < 8; ++w) m = colbest[w][threadIdx.x] > m ? colbest[w][threadIdx.x] : m;
-      const int c = c0 + threadIdx.x;
-      if (c < n1 && m != 0ull) atomicMax(b1 + c, m);
-    }
-    __syncthreads();
+      for (int j = 0; j < 4; ++j) {
+        const int r = g * FM_GROUP + i, c = lane + 32 * j;
+        int k = (int)0x80000000;  // out of range: never strictly greater than anything
+        if (FULL || (r < rows && c < cols)) k = fm_key(v[i][j]);
+        if (k > rk[r]) { rk[r] = k; ri[r] = c0 + c; }
+        if (k > ck[j]) { ck[j] = k; cr[j] = r0 + r; }
+      }
+    asm volatile("" ::: "memory");  // keep the next group's loads behind this group's compares (register budget)
   }
 #pragma unroll
-  for (int i = 0; i < FM_ROWS / 8; ++i) {
-    unsigned long long m = rowbest[i];
+  for (int j = 0; j < 4; ++j)
+    if (FULL || lane + 32 * j < cols) atomicMax(b1 + c0 + lane + 32 * j, fm_pack_key(ck[j], cr[j]));
+}
+
+__global__ void __launch_bounds__(FM_WARPS * 32, FM_MINB) fm_argmax_kernel(const float* __restrict__ scores, int R, int C,
+                                                                  const int32_t* __restrict__ lens,
+                                                                  unsigned long long* __restrict__ best0,
+                                                                  unsigned long long* __restrict__ best1) {
+  const int b = blockIdx.y;
+  const int n0 = lens ? lens[2 * b] : R - 1, n1 = lens ? lens[2 * b + 1] : C - 1;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int r0 = (blockIdx.x * FM_WARPS + wid) * FM_WROWS;
+  if (r0 >= n0 || n1 <= 0) return;  // (warps are independent: no block-wide barrier below)
+  const float* base = scores + ((size_t)b * R + r0) * C;
+  unsigned long long* b1 = best1 + (size_t)b * C;
+  const int rows = min(FM_WROWS, n0 - r0);
+  int rk[FM_WROWS], ri[FM_WROWS];
+#pragma unroll
+  for (int i = 0; i < FM_WROWS; ++i) { rk[i] = (int)0x80000000; ri[i] = 0; }
+  int c0 = 0;
+  if (rows == FM_WROWS)
+    for (; c0 + 128 <= n1; c0 += 128) fm_block<true>(base + c0, C, rows, 128, r0, c0, lane, rk, ri, b1);
+  for (; c0 < n1; c0 += 128) fm_block<false>(base + c0, C, rows, min(128, n1 - c0), r0, c0, lane, rk, ri, b1);
+  unsigned long long* b0 = best0 + (size_t)b * R + r0;
+#pragma unroll
+  for (int i = 0; i < FM_WROWS; ++i) {
+    unsigned long long m = fm_pack_key(rk[i], ri[i]);
+#pragma unroll
     for (int o = 16; o; o >>= 1) {
       const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
       m = t > m ? t : m;
     }
-    const int r = r0 + wid * (FM_ROWS / 8) + i;
-    if (lane == 0 && r < n0) b0[r] = m;
+    if (lane == (i & 31) && i < rows) b0[i] = m;
   }
 }
 
@@ -479,8 +511,8 @@ extern "C" int lgb200_filter_matches(const float* scores, int B, int R, int C, c
   if (!workspace_has_best) {  // otherwise lgb200_assign_scores already left the packed maxima there
     cudaError_t e = cudaMemsetAsync(workspace, 0, sizeof(unsigned long long) * (size_t)B * (R + C), st);
     if (e != cudaSuccess) return (int)e;
-    dim3 g1((R - 1 + FM_ROWS - 1) / FM_ROWS, B);
-    fm_argmax_kernel<<<g1, 256, 0, st>>>(scores, R, C, lens, best0, best1);
+    dim3 g1((R - 1 + FM_WARPS * FM_WROWS - 1) / (FM_WARPS * FM_WROWS), B);
+    fm_argmax_kernel<<<g1, FM_WARPS * 32, 0, st>>>(scores, R, C, lens, best0, best1);
     LG_LAUNCH_CHECK();
   }
   const int mxn = (R > C ? R : C) - 1;

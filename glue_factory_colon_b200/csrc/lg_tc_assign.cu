@@ -39,6 +39,34 @@ __device__ __forceinline__ void amax_merge(float& va, int& ia, float vb, int ib)
   if (vb > va || (vb != vb && va == va)) { va = vb; ia = ib; }
 }
 
+// First arg-max of 32 candidates held in registers, torch.max semantics (lowest index among equal maxima; the
+// first NaN if there is one).  The serial chain above is 32 dependent compare -> select steps (~300 cycles with two
+// warps per scheduler to hide them); here a NaN-propagating maximum tree of depth 5, then 32 independent equality
+// tests collected in a bit mask whose lowest set bit is the answer.  `max.NaN` makes the tree return NaN iff a
+// candidate is NaN, and only then (inputs that are already garbage) the mask is built from `v != v` instead.
+__device__ __forceinline__ float max_nan(float a, float b) {
+  float d;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
+__device__ __forceinline__ void chunk_argmax(const float (&v)[32], float& best, int& idx) {
+  float m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = max_nan(max_nan(v[i], v[i + 8]), max_nan(v[i + 16], v[i + 24]));
+  const float mx = max_nan(max_nan(max_nan(m[0], m[1]), max_nan(m[2], m[3])),
+                           max_nan(max_nan(m[4], m[5]), max_nan(m[6], m[7])));
+  uint32_t mask[4] = {0u, 0u, 0u, 0u};
+  if (mx == mx) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) mask[i & 3] |= (v[i] == mx) ? (1u << i) : 0u;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) mask[i & 3] |= (v[i] != v[i]) ? (1u << i) : 0u;
+  }
+  idx = __ffs((int)((mask[0] | mask[1]) | (mask[2] | mask[3]))) - 1;
+  best = mx;
+}
+
 // Epilogue history: the first version had 4 epilogue warps and a rolled, dependent LDS -> FADD -> STG loop per
 // output row, and fetched z / lse for the column constants on the critical path of every chunk; pass 2 wrote its
 // 1.075 GB at 0.88 TB/s (1.30 ms at 64 pairs x 2048).  Now 8 warps, each owning 32 rows x 64 columns of a tile,
@@ -229,8 +257,15 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t
             xp[lane * 33 + i] = val[i];
           }
           if (best0) {
+#ifdef LG_ASSIGN_SERIAL_ARGMAX
 #pragma unroll
             for (int i = 0; i < 32; ++i) amax_merge(rbest, ridx, val[i], cb + i);
+#else
+            float cm;
+            int ci;
+            chunk_argmax(val, cm, ci);
+            amax_merge(rbest, ridx, cm, cb + ci);
+#endif
           }
           if constexpr (LOSS) {
             if (row < nq) {
@@ -273,8 +308,12 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t
                 if constexpr (!LOSS) out[(size_t)rr * C] = cv[rr];
               }
               if (best1) {
+#ifdef LG_ASSIGN_SERIAL_ARGMAX
 #pragma unroll
                 for (int rr = 0; rr < 32; ++rr) amax_merge(cbest, cidx, cv[rr], rr);
+#else
+                chunk_argmax(cv, cbest, cidx);
+#endif
               }
             } else {
               for (int rr = 0; rr < rows_here; ++rr) {

@@ -406,6 +406,60 @@ def test_assignment_kernels(prec):
         assert sc[b, R - 1, C - 1] == 0 and (sc[b, n0:R - 1, :] == 0).all() and (sc[b, :, n1:C - 1] == 0).all()
 
 
+def test_assignment_fused_argmax_ties_and_nan():
+    """The arg-maxima fused into the bf16 MatchAssignment epilogue follow torch.max on the matrix it writes: lowest
+    index among exactly equal maxima (duplicated descriptors give bit-equal columns / rows), first NaN if any."""
+    lib = _abi.load()
+    torch.manual_seed(11)
+    B, Lp = 2, 256
+    S, R, C = 2 * B, Lp + 1, Lp + 1
+    md = (torch.randn(S, Lp, 256, device=DEV) / 4).to(torch.bfloat16)
+    z = torch.randn(S, Lp, device=DEV)
+    for dup in ((5, 77, 200), (33, 34), (130, 255)):  # equal keys in image 1 of pair 0: tied row maxima
+        md[1, list(dup[1:])] = md[1, dup[0]].clone()
+        z[1, list(dup[1:])] = z[1, dup[0]].clone()
+    for dup in ((0, 31, 32), (100, 228)):             # equal queries in image 0 of pair 0: tied column maxima
+        md[0, list(dup[1:])] = md[0, dup[0]].clone()
+        z[0, list(dup[1:])] = z[0, dup[0]].clone()
+    md[0, 1:8] = md[0, 0].clone()                      # more duplicated queries (z differs: ties only where equal)
+    z[2, 40] = float("nan")                            # pair 1: a NaN row and a NaN column
+    z[3, 130] = float("nan")
+    lse = torch.zeros(S, Lp, device=DEV)
+    assert lib.lgb200_assign_lse(_abi.BF16, ptr(md), S, Lp, None, ptr(lse), _stream()) == 0
+    sc = torch.empty(B, R, C, device=DEV)
+    ws = torch.empty(B * (R + C), device=DEV, dtype=torch.int64)
+    assert lib.lgb200_assign_scores(_abi.BF16, ptr(md), ptr(z), ptr(lse), B, Lp, None, R, C, ptr(sc), ptr(ws), _stream()) == 0
+    ws_fused = ws.clone()  # (the stand-alone filter below overwrites the workspace)
+    inner = sc[:, :-1, :-1]
+    assert torch.equal(inner[0, :, 5], inner[0, :, 77]) and torch.equal(inner[0, 0], inner[0, 31])  # ties are exact
+    assert inner[1, 40].isnan().all() and inner[1, :, 130].isnan().all()
+    got = {}
+    for has_best in (1, 0):
+        m0 = torch.empty(B, Lp, device=DEV, dtype=torch.int64); m1 = torch.empty_like(m0)
+        s0 = torch.empty(B, Lp, device=DEV); s1 = torch.empty_like(s0)
+        assert lib.lgb200_filter_matches(ptr(sc), B, R, C, None, -1.0, None, None, 0, Lp, Lp, ptr(m0), ptr(m1), ptr(s0),
+                                         ptr(s1), ptr(ws), has_best, _stream()) == 0
+        got[has_best] = (m0, m1, s0, s1)
+    for a, b_ in zip(got[1], got[0]):
+        assert torch.equal(a, b_) or torch.equal(a.nan_to_num(-7.0), b_.nan_to_num(-7.0))
+    # and against torch.max itself on the CPU (filter_matches, lightglue.py:294-319)
+    inner_c = inner.cpu()
+    mx0, mx1 = inner_c.max(2), inner_c.max(1)
+    assert int(mx0.indices[1, 40]) == 0 and int(mx1.indices[1, 130]) == 0 and int(mx0.indices[1, 3]) == 130  # first NaN
+    ws_c = ws_fused.cpu().view(-1)
+    ws_row = ws_c[: B * R].view(B, R)[:, :Lp]
+    ws_col = ws_c[B * R:].view(B, C)[:, :Lp]
+    unpack = lambda w: (0xFFFFFFFF - (w & 0xFFFFFFFF))  # noqa: E731  (fm_pack: low word = ~index)
+    bad0 = (unpack(ws_row) != mx0.indices).nonzero()
+    bad1 = (unpack(ws_col) != mx1.indices).nonzero()
+    assert bad0.numel() == 0, f"row arg-max differs from torch at {bad0[:5].tolist()}"
+    assert bad1.numel() == 0, f"column arg-max differs from torch at {bad1[:5].tolist()}"
+    mutual0 = torch.arange(Lp)[None] == mx1.indices.gather(1, mx0.indices)
+    m0 = got[1][0].cpu()
+    assert torch.equal(m0[0] > -1, mutual0[0])  # pair 0 holds no NaN; threshold -1 keeps every mutual match
+    assert (m0[1] == -1).all()                  # pair 1: every row maximum is NaN, NaN > threshold is false
+
+
 # ------------------------------------------------------------------ whole forward
 
 
