@@ -4,6 +4,7 @@
 // shuffles for reductions, no shared-memory tiling needed.
 #include "lg_common.cuh"
 #include <cuda_fp16.h>
+#include <cooperative_groups.h>
 
 unsigned long long lg_launch_counter = 0;
 
@@ -241,14 +242,22 @@ extern "C" int lgb200_exit_check(const float* conf, int B, int Lp, const int32_t
 }
 
 // ---------------------------------------------------------------------------
-// prune_compact: stable stream compaction of token rows, one CTA per sequence
+// prune_compact: stable stream compaction of token rows, one thread-block CLUSTER per sequence
 // ---------------------------------------------------------------------------
 // Phase 1: keep flags + block-wide exclusive scan (1024 threads, chunks of 1024)
-//          -> dst position per row in shared memory (Lp <= 8192).
+//          -> dst position per row in shared memory (Lp <= 8192).  Every CTA of the cluster does the whole scan
+//          (8 KB of flags): cheaper than exchanging it.
 // Phase 2: warps copy kept rows (x32 1 KB, x16 512 B, rot 256 B, ind) to the
-//          destination buffers with 16-byte accesses.
+//          destination buffers with 16-byte accesses; the rows are dealt round-robin to the PC_SPLIT x 32 warps of
+//          the cluster.  (Adaptive inference runs at batch 1 in the reference, i.e. two sequences: with one CTA per
+//          sequence the copy of 2048 rows was 64 dependent iterations per warp on two SMs, 20-38 us per layer.)
+// lens / lens_active are updated in place by rank 0 at the end; the cluster barrier after the first reads is what
+// makes that safe (all CTAs of a cluster are co-resident).
 #define LG_MAX_LP 8192
-__global__ void __launch_bounds__(1024) prune_compact_kernel(
+#ifndef PC_SPLIT
+#define PC_SPLIT 8
+#endif
+__global__ void __cluster_dims__(PC_SPLIT, 1, 1) __launch_bounds__(1024) prune_compact_kernel(
     const float* __restrict__ match, const float* __restrict__ conf, float thr, float keep_above,
     int Lp, int32_t* __restrict__ lens, int32_t* __restrict__ lens_active,
     const float* __restrict__ x32s, float* __restrict__ x32d, const __nv_bfloat16* __restrict__ x16s,
@@ -257,12 +266,12 @@ __global__ void __launch_bounds__(1024) prune_compact_kernel(
   __shared__ int16_t dst[LG_MAX_LP];
   __shared__ int warp_sum[32];
   __shared__ int running;
-  const int s = blockIdx.x;
+  const int s = blockIdx.y, part = blockIdx.x;  // part = rank in the cluster
   const int n = lens[s];
   const bool active = lens_active[s] != 0;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (threadIdx.x == 0) running = 0;
-  __syncthreads();
+  cooperative_groups::this_cluster().sync();  // (also a block barrier) every CTA has read the counts
   for (int base = 0; base < n; base += 1024) {
     const int l = base + threadIdx.x;
     int keep = 0;
@@ -292,7 +301,7 @@ __global__ void __launch_bounds__(1024) prune_compact_kernel(
   }
   const int kept = running;
   // phase 2: one warp per row
-  for (int l = wid; l < n; l += 32) {
+  for (int l = part * 32 + wid; l < n; l += 32 * PC_SPLIT) {
     const int d = dst[l];
     if (d < 0) continue;
     const size_t so = (size_t)s * Lp + l, dofs = (size_t)s * Lp + d;
@@ -314,7 +323,7 @@ __global__ void __launch_bounds__(1024) prune_compact_kernel(
       if (active) prune_cnt[(size_t)s * Lp + orig] += 1;
     }
   }
-  if (threadIdx.x == 0 && active) {
+  if (part == 0 && threadIdx.x == 0 && active) {
     lens[s] = kept;
     lens_active[s] = kept;
   }
@@ -331,10 +340,10 @@ extern "C" int lgb200_prune_compact(const float* match, const float* conf, float
   if ((x32_src && !x32_dst) || (x16_src && !x16_dst) || (rot_src && !rot_dst) || (rot16_src && !rot16_dst) ||
       (!x32_src && !x16_src))
     return LGB200_ERR_NULL;
-  if (Lp > LG_MAX_LP || Lp % 128) return LGB200_ERR_SHAPE;
+  if (Lp > LG_MAX_LP || Lp % 128 || S < 1 || S > 65535) return LGB200_ERR_SHAPE;
   // lightglue.py:564: keep = scores > (1 - width_confidence), evaluated in fp32
   const float keep_above = 1.0f - width_conf;
-  prune_compact_kernel<<<S, 1024, 0, lg_stream(stream)>>>(
+  prune_compact_kernel<<<dim3(PC_SPLIT, S), 1024, 0, lg_stream(stream)>>>(
       match, conf, thr, keep_above, Lp, lens, lens_active, x32_src, x32_dst,
       reinterpret_cast<const __nv_bfloat16*>(x16_src), reinterpret_cast<__nv_bfloat16*>(x16_dst),
       rot_src, rot_dst, reinterpret_cast<const uint32_t*>(rot16_src), reinterpret_cast<uint32_t*>(rot16_dst),
