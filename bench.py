@@ -280,30 +280,45 @@ def run_gpu_arm(args):
 
     # Public-API pipeline a user would write: a copy stream uploads step i+1's pinned host batch while the
     # compute stream runs model(step i); each step's inputs are uploaded inside the timed region and each
-    # step's matches/scores are read back to pinned host memory.
+    # step's matches/scores are read back to pinned host memory.  The device-side input buffers are two
+    # persistent sets filled alternately (allocated once, outside the timed region): the loop itself never goes
+    # through the caching allocator for them -- on some boxes of the pool (virtualised hosts) the earlier version,
+    # which let `.to(device)` allocate 270 MB of fresh device tensors on the copy stream every step, ran at 55-60 ms
+    # per step instead of 21 with identical kernels and an idle-link H2D rate of 55 GB/s.
     copy_stream = torch.cuda.Stream(device=dev)
     compute = torch.cuda.current_stream(dev)
+    dev_sets = [to_device(pinned, dev), to_device(pinned, dev)]
+    free_ev = [None, None]  # compute-stream event after the last forward that read set j
+    torch.cuda.synchronize()
 
-    def upload():
+    def copy_into(dst, src):
+        for k, v in src.items():
+            if isinstance(v, dict):
+                copy_into(dst[k], v)
+            elif isinstance(v, torch.Tensor):
+                dst[k].copy_(v, non_blocking=True)
+
+    def upload(j):
         with torch.cuda.stream(copy_stream):
-            d = to_device(pinned, dev, non_blocking=True)
+            if free_ev[j] is not None:
+                copy_stream.wait_event(free_ev[j])
+            copy_into(dev_sets[j], pinned)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        return d, ev
+        return ev
 
     def run_e2e(steps):
-        nxt = upload()
+        ev = upload(0)
         for i in range(steps):
-            d, ev = nxt
+            j = i & 1
             compute.wait_event(ev)
             if i + 1 < steps:
-                nxt = upload()
-            o = model(d)
+                ev = upload(j ^ 1)
+            o = model(dev_sets[j])
             for k in d2h_keys:
                 host_out[k].copy_(o[k], non_blocking=True)
-            # the uploaded buffers belong to the copy stream's allocator pool: keep them alive until used
-            for t in (d["keypoints0"], d["keypoints1"], d["descriptors0"], d["descriptors1"]):
-                t.record_stream(compute)
+            free_ev[j] = torch.cuda.Event()
+            free_ev[j].record(compute)
 
     run_e2e(2)
     barrier()
