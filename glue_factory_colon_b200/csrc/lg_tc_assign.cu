@@ -388,7 +388,8 @@ __global__ void assign_loss_finish_kernel(const float* __restrict__ z, int Lp, i
 
 // Dustbin row / column and zero padding of scores [B,R,C].  One WARP per row, 32 rows per CTA: without padding a
 // row's share is a single element (its dustbin), and the first version's one-CTA-per-row grid (R x B = 131 136
-// CTAs at 64 pairs) spent 78 us on block scheduling alone.
+// CTAs at 64 pairs) spent 78 us on block scheduling alone.  The dustbin ROW (C elements, each behind a load of z)
+// is dealt out 32 columns per CTA: written by one warp it is a chain of C/32 dependent-latency iterations (39 us).
 constexpr int AB_ROWS = 32;
 __global__ void __launch_bounds__(256) assign_border_kernel(const float* __restrict__ z, int Lp,
                                                             const int32_t* __restrict__ lens, int R, int C,
@@ -396,17 +397,19 @@ __global__ void __launch_bounds__(256) assign_border_kernel(const float* __restr
   const int b = blockIdx.y;
   const int n0 = lens ? lens[2 * b] : R - 1, n1 = lens ? lens[2 * b + 1] : C - 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r_end = min(R, (int)(blockIdx.x + 1) * AB_ROWS);
+  const int r_end = min(R - 1, (int)(blockIdx.x + 1) * AB_ROWS);  // rows [0, R-1); the dustbin row is handled below
   for (int r = blockIdx.x * AB_ROWS + warp; r < r_end; r += 8) {
     float* out = scores + ((size_t)b * R + r) * C;
     if (r < n0) {
       for (int c = n1 + lane; c < C - 1; c += 32) out[c] = 0.f;
       if (lane == 0) out[C - 1] = lg_logsigmoid(-z[(size_t)(2 * b) * Lp + r]);
-    } else if (r == R - 1) {
-      for (int c = lane; c < C; c += 32) out[c] = c < n1 ? lg_logsigmoid(-z[(size_t)(2 * b + 1) * Lp + c]) : 0.f;
     } else {
       for (int c = lane; c < C; c += 32) out[c] = 0.f;
     }
+  }
+  if (warp == 7) {  // this CTA's 32 columns of the dustbin row (the grid covers max(R, C) in steps of 32)
+    const int c = blockIdx.x * AB_ROWS + lane;
+    if (c < C) scores[((size_t)b * R + (R - 1)) * C + c] = c < n1 ? lg_logsigmoid(-z[(size_t)(2 * b + 1) * Lp + c]) : 0.f;
   }
 }
 
@@ -439,7 +442,7 @@ int lg_tc_assign_scores(const __nv_bfloat16* md, const float* z, const float* ls
   if (rc) return rc;
   cudaError_t e = cudaFuncSetAttribute(tc_assign_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AS_SMEM);
   if (e != cudaSuccess) return (int)e;
-  assign_border_kernel<<<dim3((R + AB_ROWS - 1) / AB_ROWS, B), 256, 0, st>>>(z, Lp, lens, R, C, scores);
+  assign_border_kernel<<<dim3(((R > C ? R : C) + AB_ROWS - 1) / AB_ROWS, B), 256, 0, st>>>(z, Lp, lens, R, C, scores);
   LG_LAUNCH_CHECK();
   unsigned long long* best0 = reinterpret_cast<unsigned long long*>(best_ws);
   unsigned long long* best1 = best0 ? best0 + (size_t)B * R : nullptr;
