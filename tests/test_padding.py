@@ -152,3 +152,27 @@ def test_random_padding_cannot_influence_valid_matches():
         assert (out["matches0"][b, n0:] == -1).all() and (out["matching_scores0"][b, n0:] == 0).all()
         torch.testing.assert_close(out["log_assignment"][b, :n0, :n1], ref["log_assignment"][0, :n0, :n1],
                                    atol=2e-4, rtol=1e-4)
+
+
+def test_counts_are_what_protects_valid_rows_from_the_padding():
+    """Oracle (CPU restatement of the reference, pinned to its goldens): the reference has no mask input
+    (lightglue.py:422-553), so reference-style random padding takes part in every attention and in both softmax
+    normalisers and changes the valid block of log_assignment; with the recorded counts the padded batch gives exactly
+    the un-padded result -- the semantics the B200 matcher implements with `num_keypoints0/1`."""
+    from helpers import build_model, oracle_batch
+
+    conf = {"filter_threshold": 0.1, "n_layers": 2}
+    model = build_model(conf, 5)
+    raw0, raw1 = _feat(90, 1, with_extras=False), _feat(70, 2, with_extras=False)
+    torch.manual_seed(3)
+    f0 = padding.pad_local_features(dict(raw0), 128, bounds=(0, 480))
+    f1 = padding.pad_local_features(dict(raw1), 128, bounds=(0, 480))
+    sizes = [[640, 480]]
+    data = padding.matcher_inputs([f0], [f1], sizes, sizes)
+    plain = padding.matcher_inputs([dict(raw0)], [dict(raw1)], sizes, sizes)
+    want = oracle_batch(model, conf, plain)[0]["log_assignment"]                       # [91, 71]
+    with_counts = oracle_batch(model, conf, data, num0=data["num_keypoints0"].tolist(),
+                               num1=data["num_keypoints1"].tolist())[0]["log_assignment"]
+    without = oracle_batch(model, conf, data)[0]["log_assignment"]                      # [129, 129], padding taken as real
+    assert torch.equal(with_counts, want)
+    assert (without[:90, :70] - want[:90, :70]).abs().max() > 1e-2
