@@ -36,6 +36,7 @@ __device__ __forceinline__ float lg_gelu_erf(float x) {
 
 // filter_matches: (value, index) packed so that a 64-bit max picks the largest value and, among equal
 // values, the LOWEST index (torch.max tie rule); NaN sorts above everything (torch.max propagates NaN).
+// Known deviation: -0.0 sorts below +0.0 here, torch.max treats them as equal (tests/test_filter_keys.py).
 __device__ __forceinline__ unsigned long long fm_pack(float v, int idx) {
   const unsigned u = __float_as_uint(v);
   unsigned key;
