@@ -3,6 +3,7 @@
 //                      zero dustbins (:72-74), from the fp32 similarity kernel of MatchAssignment (z = NULL mode)
 //   lgb200_nn_match  : find_nn (:15-31) in both directions (top-2 by value for the ratio test, distance threshold),
 //                      mutual_check (:34-43), matching_scores = (match > -1) (:75-76)
+//   lgb200_npair_loss: the N_pair loss (:85-109) on the similarity matrix, forward values
 // fp32 CUDA-core kernels (the baseline matcher is not on the headline path; its cost is the N x M write).
 #include "lg_internal.cuh"
 
@@ -95,7 +96,98 @@ __global__ void nn_mutual_kernel(const long long* __restrict__ nn0, const long l
   }
 }
 
+// ---- N_pair loss (nearest_neighbor_matcher.py:85-109), forward values ---------------------------------------------
+// scores = T * (2 - sqrt(clamp(2 (1 - sim), 1e-6)));  nll = -(sum a (prob0 + prob1)) / (2 num),  prob0 / prob1 = row /
+// column log-softmax of scores.  Three streaming passes over sim [B,N,M]: row LSE (warp per row), column LSE (32 columns
+// x 8 row groups per CTA, online max/sum merged through shared memory), then the ground-truth pass (warp per row ->
+// per-row partial sums, no atomics: bit-reproducible).
+__device__ __forceinline__ float npair_score(float sim, float T) {
+  return T * (2.f - sqrtf(fmaxf(2.f * (1.f - sim), 1e-6f)));
+}
+__device__ __forceinline__ void lse_push(float& mx, float& sm, float v) {
+  if (v > mx) { sm = sm * __expf(mx - v) + 1.f; mx = v; }
+  else sm += __expf(v - mx);
+}
+__device__ __forceinline__ void lse_merge(float& mx, float& sm, float mx2, float sm2) {
+  if (mx2 == -INFINITY) return;
+  if (mx2 > mx) { sm = sm * __expf(mx - mx2) + sm2; mx = mx2; }
+  else sm += sm2 * __expf(mx2 - mx);
+}
+
+__global__ void npair_rows_kernel(const float* __restrict__ sim, int N, int M, float T, float* __restrict__ lse_r) {
+  const int b = blockIdx.y, row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const float* p = sim + ((size_t)b * N + row) * M;
+  float mx = -INFINITY, sm = 0.f;
+  for (int c = lane; c < M; c += 32) lse_push(mx, sm, npair_score(p[c], T));
+  for (int o = 16; o; o >>= 1) {
+    const float mx2 = __shfl_xor_sync(0xffffffffu, mx, o), sm2 = __shfl_xor_sync(0xffffffffu, sm, o);
+    lse_merge(mx, sm, mx2, sm2);
+  }
+  if (lane == 0) lse_r[(size_t)b * N + row] = mx + logf(sm);
+}
+
+__global__ void npair_cols_kernel(const float* __restrict__ sim, int N, int M, float T, float* __restrict__ lse_c) {
+  __shared__ float smx[8][33], ssm[8][33];
+  const int b = blockIdx.y, cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
+  float mx = -INFINITY, sm = 0.f;
+  if (col < M) {
+    const float* p = sim + (size_t)b * N * M + col;
+    for (int r = ry; r < N; r += 8) lse_push(mx, sm, npair_score(p[(size_t)r * M], T));
+  }
+  smx[ry][cx] = mx;
+  ssm[ry][cx] = sm;
+  __syncthreads();
+  if (ry == 0 && col < M) {
+    for (int k = 1; k < 8; ++k) lse_merge(mx, sm, smx[k][cx], ssm[k][cx]);
+    lse_c[(size_t)b * M + col] = mx + logf(sm);
+  }
+}
+
+// row_sum[b,row] = sum_j a (2 score - lse_r[row] - lse_c[j]);  row_cnt[b,row] = sum_j a
+__global__ void npair_gt_kernel(const float* __restrict__ sim, const uint8_t* __restrict__ gt, int N, int M, float T,
+                                const float* __restrict__ lse_r, const float* __restrict__ lse_c,
+                                float* __restrict__ row_sum, float* __restrict__ row_cnt) {
+  const int b = blockIdx.y, row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const size_t off = ((size_t)b * N + row) * M;
+  const float lr = lse_r[(size_t)b * N + row];
+  float acc = 0.f, cnt = 0.f;
+  for (int c = lane; c < M; c += 32) {
+    if (gt[off + c]) {
+      acc += 2.f * npair_score(sim[off + c], T) - lr - lse_c[(size_t)b * M + c];
+      cnt += 1.f;
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if (lane == 0) {
+    row_sum[(size_t)b * N + row] = acc;
+    row_cnt[(size_t)b * N + row] = cnt;
+  }
+}
+
 }  // namespace
+
+extern "C" int lgb200_npair_loss(const float* similarity, const uint8_t* gt_assignment, int B, int N, int M,
+                                 float temperature, float* workspace, float* row_sum, float* row_cnt, void* stream) {
+  if (!similarity || !gt_assignment || !workspace || !row_sum || !row_cnt) return LGB200_ERR_NULL;
+  if (B <= 0 || N <= 0 || M <= 0 || B > 65535) return LGB200_ERR_SHAPE;
+  cudaStream_t st = lg_stream(stream);
+  float* lse_r = workspace;               // [B, N]
+  float* lse_c = workspace + (size_t)B * N;  // [B, M]
+  npair_rows_kernel<<<dim3((N + 7) / 8, B), 256, 0, st>>>(similarity, N, M, temperature, lse_r);
+  LG_LAUNCH_CHECK();
+  npair_cols_kernel<<<dim3((M + 31) / 32, B), 256, 0, st>>>(similarity, N, M, temperature, lse_c);
+  LG_LAUNCH_CHECK();
+  npair_gt_kernel<<<dim3((N + 7) / 8, B), 256, 0, st>>>(similarity, gt_assignment, N, M, temperature, lse_r, lse_c,
+                                                        row_sum, row_cnt);
+  LG_LAUNCH_CHECK();
+  return LGB200_OK;
+}
 
 extern "C" int lgb200_nn_scores(const float* d, const float* lse, int B, int Lp, const int32_t* lens, int R, int C,
                                 float* similarity, float* log_assignment, void* stream) {

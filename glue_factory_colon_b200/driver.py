@@ -166,8 +166,17 @@ class BatchedPairMatcher:
             h = torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory()
             h.copy_(out[k], non_blocking=True)
             host[k] = h
-        for t in (dev["keypoints0"], dev["keypoints1"], dev["descriptors0"], dev["descriptors1"]):
-            t.record_stream(compute)  # uploaded on the copy stream, consumed here
+        # every uploaded tensor (nested view dicts included: image_size, scales, oris are read by the compute-stream
+        # kernels without a copy) was allocated on the copy stream and is consumed on `compute`
+        def mark(obj):
+            if isinstance(obj, torch.Tensor):
+                if obj.is_cuda:
+                    obj.record_stream(compute)
+            elif isinstance(obj, dict):
+                for v in obj.values():
+                    mark(v)
+
+        mark(dev)
         done = torch.cuda.Event()
         done.record(compute)
         return _InFlight(list(idx), list(counts), host, done, out["log_assignment"] if self.return_log_assignment else None)

@@ -143,6 +143,9 @@ class LightGlue(nn.Module):
         # mode, no adaptive depth / width, no per-pair counts).  One pair at 2048 keypoints is ~90 launches of 5-20 us
         # each: issued from Python the forward is host-bound, replayed from a graph it is not.
         "cuda_graph": False,
+        # with cuda_graph: return the graph's own output buffers (valid until the next call) instead of copies --
+        # saves the 16.8 MB-per-pair copy of log_assignment at 2048 keypoints
+        "graph_static_outputs": False,
     }
 
     required_data_keys = ["keypoints0", "keypoints1", "descriptors0", "descriptors1"]
@@ -174,6 +177,7 @@ class LightGlue(nn.Module):
         # measurement hook (bench.py): a list to which the forward appends (start, end) CUDA events around every
         # self-attention launch, i.e. the dominant kernel timed inside the running step
         self._attn_events = None
+        self._warned_nograd = False
 
     # ---- reference-compatible helpers ------------------------------------------------
 
@@ -181,13 +185,30 @@ class LightGlue(nn.Module):
         t = 0.8 + 0.1 * np.exp(-4.0 * layer_index / self.conf.n_layers)
         return float(np.clip(t, 0, 1))
 
-    def _load_weights(self, weights) -> None:  # lightglue.py:375-401 (local files only: no network)
+    def _load_weights(self, weights) -> None:
+        """lightglue.py:375-401: a path, or a file under DATA_PATH (gluefactory.settings.DATA_PATH when the reference
+        is importable, else $GLUEFACTORY_DATA_PATH / $DATA_PATH); the release-URL branch needs a network and raises."""
         from pathlib import Path
 
-        if not Path(weights).exists():
-            raise FileNotFoundError(f"weights file {weights} not found (no download path in this build)")
-        sd = torch.load(str(weights), map_location="cpu")
-        for i in range(self.conf.n_layers):
+        cands = [Path(weights)]
+        try:
+            from gluefactory.settings import DATA_PATH  # type: ignore
+
+            cands.append(Path(DATA_PATH) / str(weights))
+        except Exception:
+            pass
+        for var in ("GLUEFACTORY_DATA_PATH", "DATA_PATH"):
+            if os.environ.get(var):
+                cands.append(Path(os.environ[var]) / str(weights))
+        path = next((c for c in cands if c.exists()), None)
+        if path is None:
+            raise FileNotFoundError(
+                f"weights '{weights}' not found (tried {', '.join(map(str, cands))}); this build has no download path "
+                f"for the official release files (lightglue.py:386-392)")
+        from .weights import strip_prefixes, unwrap_checkpoint
+
+        sd = dict(strip_prefixes(unwrap_checkpoint(torch.load(str(path), map_location="cpu", weights_only=True))))
+        for i in range(self.conf.n_layers):  # rename old state dict entries (lightglue.py:395-400)
             sd = {k.replace(f"self_attn.{i}", f"transformers.{i}.self_attn"): v for k, v in sd.items()}
             sd = {k.replace(f"cross_attn.{i}", f"transformers.{i}.cross_attn"): v for k, v in sd.items()}
         self.load_state_dict(sd, strict=False)
@@ -276,8 +297,12 @@ class LightGlue(nn.Module):
                                      ptr(col_arg), st), "loss_reduce")
         return rows[0].sum(1), rows[1].sum(1), rows[2], row_arg, col_arg
 
-    @torch.no_grad()
     def loss(self, pred, data):
+        self._warn_no_autograd()
+        with torch.no_grad():
+            return self._loss_nograd(pred, data)
+
+    def _loss_nograd(self, pred, data):
         """LightGlue.loss (lightglue.py:588-637) -> (losses, metrics) with the reference's keys, FORWARD VALUES ONLY:
         the B200 kernels have no backward pass, so the returned tensors carry no autograd graph (use them for
         validation, `do_evaluation` in the reference's train.py:100-170; optimisation needs the reference module).
@@ -369,10 +394,20 @@ class LightGlue(nn.Module):
             raise ValueError(f"precision must be fp32, bf16 or auto, got {p}")
         return BF16 if p == "bf16" else F32
 
+    def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() / .half(): parameters may be replaced
+        self._plist = None
+        return super()._apply(fn, *args, **kwargs)
+
     def _pack(self, prec: int, device) -> Dict:
-        key = (prec, str(device), tuple((p.data_ptr(), p._version) for p in self.parameters()))
+        # identity + version of every parameter; walking the module tree costs 0.3 ms per call (a third of a one-pair
+        # forward), the cached flat list 0.03 ms
+        plist = getattr(self, "_plist", None)
+        if plist is None:
+            plist = self._plist = list(self.parameters())
+        key = (prec, str(device), tuple((p.data_ptr(), p._version) for p in plist))
         if self._pack_key == key:
             return self._packed
+        # one pack is kept; captured CUDA graphs hold their own reference (see forward), so replacing it is safe
         wdt = torch.bfloat16 if prec == BF16 else torch.float32
 
         def W(t):
@@ -430,8 +465,34 @@ class LightGlue(nn.Module):
 
     _GRAPH_INPUTS = ("keypoints0", "keypoints1", "descriptors0", "descriptors1", "scales0", "scales1", "oris0", "oris1")
 
-    @torch.no_grad()
+    def _pinned_snapshots(self, rows: int, cols: int) -> torch.Tensor:
+        """Pinned int32 scratch for the adaptive path's device -> host reads (allocated once per shape: a
+        cudaHostAlloc per forward would cost more than the forward)."""
+        buf = getattr(self, "_snap_buf", None)
+        if buf is None or buf.shape[0] < rows or buf.shape[1] < cols:
+            buf = self._snap_buf = torch.zeros(max(rows, 16), max(cols, 64), dtype=torch.int32).pin_memory()
+        return buf[:rows, :cols]
+
+    def _warn_no_autograd(self) -> None:
+        """The kernels have no backward pass: a training loop that expects gradients (train.py of the reference selects
+        the matcher by name and calls loss.backward()) must be told, once, instead of silently training nothing."""
+        if self._warned_nograd or not (self.training and torch.is_grad_enabled()):
+            return
+        if any(p.requires_grad for p in self.parameters()):
+            import warnings
+
+            warnings.warn(
+                "glue_factory_colon_b200.LightGlue computes forward values only: outputs and losses carry no autograd "
+                "graph (conf.checkpointed is ignored).  Use it for inference / validation; optimisation needs the "
+                "reference module.", RuntimeWarning, stacklevel=3)
+            self._warned_nograd = True
+
     def forward(self, data: dict) -> dict:
+        self._warn_no_autograd()
+        with torch.no_grad():
+            return self._forward_nograd(data)
+
+    def _forward_nograd(self, data: dict) -> dict:
         for key in self.required_data_keys:
             assert key in data, f"Missing key {key} in data"
         conf = self.conf
@@ -468,11 +529,15 @@ class LightGlue(nn.Module):
                 out = self._forward_impl(as_data())
             if len(self._graphs) >= 8:  # a handful of signatures at most; drop the oldest
                 self._graphs.pop(next(iter(self._graphs)))
-            entry = self._graphs[sig] = (graph, static, out)
-        graph, static, out = entry
+            # the captured launches carry raw device pointers (and TMA tensor maps) into the weight pack: the entry
+            # keeps the pack alive for as long as the graph can be replayed (a precision switch replaces self._packed)
+            entry = self._graphs[sig] = (graph, static, out, self._packed)
+        graph, static, out, _ = entry
         for k, t in ins.items():
             static[k].copy_(t, non_blocking=True)
         graph.replay()
+        if conf.get("graph_static_outputs", False):  # caller consumes the results before the next call: no copies
+            return dict(out)
         return {k: v.clone() for k, v in out.items()}  # the graph's output buffers are overwritten by the next replay
 
     def _forward_impl(self, data: dict) -> dict:
@@ -617,8 +682,17 @@ class LightGlue(nn.Module):
         if adaptive:
             conf_buf = torch.zeros(T, **f32)
             msig = torch.zeros(T, **f32)
-            done = torch.zeros(B, **i32)
+            # device state read by the host: [done (B) | lens (S)], snapshotted into pinned memory without blocking
+            state = torch.zeros(B + S, **i32)
+            done = state[:B]
+            if lens.data_ptr() != state[B:].data_ptr():
+                state[B:].copy_(lens)
+                lens = state[B:]
+                lens_act = lens.clone()
             total = torch.from_numpy(lens_host.sum(1).astype(np.int32)).to(dev)
+            snaps = self._pinned_snapshots(L + 1, B + S)
+            snap_ev = []
+            polled = 0
         if do_prune:
             ind = torch.arange(Lp, **i32).repeat(S, 1).contiguous()
             prune_cnt = torch.ones(S, Lp, **i32)
@@ -672,10 +746,19 @@ class LightGlue(nn.Module):
                 rowdot(x, (tk["w"], tk["b"]), la, 1, conf_buf)
                 check(lib.lgb200_exit_check(ptr(conf_buf), B, Lp, ptr(lens), ptr(total), thr,
                                             float(conf.depth_confidence), i, ptr(done), ptr(lens_act), st), "exit_check")
-                done_h = done.cpu().numpy()  # one host read per layer (the reference syncs 2-3 times)
-                newly = (done_h == i + 1)
-                exit_layer[newly] = i
-                if (done_h != 0).all():
+                # No host round trip here (the reference syncs 2-3 times per layer, lightglue.py:501-521): the kernels
+                # of later layers skip finished pairs by themselves (lens_active == 0), so the host only needs to
+                # learn about the exit EVENTUALLY, to stop launching.  The flags are copied to pinned memory behind
+                # the check and older snapshots are polled without blocking.
+                snaps[i, :B].copy_(done, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                snap_ev.append(ev)
+                stop = False
+                while polled < len(snap_ev) and snap_ev[polled].query():
+                    stop = stop or bool((snaps[polled, :B] != 0).all())
+                    polled += 1
+                if stop:
                     break
             if do_prune:  # lightglue.py:506-521
                 ma = W["assign"][i]
@@ -692,6 +775,14 @@ class LightGlue(nn.Module):
                 rot16, rot16_b = rot16_b, rot16
                 ind, ind_b = ind_b, ind
 
+        if adaptive:
+            # the one blocking read of an adaptive forward: exit flags and (pruned) counts together
+            snaps[L].copy_(state, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            st_h = snaps[L].numpy()
+            done_h = st_h[:B]
+            exit_layer = np.where(done_h != 0, done_h - 1, L - 1).astype(np.int64)
+            lens_final = st_h[B:].reshape(B, 2).copy()
         # ---- log assignment (lightglue.py:523-524) ----
         md = msg  # reuse: [T,256] in the activation dtype
         z = torch.zeros(T, **f32)
@@ -706,8 +797,7 @@ class LightGlue(nn.Module):
             linear(EPI_ROWMAJOR, x, a["fp_w"], a["fp_b"], 256, 256, scale=(0.25, 1.0, 1.0), out=md, lens_=lens_g)
             rowdot(x, (a["m_w"], a["m_b"]), lens_g, 0, z)
             check(lib.lgb200_assign_lse(prec, ptr(md), S, Lp, ptr(lens_g), ptr(lse), st), "assign_lse")
-        if do_prune:
-            lens_final = lens.cpu().numpy().reshape(B, 2)  # pruned shape is data dependent (lightglue.py:285 note)
+        if do_prune:  # pruned shape is data dependent (lightglue.py:285 note)
             R, C = int(lens_final[:, 0].max()) + 1, int(lens_final[:, 1].max()) + 1
         else:
             R, C = m + 1, n + 1

@@ -84,9 +84,36 @@ class NearestNeighborMatcher(nn.Module):
                 "similarity": sim, "log_assignment": la}
 
     def loss(self, pred, data):
-        # the N_pair loss (:85-109) needs autograd through the similarity; TwoViewPipeline.loss treats
-        # NotImplementedError as "skip" (two_view_pipeline.py:417-429)
-        raise NotImplementedError
+        """nearest_neighbor_matcher.py:85-109, FORWARD VALUES (no autograd graph: the temperature is not trained here).
+        `N_pair`: three streaming passes over the similarity matrix in `lgb200_npair_loss`; metrics as the
+        reference's matcher_metrics in eval mode.  Any other conf.loss raises NotImplementedError, which
+        TwoViewPipeline.loss treats as "skip" (two_view_pipeline.py:417-429)."""
+        if self.conf.loss != "N_pair":
+            raise NotImplementedError
+        with torch.no_grad():
+            sim = pred["similarity"]
+            if not sim.is_cuda:
+                raise _abi.LightGlueB200Error("glue_factory_colon_b200.NearestNeighborMatcher.loss runs on CUDA tensors only")
+            lib = _abi.load()
+            sim = sim.to(torch.float32).contiguous()
+            B, N, M = sim.shape
+            dev = sim.device
+            gt = data["gt_assignment"].to(dev).to(torch.bool).contiguous()
+            assert gt.shape == (B, N, M), "gt_assignment must be [B, N, M]"
+            f32 = dict(device=dev, dtype=torch.float32)
+            rows = torch.empty(2, B, N, **f32)
+            ws = torch.empty(B * (N + M), **f32)
+            check(lib.lgb200_npair_loss(ptr(sim), ptr(gt), B, N, M, float(self.temperature), ptr(ws), ptr(rows[0]),
+                                        ptr(rows[1]), torch.cuda.current_stream(dev).cuda_stream), "npair_loss")
+            num = rows[1].sum(1).clamp(min=1.0)
+            nll = -(rows[0].sum(1) / num) / 2
+            losses = {"n_pair_nll": nll, "total": nll, "num_matchable": num,
+                      "n_pair_temperature": self.temperature.detach()[None]}
+            if self.training:
+                return losses, {}
+            from .lightglue import LightGlue
+
+            return losses, LightGlue._matcher_metrics(pred, {"gt_matches0": data["gt_matches0"].to(dev)})
 
 
 __main_model__ = NearestNeighborMatcher

@@ -194,6 +194,16 @@ int lgb200_nn_match(const float* similarity, int B, int N, int M, const int32_t*
                     float distance_thresh, int mutual, int64_t* workspace, int64_t* m0, int64_t* m1,
                     float* ms0, float* ms1, void* stream);
 
+/* N_pair loss of the nearest-neighbour matcher, forward values.  Replaces
+ * NearestNeighborMatcher.loss, nearest_neighbor_matcher.py:85-109:
+ * scores = T (2 - sqrt(clamp(2 (1 - sim), 1e-6))), prob0 / prob1 = row / column
+ * log-softmax of scores.  similarity [B,N,M] fp32, gt_assignment [B,N,M] bytes
+ * (non-zero = match).  Outputs per row: row_sum[b,i] = sum_j a (prob0 + prob1),
+ * row_cnt[b,i] = sum_j a; the caller forms nll = -sum_i row_sum / (2 max(sum_i row_cnt, 1)).
+ * workspace: B * (N + M) floats. */
+int lgb200_npair_loss(const float* similarity, const uint8_t* gt_assignment, int B, int N, int M,
+                      float temperature, float* workspace, float* row_sum, float* row_cnt, void* stream);
+
 /* ---- loss-side reductions (forward values only) -------------------
  * Replaces the dense [B,R,C] reductions behind LightGlue.loss, lightglue.py:588-637:
  *   NLLLoss / weight_loss, gluefactory/models/utils/losses.py:6-26 -- row_pos[b,i] = sum_j la[b,i,j] *

@@ -35,6 +35,22 @@ def main():
                                                            "matching_scores1", "similarity", "log_assignment")}))
         print(c["name"], "valid matches:", int((pred["matches0"] > -1).sum()), tuple(pred["similarity"].shape))
     torch.save(out, ROOT / "tests" / "golden" / "nn_matcher.pt")
+    # N_pair loss (nearest_neighbor_matcher.py:85-109): forward values of the unmodified reference, eval and train mode
+    loss_cases = []
+    for name, temp, train, kw in (("eval", 1.0, False, dict(B=2, n0=140, n1=111, seed=24, with_gt=True)),
+                                  ("train_T3", 3.0, True, dict(B=1, n0=90, n1=130, seed=25, dim=128, with_gt=True))):
+        model = get_model("matchers.nearest_neighbor_matcher")({"loss": "N_pair"})
+        model.train(train)
+        with torch.no_grad():
+            model.temperature.fill_(temp)
+            data = make_pairs(**kw)
+            pred = model(data)
+            losses, metrics = model.loss(pred, data)
+        loss_cases.append(dict(name=name, temperature=temp, train=train, data_kwargs=kw,
+                               losses={k: v.clone() for k, v in losses.items()},
+                               metrics={k: v.clone() for k, v in metrics.items()}))
+        print("npair", name, {k: [round(float(x), 5) for x in v.reshape(-1)] for k, v in losses.items()})
+    torch.save(loss_cases, ROOT / "tests" / "golden" / "nn_npair_loss.pt")
 
 
 if __name__ == "__main__":

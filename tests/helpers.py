@@ -50,3 +50,40 @@ def assert_matches_equal(got_m, got_s, exp_m, exp_s, scores_row_gap=None, what="
     assert not bad.any(), f"{what}: {int(bad.sum())} index mismatches"
     same = got_m == exp_m
     torch.testing.assert_close(got_s[same], exp_s[same], atol=2e-4, rtol=1e-3)
+
+
+# ---- BASELINE config 1 fixture (oracle/make_golden_c1.py) -------------------------------------------------------
+
+
+def sharp_assignment_overrides(layer=8, scale=2.0, bias=4.0):
+    """Weights under which a random-init LightGlue makes confident matches: the exit layer's MatchAssignment gets
+    final_proj = scale * I and a positive matchability bias, so the similarity of two tokens is (scale/4)^2 times the
+    dot product of their layer outputs (which still carry the input descriptors through the residual stream).  With
+    the synthetic pairs of synthetic.make_pairs (60 % true correspondences) several hundred matches then pass
+    filter_threshold 0.1 -- without it none does and every `matches0 == oracle` check would be vacuous."""
+    return {
+        f"log_assignment.{layer}.final_proj.weight": scale * torch.eye(256),
+        f"log_assignment.{layer}.final_proj.bias": torch.zeros(256),
+        f"log_assignment.{layer}.matchability.bias": torch.tensor([bias]),
+    }
+
+
+def load_c1_fixture(path):
+    """-> (fx, model, data): the boat1/boat2 pair exactly as oracle/make_golden_c1.py fed it to the reference."""
+    fx = torch.load(path, weights_only=False)
+    model = build_model(fx["conf"], fx["seed"], sharp_assignment_overrides())
+    assert abs(fingerprint(model.state_dict()) - fx["fingerprint"]) < 1e-6 * fx["fingerprint"]
+
+    def lift(sift_u8):  # same arithmetic as make_golden_c1.lift_descriptors
+        g = torch.Generator().manual_seed(22)
+        P = torch.randn(128, 256, generator=g) / 128 ** 0.5
+        d = torch.nn.functional.normalize(sift_u8.float(), dim=-1)
+        return torch.nn.functional.normalize(d @ P, dim=-1)
+
+    data = {
+        "keypoints0": fx["keypoints0"][None], "keypoints1": fx["keypoints1"][None],
+        "descriptors0": lift(fx["sift0"])[None], "descriptors1": lift(fx["sift1"])[None],
+        "view0": {"image_size": torch.tensor([fx["image_size0"]])},
+        "view1": {"image_size": torch.tensor([fx["image_size1"]])},
+    }
+    return fx, model, data

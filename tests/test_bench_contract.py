@@ -1,4 +1,4 @@
-"""bench.py's driver contract on the CPU: the reference arm (`--impl reference`, the CPU port of the reference timed on
+"""bench.py's driver contract on the CPU: the reference arm (`--impl reference`, the reference's CPU path timed on
 the host cores) prints one JSON line with the agreed keys; ranks other than 0 do no work; the GPU arm has no CPU path."""
 import json
 import os
@@ -26,7 +26,17 @@ def test_reference_arm_prints_the_contract_line():
     assert d["value"] > 0 and abs(d["value"] - 1e3 / d["ms_per_step"]) < 1e-6 * d["value"]  # one pair per step
     assert "workload" in d["config"] and "model" not in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "2048" in cb["sample"]
+    # "reference": the unmodified module from git-ignored baseline/_ref when that install is present, else the port
+    have_ref = (ROOT / "baseline" / "_ref" / "gluefactory").exists()
+    assert cb["kind"] == ("reference" if have_ref else "port")
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and "2048" in cb["sample"]
+    # both arms print the same `config` object (the driver compares them)
+    import argparse
+    sys.path.insert(0, str(ROOT))
+    import bench
+
+    ns = argparse.Namespace(workload="c2", pairs=bench.PAIRS_PER_GPU, kpts=bench.KPTS, precision="bf16")
+    assert d["config"] == bench.workload_config(ns, 1)
     assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
 

@@ -1,0 +1,246 @@
+"""GPU parity at the shapes BASELINE.json's configs name (run with -m gpu on a B200): the CUDA path against the CPU
+oracle (itself pinned to the unmodified reference, tests/test_oracle.py) on the same seeded inputs.
+
+  C1  boat1/boat2, 1024 real SIFT keypoints, official conf (filter_threshold 0.1): committed golden of the reference
+  C2  2048 keypoints: fp32 within 1e-3 (and 1024), bf16 envelope + matches0 agreement at filter_threshold 0.1
+  C3  4 pairs with counts in 1024..4096 padded to 4096: valid block vs per-pair un-padded oracle
+  C4  adaptive depth / width at 2048 keypoints in bf16: prune layers, exit layer and matches vs the oracle
+  C5  one pair at 8192 keypoints (largest sweep point), bf16
+
+Tolerances (stated where asserted):
+  fp32: |d log_assignment| < 1e-3 absolute (north_star); indices bit-exact except where the oracle's own top-2 gap is
+        below 1e-4 (compare_to_oracle's tie-gap rule).
+  bf16, random-init weights (|log_assignment| <= 26): mean |d| < 0.03, max |d| < 0.2, row-argmax agreement > 97 %
+        (the reference's own bf16-autocast run is at 0.043 / 0.26 / 91.9 %).
+  bf16, sharp assignment (|log_assignment| up to ~200, helpers.sharp_assignment_overrides): errors scale with the
+        magnitude of the logits, so the matrix is checked relative to it (|d| < 0.02 |la| + 0.25) and the decisive
+        check is on the result: matches0 / matches1 equal to the oracle's for >= 98 % of the keypoints.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import build_model, load_c1_fixture, make_pairs, oracle_batch, sharp_assignment_overrides
+from test_gpu_parity import compare_to_oracle
+from glue_factory_colon_b200 import _abi
+from glue_factory_colon_b200._abi import ptr
+from glue_factory_colon_b200.synthetic import to_device
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _valid_block(la, n0, n1):
+    R, C = la.shape
+    return torch.cat([torch.cat([la[:n0, :n1], la[:n0, C - 1:C]], 1),
+                      torch.cat([la[R - 1:R, :n1], la[R - 1:R, C - 1:C]], 1)], 0)
+
+
+def _bf16_report(tag, out, res, rel=False, min_equal=0.98):
+    """bf16 run vs fp32 oracle, per pair: matrix error, row arg-max agreement, match agreement.  Prints the measured
+    values (pytest -s / the GPU log) and asserts the envelope stated in the module docstring."""
+    for b, r in enumerate(res):
+        la_o = r["log_assignment"]
+        n0, n1 = la_o.shape[0] - 1, la_o.shape[1] - 1
+        la = _valid_block(out["log_assignment"][b].float().cpu(), n0, n1)
+        d = (la - la_o).abs()
+        agree = (la[:n0, :n1].argmax(1) == la_o[:n0, :n1].argmax(1)).float().mean().item()
+        m0, m1 = out["matches0"][b, :n0].cpu(), out["matches1"][b, :n1].cpu()
+        eq0 = (m0 == r["matches0"]).float().mean().item()
+        eq1 = (m1 == r["matches1"]).float().mean().item()
+        nv = int((r["matches0"] > -1).sum())
+        print(f"[{tag}] pair {b} ({n0}x{n1}): mean|d| {d.mean():.4f} max|d| {d.max():.3f} max|la| {la_o.abs().max():.1f} "
+              f"row-argmax {agree:.4f} matches0== {eq0:.4f} matches1== {eq1:.4f} oracle-valid {nv}")
+        if rel:
+            assert (d <= 0.02 * la_o.abs() + 0.25).all(), f"{tag} pair {b}: max excess {(d - 0.02 * la_o.abs()).max():.3f}"
+        else:
+            assert d.mean() < 0.03 and d.max() < 0.2, f"{tag} pair {b}: mean {d.mean():.4f} max {d.max():.3f}"
+            assert agree > 0.97, f"{tag} pair {b}: row-argmax agreement {agree:.4f}"
+        assert eq0 >= min_equal and eq1 >= min_equal, f"{tag} pair {b}: matches equal {eq0:.4f} / {eq1:.4f}"
+        assert (out["matches0"][b, n0:] == -1).all() and (out["matches1"][b, n1:] == -1).all()
+
+
+# ------------------------------------------------------------------ C1
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_c1_boat_pair_against_reference_golden(prec, golden_dir):
+    fx, model, data = load_c1_fixture(golden_dir / "c1_boat.pt")
+    model.conf.precision = prec
+    out = model.to(DEV)(to_device(data, DEV))
+    la = out["log_assignment"][0].float().cpu()
+    assert la.shape == (1025, 1025)
+    res = oracle_batch(model.cpu(), fx["conf"], data)
+    if prec == "fp32":
+        for got, exp in ((la[::4, ::4], fx["la_sub"]), (la[:, -1], fx["la_dust_col"]), (la[-1, :], fx["la_dust_row"])):
+            assert (got - exp).abs().max() < 1e-3  # vs the unmodified reference's own output
+        compare_to_oracle(out, res, 1024, 1024, fp32=True)
+        mism = (out["matches0"][0].cpu() != fx["matches0"]).sum()
+        assert mism <= 2, f"{int(mism)} of 1024 matches differ from the reference"
+    else:
+        _bf16_report("C1 bf16", out, res, rel=True)
+        eq = (out["matches0"][0].cpu() == fx["matches0"]).float().mean()
+        assert eq >= 0.98, f"matches0 equal to the reference's: {eq:.4f}"
+
+
+# ------------------------------------------------------------------ C2
+
+
+@pytest.mark.parametrize("n", [1024, 2048])
+@pytest.mark.parametrize("sharp", [False, True])
+def test_c2_fp32_against_oracle(n, sharp):
+    conf = {"filter_threshold": 0.1 if sharp else 0.0, "precision": "fp32"}
+    model = build_model(conf, 0, sharp_assignment_overrides() if sharp else None).to(DEV)
+    data = make_pairs(B=1, n0=n, n1=n, seed=51)
+    out = model(to_device(data, DEV))
+    res = oracle_batch(model.cpu(), conf, data)
+    assert int((res[0]["matches0"] > -1).sum()) > (n // 4 if sharp else 0)
+    compare_to_oracle(out, res, n, n, fp32=True)
+
+
+def test_c2_bf16_random_init_against_oracle():
+    conf = {"filter_threshold": 0.0, "precision": "bf16"}
+    model = build_model(conf, 0).to(DEV)
+    data = make_pairs(B=2, n0=2048, n1=2048, seed=51)
+    out = model(to_device(data, DEV))
+    res = oracle_batch(model.cpu(), conf, data)
+    # filter_threshold 0 keeps every mutual arg-max, including near-ties of a flat (random-init) matrix
+    _bf16_report("C2 bf16 random-init", out, res, rel=False, min_equal=0.90)
+
+
+def test_c2_bf16_matches_at_threshold_against_oracle():
+    conf = {"filter_threshold": 0.1, "precision": "bf16"}
+    model = build_model(conf, 0, sharp_assignment_overrides()).to(DEV)
+    data = make_pairs(B=2, n0=2048, n1=2048, seed=51)
+    out = model(to_device(data, DEV))
+    res = oracle_batch(model.cpu(), conf, data)
+    assert all(int((r["matches0"] > -1).sum()) > 700 for r in res)
+    _bf16_report("C2 bf16 th=0.1", out, res, rel=True, min_equal=0.98)
+
+
+# ------------------------------------------------------------------ C3
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_c3_ragged_4096_against_oracle(prec):
+    conf = {"filter_threshold": 0.1, "precision": prec}
+    model = build_model(conf, 0, sharp_assignment_overrides()).to(DEV)
+    g = torch.Generator().manual_seed(3)
+    num0 = torch.randint(1024, 4097, (4,), generator=g).tolist()
+    num1 = torch.randint(1024, 4097, (4,), generator=g).tolist()
+    num0[0], num1[1] = 4096, 4096  # one side at the padded size
+    data = make_pairs(B=4, n0=4096, n1=4096, seed=300, image_size=(512.0, 512.0))
+    d = to_device(data, DEV)
+    d["num_keypoints0"], d["num_keypoints1"] = torch.tensor(num0), torch.tensor(num1)
+    out = model(d)
+    assert out["log_assignment"].shape == (4, 4097, 4097)
+    res = oracle_batch(model.cpu(), conf, data, num0=num0, num1=num1)
+    if prec == "fp32":
+        compare_to_oracle(out, res, 4096, 4096, fp32=True)
+    else:
+        _bf16_report("C3 bf16", out, res, rel=True, min_equal=0.98)
+
+
+# ------------------------------------------------------------------ C4
+
+
+def _adaptive_model(prec, sharp_layer):
+    ov = {}
+    for i in range(8):
+        ov[f"token_confidence.{i}.token.0.bias"] = torch.tensor([3.0 if i >= 4 else -3.0])
+        ov[f"log_assignment.{i}.matchability.bias"] = torch.tensor([-4.5 if i % 2 == 0 else 0.0])
+    ov.update({k: v for k, v in sharp_assignment_overrides(sharp_layer, bias=0.0).items() if "matchability" not in k})
+    conf = {"depth_confidence": 0.95, "width_confidence": 0.99, "filter_threshold": 0.1, "precision": prec}
+    return conf, build_model(conf, 6, ov)
+
+
+@pytest.mark.parametrize("B,n", [(1, 2048), (2, 1024)])
+def test_c4_adaptive_bf16_against_oracle(B, n):
+    """Early exit + point pruning on the bf16 data path (x16 / rot16 ping-pong buffers): the layer at which every point
+    was pruned, the exit layer and the matches, against the fp32 oracle.  bf16 rounding may flip the keep / confident
+    decision of a point whose sigmoid lies within ~1e-2 of a threshold: agreement is asserted as a rate."""
+    probe_conf, probe = _adaptive_model("fp32", 8)
+    data = make_pairs(B=B, n0=n, n1=n, seed=400)
+    exit_layers = [r["exit_layer"] for r in oracle_batch(probe, probe_conf, data)]
+    assert len(set(exit_layers)) == 1 and 0 < exit_layers[0] < 8, exit_layers  # the biases force an early exit
+    conf, model = _adaptive_model("bf16", exit_layers[0])  # make the exit layer's assignment sharp
+    res = oracle_batch(model, conf, data)
+    out = model.to(DEV)(to_device(data, DEV))
+    for b, r in enumerate(res):
+        assert r["exit_layer"] == exit_layers[0]
+        p0, p1 = out["prune0"][b].cpu(), out["prune1"][b].cpu()
+        assert p0.dtype == torch.int64
+        assert int(p0.max()) == int(r["prune0"].max()) == r["exit_layer"] + 1, "exit layer differs"
+        pe0 = (p0 == r["prune0"]).float().mean().item()
+        pe1 = (p1 == r["prune1"]).float().mean().item()
+        m0, m1 = out["matches0"][b].cpu(), out["matches1"][b].cpu()
+        eq0, eq1 = (m0 == r["matches0"]).float().mean().item(), (m1 == r["matches1"]).float().mean().item()
+        k0, k1 = r["log_assignment"].shape[0] - 1, r["log_assignment"].shape[1] - 1
+        print(f"[C4 bf16] pair {b}: exit {r['exit_layer']} kept {k0}/{k1} of {n} prune0== {pe0:.4f} prune1== {pe1:.4f} "
+              f"matches0== {eq0:.4f} matches1== {eq1:.4f} oracle-valid {int((r['matches0'] > -1).sum())}")
+        assert 0 < k0 < n and int((r["matches0"] > -1).sum()) > 50  # pruning and matching both happened
+        assert pe0 >= 0.99 and pe1 >= 0.99, "prune layers differ from the oracle"
+        assert eq0 >= 0.98 and eq1 >= 0.98, "matches differ from the oracle"
+    la = out["log_assignment"]
+    assert la.isfinite().all()
+
+
+@pytest.mark.parametrize("bf", [False, True])
+def test_prune_compact_kernel_against_torch_gather(bf):
+    """lgb200_prune_compact on its own (lightglue.py:506-521, 560-567): keep mask -> stable compaction of the residual
+    rows, rotary rows and index rows, lens update, prune counter -- bit-exact against torch indexing, on the fp32
+    buffers and on the bf16 / packed-fp16 buffers the throughput path uses."""
+    lib = _abi.load()
+    S, Lp = 6, 384
+    g = torch.Generator(device=DEV).manual_seed(9)
+    lens_h = [384, 300, 129, 1, 0, 257]
+    lens = torch.tensor(lens_h, device=DEV, dtype=torch.int32)
+    lens_act = lens.clone()
+    lens_act[5] = 0  # a sequence whose pair has already exited: passed through, not pruned
+    match = torch.rand(S, Lp, device=DEV, generator=g)
+    conf = torch.rand(S, Lp, device=DEV, generator=g)
+    thr, width = 0.85, 0.6  # keep iff match > 0.4 or conf <= 0.85
+    xdt = torch.bfloat16 if bf else torch.float32
+    x = torch.randn(S * Lp, 256, device=DEV, generator=g).to(xdt)
+    rot = torch.randint(-2**31, 2**31 - 1, (S * Lp, 32), device=DEV, generator=g, dtype=torch.int64).to(torch.int32) if bf \
+        else torch.randn(S * Lp, 64, device=DEV, generator=g)
+    ind = torch.arange(Lp, device=DEV, dtype=torch.int32).repeat(S, 1).contiguous()
+    cnt = torch.ones(S, Lp, device=DEV, dtype=torch.int32)
+    x_d, rot_d, ind_d = torch.zeros_like(x), torch.zeros_like(rot), torch.zeros_like(ind)
+    args32 = (ptr(x), ptr(x_d), None, None, ptr(rot), ptr(rot_d), None, None)
+    args16 = (None, None, ptr(x), ptr(x_d), None, None, ptr(rot), ptr(rot_d))
+    rc = lib.lgb200_prune_compact(ptr(match), ptr(conf), thr, width, S, Lp, ptr(lens), ptr(lens_act),
+                                  *(args16 if bf else args32), ptr(ind), ptr(ind_d), ptr(cnt),
+                                  torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    xv, xdv = x.view(S, Lp, 256), x_d.view(S, Lp, 256)
+    rv, rdv = rot.view(S, Lp, -1), rot_d.view(S, Lp, -1)
+    for s in range(S):
+        n = lens_h[s]
+        if s == 5:
+            keep = torch.ones(n, dtype=torch.bool, device=DEV)
+        else:
+            keep = (match[s, :n] > 1 - width) | (conf[s, :n] <= thr)
+        k = int(keep.sum())
+        assert int(lens[s]) == k, (s, int(lens[s]), k)
+        sel = keep.nonzero()[:, 0]
+        assert torch.equal(xdv[s, :k], xv[s, sel]) and torch.equal(rdv[s, :k], rv[s, sel])
+        assert torch.equal(ind_d[s, :k].long(), sel)
+        exp_cnt = torch.ones(Lp, dtype=torch.int32, device=DEV)
+        if s != 5:
+            exp_cnt[sel] += 1
+            assert torch.equal(cnt[s], exp_cnt)
+
+
+# ------------------------------------------------------------------ C5
+
+
+def test_c5_one_pair_8192_bf16_against_oracle():
+    conf = {"filter_threshold": 0.1, "precision": "bf16"}
+    model = build_model(conf, 0, sharp_assignment_overrides()).to(DEV)
+    data = make_pairs(B=1, n0=8192, n1=8192, seed=500)
+    out = model(to_device(data, DEV))
+    assert out["log_assignment"].shape == (1, 8193, 8193)
+    res = oracle_batch(model.cpu(), conf, data)
+    _bf16_report("C5 bf16 8192", out, res, rel=True, min_equal=0.98)

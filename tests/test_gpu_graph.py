@@ -38,3 +38,30 @@ def test_graph_replay_equals_eager(precision):
     # adaptive / training / per-pair counts fall back to eager launches
     d3 = dict(d1, num_keypoints0=torch.tensor([250]), num_keypoints1=torch.tensor([260]))
     assert torch.equal(graphed(d3)["matches0"], eager(d3)["matches0"])
+
+
+def test_graph_survives_precision_switches():
+    """A captured graph bakes in device pointers into the packed weights.  Switching the precision replaces the
+    module's pack; switching back re-creates an identical signature and must replay a graph whose weights are still
+    alive (the graph entry owns them), not freed memory."""
+    torch.manual_seed(8)
+    model = LightGlue({"precision": "fp32", "filter_threshold": 0.1, "cuda_graph": True}).eval().to(DEV)
+    eager = LightGlue({"precision": "fp32", "filter_threshold": 0.1}).eval().to(DEV)
+    eager.load_state_dict(model.state_dict())
+    data = make_pairs(1, 300, 260, seed=47, device=DEV)
+    want = {}
+    for prec in ("fp32", "bf16"):
+        eager.conf.precision = prec
+        want[prec] = eager(data)["log_assignment"].clone()
+    for rnd, prec in enumerate(["fp32", "bf16", "fp32", "bf16", "fp32"]):
+        model.conf.precision = prec
+        # churn the allocator between switches so that a freed pack would be reused by something else
+        junk = [torch.randn(1 << 20, device=DEV) for _ in range(8)]
+        got = model(data)["log_assignment"]
+        assert torch.equal(got, want[prec]), f"round {rnd} ({prec})"
+        del junk
+    assert len(model._graphs) == 2  # one capture per precision, reused after the switches
+    # static outputs: no copies, valid until the next call
+    model.conf.graph_static_outputs = True
+    o = model(data)
+    assert torch.equal(o["log_assignment"], want["fp32"])

@@ -31,8 +31,8 @@ def test_plugin_discovery_and_conf():
     m = mod.__main_model__({"ratio_thresh": 0.9, "name": "whatever", "loss": "N_pair"})
     assert m.conf.ratio_thresh == 0.9 and m.conf.mutual_check is True
     assert [k for k, _ in m.named_parameters()] == ["temperature"]
-    with pytest.raises(NotImplementedError):
-        m.loss({}, {})
+    with pytest.raises(NotImplementedError):  # any loss other than N_pair: skipped by TwoViewPipeline.loss
+        mod.__main_model__({})  .loss({}, {})
     with pytest.raises(Exception):  # no CPU path
         m(make_pairs(1, 8, 8))
 
@@ -79,3 +79,35 @@ def test_cuda_path_ties_counts_and_empty_side():
     # empty side (find_nn with no candidates)
     e = NearestNeighborMatcher({}).cuda()({"descriptors0": torch.zeros(1, 0, 256).cuda(), "descriptors1": torch.randn(1, 5, 256).cuda()})
     assert e["matches1"].tolist() == [[-1] * 5] and e["log_assignment"].shape == (1, 1, 6)
+
+
+NPAIR = ROOT / "tests" / "golden" / "nn_npair_loss.pt"
+
+
+def test_npair_oracle_reproduces_the_reference_goldens():
+    for c in torch.load(NPAIR, map_location="cpu", weights_only=True):
+        data = make_pairs(**c["data_kwargs"])
+        sim = nn_oracle.forward({}, data)["similarity"]
+        res = nn_oracle.npair_loss(sim, data["gt_assignment"], c["temperature"])
+        for k in ("n_pair_nll", "total", "num_matchable"):
+            torch.testing.assert_close(res[k], c["losses"][k].detach(), atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.gpu
+def test_npair_loss_cuda_matches_reference_goldens():
+    """NearestNeighborMatcher.loss (nearest_neighbor_matcher.py:85-109): the three-pass kernel against what the
+    unmodified reference returned (losses in both modes, matcher metrics in eval mode)."""
+    from glue_factory_colon_b200.nearest_neighbor_matcher import NearestNeighborMatcher
+
+    for c in torch.load(NPAIR, map_location="cpu", weights_only=True):
+        model = NearestNeighborMatcher({"loss": "N_pair"}).cuda()
+        model.train(c["train"])
+        with torch.no_grad():
+            model.temperature.fill_(c["temperature"])
+        data = to_device(make_pairs(**c["data_kwargs"]), "cuda")
+        losses, metrics = model.loss(model(data), data)
+        assert set(losses) == set(c["losses"]) and set(metrics) == set(c["metrics"])
+        for k, v in c["losses"].items():
+            torch.testing.assert_close(losses[k].cpu(), v.detach(), atol=2e-5, rtol=2e-5)
+        for k, v in c["metrics"].items():
+            torch.testing.assert_close(metrics[k].cpu(), v, atol=1e-5, rtol=1e-5)

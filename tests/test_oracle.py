@@ -91,3 +91,19 @@ def test_oracle_against_live_reference():
     assert torch.equal(r["matches0"], out["matches0"][0])
     # layer-level masked oracle: masked_forward on padded input == un-padded run (lightglue.py:248-254)
     torch.testing.assert_close(r["ref_descriptors0"][0], out["ref_descriptors0"][0, 0], atol=1e-4, rtol=1e-4)
+
+
+def test_oracle_matches_reference_on_c1_boat_pair(golden_dir):
+    """BASELINE config 1: boat1/boat2, 1024 SIFT keypoints, official conf (filter_threshold 0.1) -- the oracle against
+    what the unmodified reference returned (oracle/make_golden_c1.py)."""
+    from helpers import load_c1_fixture
+
+    fx, model, data = load_c1_fixture(golden_dir / "c1_boat.pt")
+    r = oracle_batch(model, fx["conf"], data)[0]
+    assert int((fx["matches0"] > -1).sum()) > 300  # the fixture is not vacuous
+    assert torch.equal(r["matches0"], fx["matches0"]) and torch.equal(r["matches1"], fx["matches1"])
+    torch.testing.assert_close(r["matching_scores0"], fx["matching_scores0"], atol=1e-5, rtol=1e-4)
+    la = r["log_assignment"]
+    torch.testing.assert_close(la[::4, ::4], fx["la_sub"], atol=5e-4, rtol=0)
+    torch.testing.assert_close(la[:, -1], fx["la_dust_col"], atol=5e-4, rtol=0)
+    torch.testing.assert_close(la[-1, :], fx["la_dust_row"], atol=5e-4, rtol=0)
