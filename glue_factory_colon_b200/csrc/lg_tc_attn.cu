@@ -47,7 +47,20 @@ __device__ unsigned int g_attn_sm_slot[1024];
 #ifndef LG_ATTN_POLY_DEG
 #define LG_ATTN_POLY_DEG 3
 #endif
+#ifndef LG_ATTN_SPLIT_P
+#define LG_ATTN_SPLIT_P 1  // 1: the fast path stores P in two halves, with the P.V(j-1) wait between them
+#endif
+#ifndef LG_ATTN_POLY_PACKED
+#define LG_ATTN_POLY_PACKED 1  // 1: the polynomial exponentials are evaluated two at a time with packed f32x2 FMA-pipe ops
+#endif
+#if LG_ATTN_POLY_PACKED
+// pair i of a thread's 32 pairs: BOTH of its exponentials go through the polynomial (LG_ATTN_POLY16 of every 16 pairs)
+#define LG_POLY_PAIR(i) ((((i) * LG_ATTN_POLY16) % 16) < LG_ATTN_POLY16)
+#define LG_POLY_HERE(i) 0
+#else
+#define LG_POLY_PAIR(i) 0
 #define LG_POLY_HERE(i) ((((i) * LG_ATTN_POLY16) % 8) < LG_ATTN_POLY16)
+#endif
 
 // waits of the TMA-producer and MMA-issuer warps: polling with a 64 ns sleep in between (a bare try_wait loop takes
 // issue slots from the softmax warps of the same sub-partitions: 0.661 -> 0.650 ms with the deferred-maximum loop, which
@@ -108,6 +121,28 @@ __device__ __forceinline__ float ex2_poly(float x) {
   p = fmaf(p, f, 1.0f);
 #endif
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// Two polynomial exponentials per call on packed f32x2 operations (add.f32x2 / fma.rn.f32x2: one issue slot for both
+// lanes): 2 FMNMX + 3 FADD2 + 3 FFMA2 + 2 integer ops per pair = 5 issue slots per exponential instead of 8.5 -- the
+// loop is bound by issue slots as much as by the MUFU unit, so a cheaper polynomial moves the optimum share up.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.f);
+  x.y = fmaxf(x.y, -126.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f), nmagic = make_float2(-12582912.f, -12582912.f);
+  const float2 t = __fadd2_rn(x, magic);
+  const float2 u = __fadd2_rn(t, nmagic);
+  const float2 f = __fadd2_rn(x, make_float2(-u.x, -u.y));
+#if LG_ATTN_POLY_DEG == 2
+  float2 p = __ffma2_rn(f, make_float2(0.23842894f, 0.23842894f), make_float2(0.70344801f, 0.70344801f));
+  p = __ffma2_rn(p, f, make_float2(1.00044314f, 1.00044314f));
+#else
+  float2 p = __ffma2_rn(f, make_float2(0.05500889f, 0.05500889f), make_float2(0.24221097f, 0.24221097f));
+  p = __ffma2_rn(p, f, make_float2(0.69328294f, 0.69328294f));
+  p = __ffma2_rn(p, f, make_float2(1.0f, 1.0f));
+#endif
+  return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23)),
+                     __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23)));
 }
 
 // NP = softmax threads per query row (2: 8 softmax warps, 64 key columns each; 4: 16 warps, 32 columns each)
@@ -453,9 +488,15 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
         for (int i = 0; i < COLS / 2; ++i) {
           float p0 = __uint_as_float(sv[2 * i]) - delta, p1 = __uint_as_float(sv[2 * i + 1]) - delta;
-          p0 = ex2(p0);
-          if (LG_POLY_HERE(i)) pmax = fmaxf(pmax, p1);
-          p1 = LG_POLY_HERE(i) ? ex2_poly(p1) : ex2(p1);
+          if (LG_POLY_PAIR(i)) {
+            pmax = max3(pmax, p0, p1);
+            const float2 pp = ex2_poly2(make_float2(p0, p1));
+            p0 = pp.x, p1 = pp.y;
+          } else {
+            p0 = ex2(p0);
+            if (LG_POLY_HERE(i)) pmax = fmaxf(pmax, p1);
+            p1 = LG_POLY_HERE(i) ? ex2_poly(p1) : ex2(p1);
+          }
           rsum[i & 3] += p0 + p1;
           pk[i] = tc::pack_bf16(p0, p1);
         }
@@ -466,16 +507,42 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         float pend = -INFINITY;
         bool have_pend = false;  // (compile-time after unrolling)
         float2 rs2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#if LG_ATTN_SPLIT_P
+        // P leaves in two halves: the wait for P.V(j-1) (P buffer free) sits in the middle of the exponentials instead of
+        // after them, and the first half's tcgen05.st is in flight during the second half's exponentials
 #pragma unroll
-        for (int i = 0; i < COLS / 2; ++i) {
-          float p0 = ex2(__uint_as_float(sv[2 * i])), p1 = __uint_as_float(sv[2 * i + 1]);
-          if (LG_POLY_HERE(i)) {  // two polynomial inputs per FMNMX3
-            if (have_pend) { pmax = max3(pmax, pend, p1); have_pend = false; }
-            else { pend = p1; have_pend = true; }
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+          for (int i = half * (COLS / 4); i < (half + 1) * (COLS / 4); ++i) {
+#else
+        {
+#pragma unroll
+          for (int i = 0; i < COLS / 2; ++i) {
+#endif
+            float p0 = __uint_as_float(sv[2 * i]), p1 = __uint_as_float(sv[2 * i + 1]);
+            if (LG_POLY_PAIR(i)) {
+              pmax = max3(pmax, p0, p1);
+              const float2 pp = ex2_poly2(make_float2(p0, p1));
+              p0 = pp.x, p1 = pp.y;
+            } else {
+              p0 = ex2(p0);
+              if (LG_POLY_HERE(i)) {  // two polynomial inputs per FMNMX3
+                if (have_pend) { pmax = max3(pmax, pend, p1); have_pend = false; }
+                else { pend = p1; have_pend = true; }
+              }
+              p1 = LG_POLY_HERE(i) ? ex2_poly(p1) : ex2(p1);
+            }
+            rs2[i & 1] = __fadd2_rn(rs2[i & 1], make_float2(p0, p1));
+            pk[i] = tc::pack_bf16(p0, p1);
           }
-          p1 = LG_POLY_HERE(i) ? ex2_poly(p1) : ex2(p1);
-          rs2[i & 1] = __fadd2_rn(rs2[i & 1], make_float2(p0, p1));
-          pk[i] = tc::pack_bf16(p0, p1);
+#if LG_ATTN_SPLIT_P
+          if (half == 0 && j > 0) {
+            tc::mbar_wait(pv_done, (j - 1) & 1);  // PV(j-1) retired: P is free
+            tc::fence_after_sync();
+          }
+          if constexpr (NP == 2) tc::tmem_st16(tmem + lane_base + TM_P + part * (COLS / 2) + half * (COLS / 4), pk + half * (COLS / 4));
+          else tc::tmem_st8(tmem + lane_base + TM_P + part * (COLS / 2) + half * (COLS / 4), pk + half * (COLS / 4));
+#endif
         }
         if (have_pend) pmax = fmaxf(pmax, pend);
         tile_sum = (rs2[0].x + rs2[0].y) + (rs2[1].x + rs2[1].y);
@@ -485,6 +552,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       any_next = __any_sync(0xffffffffu, move_next);  // (exact mode: sums <= 128, never set)
       sum_m1 = tile_sum;
       STAMP(5);
+      if (!LG_ATTN_SPLIT_P || any_move) {
       if (j > 0) {
         tc::mbar_wait(pv_done, (j - 1) & 1);  // PV(j-1) retired: P is free, O is up to date
         tc::fence_after_sync();
@@ -502,6 +570,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       if constexpr (NP == 2) tc::tmem_st32(tmem + lane_base + TM_P + part * (COLS / 2), pk);
       else tc::tmem_st16(tmem + lane_base + TM_P + part * (COLS / 2), pk);
+      }
       tc::tmem_st_wait();
       STAMP(7);
       tc::fence_before_sync();

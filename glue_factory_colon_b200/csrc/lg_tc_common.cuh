@@ -214,6 +214,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t r[16]) 
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t r[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};"
+      ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(taddr)
+      : "memory");
+}
 // 16 lanes x 64 columns through the 16x256b shape (x8): thread t gets rows (t/4, t/4 + 8) of the 16-lane group and, for
 // step k = 0..7, registers [4k..4k+3] = (row_lo, 8k + 2(t%4)), (row_lo, +1), (row_hi, 8k + 2(t%4)), (row_hi, +1)
 // (measured: tools/micro/tmem_layout.cu) -- a row's columns live in one quad, so row reductions are two shuffles.

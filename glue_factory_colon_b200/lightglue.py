@@ -372,7 +372,7 @@ class LightGlue(nn.Module):
         in_recall, in_acc = (gt > -1).float(), (gt >= -1).float()
         in_prec = ((mt > -1) & (gt >= -1)).float()
         eps = 1e-8
-        order = torch.argsort(-sc)
+        order = torch.argsort(-sc, stable=True)  # ties: lowest index first (deterministic)
         tp, pm, rm = same.gather(-1, order), in_prec.gather(-1, order), in_recall.gather(-1, order)
         prec_curve = torch.cumsum(tp * pm, -1) / (eps + torch.cumsum(pm, -1))
         rec_curve = torch.cumsum(tp * rm, -1) / (eps + rm.sum(-1, keepdim=True))

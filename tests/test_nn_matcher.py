@@ -110,4 +110,8 @@ def test_npair_loss_cuda_matches_reference_goldens():
         for k, v in c["losses"].items():
             torch.testing.assert_close(losses[k].cpu(), v.detach(), atol=2e-5, rtol=2e-5)
         for k, v in c["metrics"].items():
-            torch.testing.assert_close(metrics[k].cpu(), v, atol=1e-5, rtol=1e-5)
+            # ranking AP = (recall_last - recall_first) * precision_last: it depends on WHICH of the tied top scores
+            # (the NN matcher's scores are 0 / 1) argsort puts first, which differs between the reference's CPU sort
+            # and a CUDA sort -- one true positive more or less in the first slot = 1 / num_matchable
+            tol = 1.0 / float(losses["num_matchable"].min()) + 1e-5 if k == "average_precision" else 1e-5
+            torch.testing.assert_close(metrics[k].cpu(), v, atol=tol, rtol=1e-5)
