@@ -11,9 +11,9 @@ from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "liblightglue_b200.so"
 
-F32, BF16 = 0, 1
+F32, BF16, F32X3 = 0, 1, 2
 EPI_ROWMAJOR, EPI_HEADS, EPI_LN_GELU = 0, 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _p, _i, _f = C.c_void_p, C.c_int, C.c_float
 
@@ -37,6 +37,10 @@ SIGNATURES = {
     "lgb200_loss_reduce": [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
     "lgb200_assign_loss": [_i, _p, _p, _p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p],
     "lgb200_exit_check": [_p, _i, _i, _p, _p, _f, _f, _i, _p, _p, _p],
+    "lgb200_split_rows": [_p, C.c_longlong, _p, _p],
+    "lgb200_x3_similarity": [_p, _i, _i, _p, _p, _p],
+    "lgb200_x3_assign_lse": [_p, _i, _i, _p, _i, _i, _p, _p],
+    "lgb200_x3_assign_scores": [_p, _p, _p, _i, _i, _p, _i, _i, _p, _p],
     "lgb200_prune_compact": [_p, _p, _f, _f, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
 }
 

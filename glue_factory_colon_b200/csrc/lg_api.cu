@@ -13,7 +13,7 @@ extern "C" int lgb200_linear(int precision, int epilogue, const void* A0, const 
     return LGB200_ERR_SHAPE;
   if (K0 < K && !A1) return LGB200_ERR_NULL;
   if (resid32 && resid16) return LGB200_ERR_SHAPE;
-  if (precision == LGB200_F32 && (resid16 || (rot16 && !rot))) return LGB200_ERR_PRECISION;
+  if ((precision == LGB200_F32 || precision == LGB200_F32X3) && (resid16 || (rot16 && !rot))) return LGB200_ERR_PRECISION;
   LgEpi e;
   e.mode = epilogue;
   e.N = N;
@@ -50,6 +50,10 @@ extern "C" int lgb200_linear(int precision, int epilogue, const void* A0, const 
   if (precision == LGB200_F32)
     return lg_simt_linear(epilogue, (const float*)A0, (const float*)A1, K0, (const float*)W, T, N, K,
                           lens, e, st);
+  if (precision == LGB200_F32X3) {  // operands and out16 / outp are split-fp16 planes
+    e.out16 = nullptr;
+    return lg_x3_linear(epilogue, A0, A1, K0, W, T, N, K, lens, e, out16, st);
+  }
   if (precision == LGB200_BF16) {
     // v2 = weight-stationary / cluster-multicast kernel (lg_tc_gemm2.cu); LGB200_GEMM_V1=1 selects the
     // first-generation streaming kernel (lg_tc_gemm.cu) for A/B measurements.
@@ -85,6 +89,7 @@ extern "C" int lgb200_attention_ordered(int precision, const void* Q, const void
   if (precision == LGB200_F32)
     return lg_simt_attention((const float*)Q, (const float*)K, (const float*)V, S, Lp, lens, kv_xor,
                              (float*)ctx, st);
+  if (precision == LGB200_F32X3) return lg_x3_attention(Q, K, V, S, Lp, lens, kv_xor, ctx, st);
   if (precision == LGB200_BF16) {
     // LGB200_ATTN2=1 selects the two-query-tile kernel with ordered softmax groups (lg_tc_attn2.cu)
     static const int attn2 = getenv("LGB200_ATTN2") ? atoi(getenv("LGB200_ATTN2")) : 0;

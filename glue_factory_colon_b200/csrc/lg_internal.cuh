@@ -29,3 +29,15 @@ int lg_tc_assign_scores(const __nv_bfloat16* md, const float* z, const float* ls
 int lg_tc_assign_loss(const __nv_bfloat16* md, const float* z, const float* lse, int B, int Lp, const int32_t* lens,
                       int R, int C, const uint8_t* gt, float* row_pos, float* row_cnt, float* row_exp,
                       int32_t* row_arg, int32_t* col_arg, void* best_ws, cudaStream_t st);
+
+// fp32-accurate tensor-core path: split-fp16 operands, three MMAs per product (lg_x3.cu, lg_x3_attn.cu)
+int lg_x3_linear(int epilogue, const void* A0, const void* A1, int K0, const void* W, int T, int N, int K,
+                 const int32_t* lens, LgEpi epi, void* outs, cudaStream_t st);
+int lg_x3_attention(const void* Q, const void* K, const void* V, int S, int Lp, const int32_t* lens, int kv_xor,
+                    void* ctx, cudaStream_t st);
+// x3 plane scaling: a plane pair stores x * 2^e so that the LOW plane stays a normal fp16 number (fp16 normals end at
+// 6.1e-5 and lo ~ 2^-11 |x|: unscaled, the low planes of all weights and of every activation below 0.12 are subnormal
+// (or flushed) and the pair carries ~12 bits instead of 22).  Powers of two: exact, undone in the consuming epilogue.
+#define LG_X3_EA 64.0f    /* activations, q / k / v, md: |x| < 1023, low plane normal for |x| > 2e-3 */
+#define LG_X3_EW 256.0f   /* weights (host side, lightglue.py:_pack) */
+#define LG_X3_EP 256.0f   /* attention probabilities (<= 16 with the lazy maximum threshold of 4) */

@@ -42,13 +42,27 @@ __device__ unsigned int g_attn_sm_slot[1024];
 #define LG_ATTN_MSUB 1  // 1: the row-max subtraction s - m_ref is folded into the QK^T MMA (a fifth K=16 slice)
 #endif
 #ifndef LG_ATTN_POLY16
-#define LG_ATTN_POLY16 4  // LG_ATTN_POLY16 of every 16 exponentials are evaluated by polynomial on the FMA pipe (0..8)
+#define LG_ATTN_POLY16 5  // LG_ATTN_POLY16 of every 16 exponentials are evaluated by polynomial on the FMA pipe (0..8)
 #endif
 #ifndef LG_ATTN_POLY_DEG
 #define LG_ATTN_POLY_DEG 3
 #endif
 #ifndef LG_ATTN_SPLIT_P
-#define LG_ATTN_SPLIT_P 1  // 1: the fast path stores P in two halves, with the P.V(j-1) wait between them
+#define LG_ATTN_SPLIT_P 0  // 1: the fast path stores P in two halves, with the P.V(j-1) wait between them
+#endif
+#ifndef LG_ATTN_EARLY_POLL
+// 1: the softmax warps poll pv_done(j-1) / s_full(j+1) with a non-blocking test one phase of work BEFORE they need the
+// answer (a successful mbarrier try_wait still costs ~100-130 cycles of latency: ncu source page of r2, 15 % + 6 % of a
+// softmax warp's tile time sat on the two polls), and fall back to the blocking wait only if the early test failed
+#define LG_ATTN_EARLY_POLL 1
+#endif
+#ifndef LG_ATTN_PRELOAD
+// 1: the score tile of step j+1 is loaded (tcgen05.ld) right behind the P store of step j, so that the TMEM load
+// latency overlaps the store's completion wait and the p_ready hand-shake instead of opening the next step
+#define LG_ATTN_PRELOAD 1
+#endif
+#ifndef LG_ATTN_PVTEST_AT
+#define LG_ATTN_PVTEST_AT 20  // pair index (of 32) in the exponential loop at which pv_done(j-1) is polled (PRELOAD)
 #endif
 #ifndef LG_ATTN_POLY_PACKED
 #define LG_ATTN_POLY_PACKED 1  // 1: the polynomial exponentials are evaluated two at a time with packed f32x2 FMA-pipe ops
@@ -405,16 +419,35 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     } while (0)
     const bool rec = (dbg_in & 16) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == LG_DBG_Z && warp == 2 && lane == 0;
 #define STAMP(k) do { if (rec && j < 16) g_attn_times[(j * 16) + (k)] = clock64(); } while (0)
+    bool sf_ok = false;
     for (int j = 0; j < n_tiles; ++j) {
       STAMP(0);
       bool move = move_next, any_move = any_next;  // deferred mode: decided in the previous tile
       const float joint = joint_next;
+#if LG_ATTN_EARLY_POLL
+      if (!sf_ok) tc::mbar_wait(s_full, j & 1);
+#else
       tc::mbar_wait(s_full, j & 1);
+#endif
       tc::fence_after_sync();
       STAMP(1);
       uint32_t sv[COLS];
 #pragma unroll
       for (int c = 0; c < COLS; c += 32) tc::tmem_ld32(tmem + lane_base + TM_S + part * COLS + c, sv + c);
+#if LG_ATTN_PRELOAD
+      if (j > 0) {  // the previous step's P store: its completion wait and the p_ready hand-shake sit behind this load
+        tc::tmem_st_wait();
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(p_ready);
+      }
+#endif
+#if LG_ATTN_EARLY_POLL
+      bool pv_ok = false;
+#if !LG_ATTN_PRELOAD
+      pv_ok = j > 0 && tc::mbar_test(pv_done, (j - 1) & 1);  // consumed after the exponentials
+#endif
+#endif
       tc::tmem_ld_wait();
       STAMP(2);
       const int valid = nk - j * AT_BN - part * COLS;  // valid keys among this thread's columns
@@ -519,6 +552,9 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
           for (int i = 0; i < COLS / 2; ++i) {
 #endif
+#if LG_ATTN_EARLY_POLL && LG_ATTN_PRELOAD
+            if (i == LG_ATTN_PVTEST_AT) pv_ok = tc::mbar_test(pv_done, (j - 1) & 1);  // P.V(j-1) was released at the top of this step (j = 0: not consumed)
+#endif
             float p0 = __uint_as_float(sv[2 * i]), p1 = __uint_as_float(sv[2 * i + 1]);
             if (LG_POLY_PAIR(i)) {
               pmax = max3(pmax, p0, p1);
@@ -552,8 +588,14 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       any_next = __any_sync(0xffffffffu, move_next);  // (exact mode: sums <= 128, never set)
       sum_m1 = tile_sum;
       STAMP(5);
+#if LG_ATTN_EARLY_POLL
+      sf_ok = tc::mbar_test(s_full, (j + 1) & 1);  // S(j+1) (never completes after the last tile: not consumed)
+#endif
       if (!LG_ATTN_SPLIT_P || any_move) {
       if (j > 0) {
+#if LG_ATTN_EARLY_POLL
+        if (!pv_ok)
+#endif
         tc::mbar_wait(pv_done, (j - 1) & 1);  // PV(j-1) retired: P is free, O is up to date
         tc::fence_after_sync();
         STAMP(6);
@@ -571,13 +613,21 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if constexpr (NP == 2) tc::tmem_st32(tmem + lane_base + TM_P + part * (COLS / 2), pk);
       else tc::tmem_st16(tmem + lane_base + TM_P + part * (COLS / 2), pk);
       }
+#if !LG_ATTN_PRELOAD
       tc::tmem_st_wait();
       STAMP(7);
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(p_ready);
       STAMP(8);
+#endif
     }
+#if LG_ATTN_PRELOAD
+    tc::tmem_st_wait();
+    tc::fence_before_sync();
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(p_ready);
+#endif
     XSTAMP(2);
     // combine the partial row sums (ring slot n_tiles & 3 is the one no pending tile sum lives in; the exact mode, whose
     // maxima use slots 0 and 1, gets slot 2), normalise this thread's output columns

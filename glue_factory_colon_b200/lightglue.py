@@ -28,7 +28,7 @@ import torch
 from torch import nn
 
 from . import _abi
-from ._abi import BF16, EPI_HEADS, EPI_LN_GELU, EPI_ROWMAJOR, F32, check, ptr
+from ._abi import BF16, EPI_HEADS, EPI_LN_GELU, EPI_ROWMAJOR, F32, F32X3, check, ptr
 
 LOG2E = 1.4426950408889634
 
@@ -136,7 +136,9 @@ class LightGlue(nn.Module):
         "weights": None,
         "weights_from_version": "v0.1_arxiv",
         "loss": {"gamma": 1.0, "fn": "nll", "nll_balancing": 0.5},
-        # B200 extension: "fp32" (CUDA-core parity kernels), "bf16" (tcgen05 kernels),
+        # B200 extension: "fp32" = fp32-accurate mode on the tensor cores (split-fp16 operands, three tcgen05 MMAs per
+        # product, fp32 softmax / LayerNorm / GELU / residuals: 1e-3 parity on log_assignment), "bf16" = bf16 tcgen05
+        # kernels (throughput mode), "fp32_simt" = the CUDA-core fp32 kernels (debug / cross-check),
         # "auto" = bf16 when conf.mp or torch autocast is active, else fp32.
         "precision": "auto",
         # B200 extension: capture the whole forward of a fixed input signature in a CUDA graph and replay it (eval
@@ -172,6 +174,7 @@ class LightGlue(nn.Module):
             torch.Tensor([self.confidence_threshold(i) for i in range(n)]),
         )
         self._packed: Dict = {}
+        self._packs: Dict = {}
         self._pack_key = None
         self._graphs: Dict = {}
         # measurement hook (bench.py): a list to which the forward appends (start, end) CUDA events around every
@@ -318,6 +321,8 @@ class LightGlue(nn.Module):
         B, N, m, _ = r0.shape
         n = r1.shape[2]
         prec = self._precision()
+        if prec == F32X3:  # the loss reductions of the fp32 mode run in the CUDA-core fp32 kernels
+            prec = F32
         st = torch.cuda.current_stream(dev).cuda_stream
         L = conf.n_layers
         gt = data["gt_assignment"].to(dev).to(torch.bool).contiguous()
@@ -390,9 +395,9 @@ class LightGlue(nn.Module):
         p = self.conf.precision
         if p == "auto":
             p = "bf16" if (self.conf.mp or torch.is_autocast_enabled()) else "fp32"
-        if p not in ("fp32", "bf16"):
-            raise ValueError(f"precision must be fp32, bf16 or auto, got {p}")
-        return BF16 if p == "bf16" else F32
+        if p not in ("fp32", "bf16", "fp32_simt"):
+            raise ValueError(f"precision must be fp32, fp32_simt, bf16 or auto, got {p}")
+        return {"bf16": BF16, "fp32": F32X3, "fp32_simt": F32}[p]
 
     def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() / .half(): parameters may be replaced
         self._plist = None
@@ -405,13 +410,22 @@ class LightGlue(nn.Module):
         if plist is None:
             plist = self._plist = list(self.parameters())
         key = (prec, str(device), tuple((p.data_ptr(), p._version) for p in plist))
-        if self._pack_key == key:
-            return self._packed
-        # one pack is kept; captured CUDA graphs hold their own reference (see forward), so replacing it is safe
+        hit = self._packs.get(prec)
+        if hit is not None and hit[0] == key:
+            self._packed, self._pack_key = hit[1], key
+            return hit[1]
+        # one pack per precision is kept (forward in the fp32 tensor-core mode, loss in the CUDA-core fp32 kernels);
+        # captured CUDA graphs hold their own reference (see forward), so replacing one is safe
         wdt = torch.bfloat16 if prec == BF16 else torch.float32
 
         def W(t):
-            return t.detach().to(device=device, dtype=wdt).contiguous()
+            t = t.detach().to(device=device, dtype=torch.float32)
+            if prec == F32X3:  # split planes [2][N][K] fp16: 256 w = hi + lo (LG_X3_EW in csrc/lg_internal.cuh:
+                t = t * 256.0   # the power of two keeps the low plane a normal fp16 number; undone in the epilogues)
+                hi = t.to(torch.float16)
+                lo = (t - hi.to(torch.float32)).to(torch.float16)
+                return torch.stack([hi, lo]).contiguous()
+            return t.to(wdt).contiguous()
 
         def Fp(t):
             return t.detach().to(device=device, dtype=torch.float32).contiguous()
@@ -423,12 +437,13 @@ class LightGlue(nn.Module):
             into the first FFN matrix -- W1.cat[x, Wo.ctx + bo] = [W1x | W1m.Wo].cat[x, ctx] + (b1 + W1m.bo) -- so the
             [T,256]x[256,256] launch and the `msg` round trip through HBM disappear (exact in real arithmetic; the
             product is formed in fp32 and rounded to bf16 once, like every other weight)."""
-            w1 = ffn0.weight.detach().float()
-            wo, bo = out_proj.weight.detach().float(), out_proj.bias.detach().float()
+            w1 = ffn0.weight.detach().double()
+            wo, bo = out_proj.weight.detach().double(), out_proj.bias.detach().double()
             d = wo.shape[0]
-            return torch.cat([w1[:, :d], w1[:, d:] @ wo], 1), ffn0.bias.detach().float() + w1[:, d:] @ bo
+            return (torch.cat([w1[:, :d], w1[:, d:] @ wo], 1).float(),
+                    (ffn0.bias.detach().double() + w1[:, d:] @ bo).float())
 
-        fold = prec == BF16
+        fold = prec in (BF16, F32X3)
         layers = []
         for lyr in self.transformers:
             sa, ca = lyr.self_attn, lyr.cross_attn
@@ -459,6 +474,7 @@ class LightGlue(nn.Module):
         if isinstance(self.input_proj, nn.Linear):
             packed["in_w"], packed["in_b"] = W(self.input_proj.weight), Fp(self.input_proj.bias)
         self._packed, self._pack_key = packed, key
+        self._packs[prec] = (key, packed)
         return packed
 
     # ---- forward ---------------------------------------------------------------------------
@@ -585,11 +601,14 @@ class LightGlue(nn.Module):
 
         prec = self._precision()
         bf = prec == BF16
+        x3 = prec == F32X3   # fp32-accurate tensor-core mode: MMA operands are split-fp16 planes [2][rows][K]
+        fold = bf or x3      # out_proj / to_out folded into the first FFN matrix (see _pack)
         W = self._pack(prec, dev)
         st = torch.cuda.current_stream(dev).cuda_stream
         L = conf.n_layers
         S = 2 * B
-        Lp = max(128, ((max(m, n) + 127) // 128) * 128)
+        gran = 256 if x3 else 128  # (the x3 similarity GEMM tiles the keys by 256)
+        Lp = max(gran, ((max(m, n) + gran - 1) // gran) * gran)
         T = S * Lp
 
         # per-sequence valid counts (B200 extension for padded batches)
@@ -629,23 +648,36 @@ class LightGlue(nn.Module):
         adt = dict(device=dev, dtype=act)
         # Residual stream x [T,256] in the activation dtype (bf16 mode keeps it in bf16 only: measured
         # against the fp32 oracle this is still 2x closer than the reference's own autocast run).
+        # x3 mode: x stays the fp32 master (exact residual adds, token heads, returned descriptors) and xs holds its
+        # split planes, the A operand of the projections.
         x = torch.empty(T, 256, **adt)
         rot = None if bf else torch.empty(T, 64, **f32)           # (cos, sin) fp32 pairs
         rot16 = torch.empty(T, 32, **i32) if bf else None          # packed fp16 (cos, sin)
         # padded rows must hold finite values (masked keys multiply V rows by exactly 0); without
         # padding every row is written before it is read, so the fills are skipped
         alloc = torch.zeros if use_lens else torch.empty
-        q = alloc(T * 256, **adt)
-        k = alloc(T * 256, **adt)
-        v = alloc(T * 256, **adt)
-        ctx = alloc(T, 256, **adt)
-        msg = alloc(T, 256, **adt)
-        hid = alloc(T, 512, **adt)
+        if x3:
+            h16 = dict(device=dev, dtype=torch.float16)
+            xs = alloc(2, T, 256, **h16)
+            q, k, v = alloc(2, T * 256, **h16), alloc(2, T * 256, **h16), alloc(2, T * 256, **h16)
+            ctx, msg, hid = alloc(2, T, 256, **h16), alloc(2, T, 256, **h16), alloc(2, T, 512, **h16)
+        else:
+            xs = None
+            q = alloc(T * 256, **adt)
+            k = alloc(T * 256, **adt)
+            v = alloc(T * 256, **adt)
+            ctx = alloc(T, 256, **adt)
+            msg = alloc(T, 256, **adt)
+            hid = alloc(T, 512, **adt)
 
         def linear(epi, A0, Wt, bias, N, K, A1=None, K0=None, scale=(1.0, 1.0, 1.0), resid=None,
-                   out=None, n_rot=0, outp=(None, None, None), gamma=None, beta=None, lens_=None):
-            r32, r16 = (None, resid) if bf else (resid, None)
-            o32, o16 = (None, out) if bf else (out, None)
+                   out=None, n_rot=0, outp=(None, None, None), gamma=None, beta=None, lens_=None, out32=None):
+            """x3: A0 / A1 / out / outp are split planes, resid / out32 fp32."""
+            if x3:
+                r32, r16, o32, o16 = resid, None, out32, out
+            else:
+                r32, r16 = (None, resid) if bf else (resid, None)
+                o32, o16 = (None, out) if bf else (out, None)
             check(
                 lib.lgb200_linear(
                     prec, epi, ptr(A0), ptr(A1), K if K0 is None else K0, ptr(Wt), ptr(bias), T, N, K,
@@ -656,12 +688,17 @@ class LightGlue(nn.Module):
                 "lgb200_linear",
             )
 
+        def split(src32, dst16):  # fp32 rows -> split planes
+            check(lib.lgb200_split_rows(ptr(src32), src32.numel(), ptr(dst16), st), "split_rows")
+
         def pack(dsc, cnt, dim, img, dst):
             x32_, x16_ = (None, dst) if bf else (dst, None)
             check(lib.lgb200_pack_rows(ptr(dsc), B, cnt, dim, img, Lp, ptr(x32_), ptr(x16_), st), "pack_rows")
 
+        hprec = F32 if x3 else prec  # the token / matchability heads read the fp32 master in x3 mode
+
         def rowdot(xt, wb, lens_, sigmoid, out):
-            check(lib.lgb200_rowdot(prec, ptr(xt), ptr(wb[0]), ptr(wb[1]), S, Lp, ptr(lens_), sigmoid, ptr(out), st),
+            check(lib.lgb200_rowdot(hprec, ptr(xt), ptr(wb[0]), ptr(wb[1]), S, Lp, ptr(lens_), sigmoid, ptr(out), st),
                   "lgb200_rowdot")
 
         # ---- staging: descriptors (+ input_proj) and positional encoding ----
@@ -670,10 +707,17 @@ class LightGlue(nn.Module):
             xin = torch.empty(T, din, **adt)
             for img, dsc, cnt in ((0, desc0, m), (1, desc1, n)):
                 pack(dsc, cnt, din, img, xin)
-            linear(EPI_ROWMAJOR, xin, W["in_w"], W["in_b"], 256, din, out=x)
+            if x3:
+                xin_s = torch.empty(2, T, din, **h16)
+                split(xin, xin_s)
+                linear(EPI_ROWMAJOR, xin_s, W["in_w"], W["in_b"], 256, din, out=xs, out32=x)
+            else:
+                linear(EPI_ROWMAJOR, xin, W["in_w"], W["in_b"], 256, din, out=x)
         else:
             for img, dsc, cnt in ((0, desc0, m), (1, desc1, n)):
                 pack(dsc, cnt, 256, img, x)
+            if x3:
+                split(x, xs)
         for img, kk, cnt, sz in ((0, k0, m, size0), (1, k1, n, size1)):
             check(lib.lgb200_posenc(ptr(kk), B, cnt, kdim, ptr(sz), ptr(W["wr"]), ptr(lens), img, Lp, ptr(rot),
                                     ptr(rot16), st), "lgb200_posenc")
@@ -709,7 +753,8 @@ class LightGlue(nn.Module):
             w = W["layers"][i]
             la = lens_act
             # self block (lightglue.py:151-164)
-            linear(EPI_HEADS, x, w["qkv_w"], w["qkv_b"], 768, 256, scale=(q_scale, 1.0, 1.0), n_rot=2,
+            xa = xs if x3 else x  # A operand of the projections
+            linear(EPI_HEADS, xa, w["qkv_w"], w["qkv_b"], 768, 256, scale=(q_scale, 1.0, 1.0), n_rot=2,
                    outp=(q, k, v), lens_=la)
             if self._attn_events is not None:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -719,21 +764,27 @@ class LightGlue(nn.Module):
             if self._attn_events is not None:
                 ev1.record()
                 self._attn_events.append((ev0, ev1))
-            if not bf:  # (bf16: out_proj is folded into sf0_w, see _pack)
+            if not fold:  # (bf16 / x3: out_proj is folded into sf0_w, see _pack)
                 linear(EPI_ROWMAJOR, ctx, w["so_w"], w["so_b"], 256, 256, out=msg, lens_=la)
-            linear(EPI_LN_GELU, x, w["sf0_w"], w["sf0_b"], 512, 512, A1=ctx if bf else msg, K0=256, gamma=w["sln_g"],
+            linear(EPI_LN_GELU, xa, w["sf0_w"], w["sf0_b"], 512, 512, A1=ctx if fold else msg, K0=256, gamma=w["sln_g"],
                    beta=w["sln_b"], out=hid, lens_=la)
-            linear(EPI_ROWMAJOR, hid, w["sf3_w"], w["sf3_b"], 256, 512, resid=x, out=x, lens_=la)
+            if x3:
+                linear(EPI_ROWMAJOR, hid, w["sf3_w"], w["sf3_b"], 256, 512, resid=x, out=xs, out32=x, lens_=la)
+            else:
+                linear(EPI_ROWMAJOR, hid, w["sf3_w"], w["sf3_b"], 256, 512, resid=x, out=x, lens_=la)
             # cross block (lightglue.py:193-222)
-            linear(EPI_HEADS, x, w["cqv_w"], w["cqv_b"], 512, 256, scale=(c_scale, 1.0, 1.0), n_rot=0,
+            linear(EPI_HEADS, xa, w["cqv_w"], w["cqv_b"], 512, 256, scale=(c_scale, 1.0, 1.0), n_rot=0,
                    outp=(q, v, None), lens_=la)
             check(lib.lgb200_attention_ordered(prec, ptr(q), ptr(q), ptr(v), S, Lp, ptr(la), ptr(order_cross), 1, ptr(ctx),
                                                st), "attention")
-            if not bf:
+            if not fold:
                 linear(EPI_ROWMAJOR, ctx, w["co_w"], w["co_b"], 256, 256, out=msg, lens_=la)
-            linear(EPI_LN_GELU, x, w["cf0_w"], w["cf0_b"], 512, 512, A1=ctx if bf else msg, K0=256, gamma=w["cln_g"],
+            linear(EPI_LN_GELU, xa, w["cf0_w"], w["cf0_b"], 512, 512, A1=ctx if fold else msg, K0=256, gamma=w["cln_g"],
                    beta=w["cln_b"], out=hid, lens_=la)
-            linear(EPI_ROWMAJOR, hid, w["cf3_w"], w["cf3_b"], 256, 512, resid=x, out=x, lens_=la)
+            if x3:
+                linear(EPI_ROWMAJOR, hid, w["cf3_w"], w["cf3_b"], 256, 512, resid=x, out=xs, out32=x, lens_=la)
+            else:
+                linear(EPI_ROWMAJOR, hid, w["cf3_w"], w["cf3_b"], 256, 512, resid=x, out=x, lens_=la)
             if self.training:
                 xl = x.view(B, 2, Lp, 256)
                 collected0.append(xl[:, 0, :m].clone())
@@ -771,6 +822,8 @@ class LightGlue(nn.Module):
                                                ptr(rot16), ptr(rot16_b), ptr(ind), ptr(ind_b), ptr(prune_cnt), st),
                       "prune_compact")
                 x, x_b = x_b, x
+                if x3:  # the split planes follow the compacted fp32 master
+                    split(x, xs)
                 rot, rot_b = rot_b, rot
                 rot16, rot16_b = rot16_b, rot16
                 ind, ind_b = ind_b, ind
@@ -784,7 +837,8 @@ class LightGlue(nn.Module):
             exit_layer = np.where(done_h != 0, done_h - 1, L - 1).astype(np.int64)
             lens_final = st_h[B:].reshape(B, 2).copy()
         # ---- log assignment (lightglue.py:523-524) ----
-        md = msg  # reuse: [T,256] in the activation dtype
+        md = msg  # reuse: [T,256] in the activation dtype (x3: split planes)
+        sim = None
         z = torch.zeros(T, **f32)
         lse = torch.zeros(T, **f32)
         for e in np.unique(exit_layer):
@@ -794,9 +848,16 @@ class LightGlue(nn.Module):
             else:
                 lens_g = lens
             a = W["assign"][int(e)]
-            linear(EPI_ROWMAJOR, x, a["fp_w"], a["fp_b"], 256, 256, scale=(0.25, 1.0, 1.0), out=md, lens_=lens_g)
+            linear(EPI_ROWMAJOR, xs if x3 else x, a["fp_w"], a["fp_b"], 256, 256, scale=(0.25, 1.0, 1.0), out=md,
+                   lens_=lens_g)
             rowdot(x, (a["m_w"], a["m_b"]), lens_g, 0, z)
-            check(lib.lgb200_assign_lse(prec, ptr(md), S, Lp, ptr(lens_g), ptr(lse), st), "assign_lse")
+            if x3:
+                if sim is None:
+                    sim = torch.empty(B, Lp, Lp, **f32)
+                check(lib.lgb200_x3_similarity(ptr(md), B, Lp, ptr(lens_g), ptr(sim), st), "x3_similarity")
+                check(lib.lgb200_x3_assign_lse(ptr(sim), B, Lp, ptr(lens_g), m, n, ptr(lse), st), "x3_assign_lse")
+            else:
+                check(lib.lgb200_assign_lse(prec, ptr(md), S, Lp, ptr(lens_g), ptr(lse), st), "assign_lse")
         if do_prune:  # pruned shape is data dependent (lightglue.py:285 note)
             R, C = int(lens_final[:, 0].max()) + 1, int(lens_final[:, 1].max()) + 1
         else:
@@ -805,8 +866,12 @@ class LightGlue(nn.Module):
         fm_ws = torch.empty(B * (R + C), device=dev, dtype=torch.int64)
         # bf16: the assignment epilogue also emits the row/column arg-maxima, so filter_matches never
         # re-reads the 1 GB score matrix
-        check(lib.lgb200_assign_scores(prec, ptr(md), ptr(z), ptr(lse), B, Lp, ptr(lens), R, C, ptr(scores),
-                                       ptr(fm_ws) if bf else None, st), "assign_scores")
+        if x3:
+            check(lib.lgb200_x3_assign_scores(ptr(sim), ptr(z), ptr(lse), B, Lp, ptr(lens), R, C, ptr(scores), st),
+                  "x3_assign_scores")
+        else:
+            check(lib.lgb200_assign_scores(prec, ptr(md), ptr(z), ptr(lse), B, Lp, ptr(lens), R, C, ptr(scores),
+                                           ptr(fm_ws) if bf else None, st), "assign_scores")
 
         # ---- filter_matches (lightglue.py:525-536) ----
         m0 = torch.empty(B, m, device=dev, dtype=torch.int64)

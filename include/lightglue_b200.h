@@ -21,7 +21,13 @@
  *     lens[s] == 0 is skipped by every kernel (used for early-exited pairs).
  *   - precision: LGB200_F32 runs hand-written CUDA-core fp32 kernels (the
  *     parity mode, 1e-3 on log_assignment); LGB200_BF16 runs tcgen05/TMEM/TMA
- *     kernels with bf16 operands and fp32 accumulation (the throughput mode).
+ *     kernels with bf16 operands and fp32 accumulation (the throughput mode);
+ *     LGB200_F32X3 is the fp32-accurate mode ON the tensor cores: every MMA
+ *     operand is a pair of fp16 planes [2][rows][K] (x = hi + lo, 22 mantissa
+ *     bits), every product is three tcgen05 MMAs with fp32 accumulation,
+ *     softmax / LayerNorm / GELU(erf) / residuals stay in fp32 (lg_x3*.cu).
+ *     In that mode the operand pointers of lgb200_linear (A0, A1, W, out16,
+ *     outp0..2) and of lgb200_attention (Q, K, V, ctx) are split planes.
  */
 #ifndef LIGHTGLUE_B200_H_
 #define LIGHTGLUE_B200_H_
@@ -32,9 +38,9 @@
 extern "C" {
 #endif
 
-#define LGB200_ABI_VERSION 3
+#define LGB200_ABI_VERSION 4
 
-enum { LGB200_F32 = 0, LGB200_BF16 = 1 };
+enum { LGB200_F32 = 0, LGB200_BF16 = 1, LGB200_F32X3 = 2 };
 
 enum {
   LGB200_OK = 0,
@@ -254,6 +260,22 @@ int lgb200_prune_compact(const float* match, const float* conf, float thr, float
                          const void* rot16_src, void* rot16_dst,
                          const int32_t* ind_src, int32_t* ind_dst,
                          int32_t* prune_cnt, void* stream);
+
+/* ---- fp32-accurate tensor-core mode (LGB200_F32X3): helpers -------------------------------------
+ * lgb200_split_rows: x [n] fp32 -> xs [2][n] fp16 planes (hi = fp16(x), lo = fp16(x - hi)); n % 4 == 0.
+ * Used for the staged descriptors (lightglue.py:456-465) and after point pruning (:506-521). */
+int lgb200_split_rows(const float* x, long long n, void* xs, void* stream);
+/* Similarity of MatchAssignment (the einsum of lightglue.py:284) for all pairs: mds = split planes of
+ * final_proj(desc)/4 [2][S*Lp][256]; sim [B][Lp][Lp] fp32 receives <md[2b,i], md[2b+1,j]> for i < lens[2b],
+ * j < lens[2b+1] (tiles past the valid counts are not touched). Lp % 256 == 0. */
+int lgb200_x3_similarity(const void* mds, int B, int Lp, const int32_t* lens, float* sim, void* stream);
+/* lse [S*Lp]: row normaliser log_softmax(sim, 2) for image 0, column normaliser log_softmax(sim, 1) for image 1
+ * (lightglue.py:262-263), natural log; n0 / n1 = counts when lens is NULL. */
+int lgb200_x3_assign_lse(const float* sim, int B, int Lp, const int32_t* lens, int n0, int n1, float* lse,
+                         void* stream);
+/* scores [B][R][C] (lightglue.py:257-269) from sim, z (matchability logits [S*Lp]) and lse. */
+int lgb200_x3_assign_scores(const float* sim, const float* z, const float* lse, int B, int Lp,
+                            const int32_t* lens, int R, int C, float* scores, void* stream);
 
 #ifdef __cplusplus
 }
