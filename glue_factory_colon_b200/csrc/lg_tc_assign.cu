@@ -18,10 +18,28 @@ namespace {
 
 constexpr int AS_TILE = 128 * 64 * 2;        // one 128-row x 64-col bf16 box (16 KB)
 constexpr int AS_OPER = 4 * AS_TILE;         // 128 rows x K=256 (64 KB)
-constexpr int AS_STAGE_OFF = AS_OPER;        // B stages follow A
-constexpr int AS_BAR_OFF = 3 * AS_OPER;
-constexpr int AS_XPOSE_OFF = AS_BAR_OFF + 128;
-constexpr int AS_EPI_WARPS = 8;              // epilogue warps: (TMEM lane quarter) x (64-column half of the tile)
+constexpr int AS_STAGE_OFF = AS_OPER;        // the B ring follows A
+#ifndef LG_ASSIGN_WARPS
+#define LG_ASSIGN_WARPS 16
+#endif
+// Epilogue warps: (TMEM lane quarter) x (column part of the tile).  r1 had 8 (two 32-column chunks per warp and tile)
+// beside two full 64 KB B stages, and pass 2 was latency-bound at one CTA per SM (issue 38 % active, DRAM 24 %).
+// r2: 16 warps, one 32-column chunk each; to make room for their transpose tiles the B operand streams through a ring
+// of AS_RING K-boxes of 16 KB (a tile's 16 MMAs take ~1 000 tensor cycles of the ~4 000+ its epilogue needs, so the
+// shallower prefetch costs nothing).
+#ifndef LG_ASSIGN_CL
+#define LG_ASSIGN_CL 1
+#endif
+// Optional (-DLG_ASSIGN_CL=2): the two CTAs of neighbouring strips form a cluster and share every B box (each loads 64
+// of its 128 rows and TMA-multicasts them to both), halving the L2->SM stream (2 048 CTAs x 1 MB at 64 x 2048).  Measured
+// on B200: pass 1 270 vs 255 us, pass 2 443 vs 433 us -- the L2 stream is not the limiter, so the default stays 1.
+constexpr int AS_CL = LG_ASSIGN_CL;          // CTAs (row strips) that share the B stream: 1 or 2
+constexpr int AS_EPI_WARPS = LG_ASSIGN_WARPS;
+constexpr int AS_PARTS = AS_EPI_WARPS / 4;   // column parts of a 128-column tile (2 or 4)
+constexpr int AS_PCOLS = 128 / AS_PARTS;     // columns per warp and tile (64 or 32)
+constexpr int AS_RING = AS_EPI_WARPS == 16 ? 5 : 8;  // B ring depth in K-boxes (8 = the two full stages of r1)
+constexpr int AS_BAR_OFF = AS_OPER + AS_RING * AS_TILE;
+constexpr int AS_XPOSE_OFF = AS_BAR_OFF + 256;
 constexpr int AS_THREADS = (2 + AS_EPI_WARPS) * 32;
 constexpr int AS_XP = 32 * 33;               // floats of one warp's 32 x 32 transpose tile (padded)
 constexpr int AS_SMEM = AS_XPOSE_OFF + AS_EPI_WARPS * (AS_XP + 32) * 4;
@@ -84,7 +102,8 @@ struct AsLoss {
 
 template <int MODE>
 __global__ void __launch_bounds__(AS_THREADS, 1)
-tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t* __restrict__ lens,
+tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, const __grid_constant__ CUtensorMap tmB, int Lp,
+                 const int32_t* __restrict__ lens,
                  const float* __restrict__ z, const float* __restrict__ lse_in, float* __restrict__ lse_out,
                  int R, int C, float* __restrict__ scores, unsigned long long* __restrict__ best0,
                  unsigned long long* __restrict__ best1, AsLoss ls) {
@@ -96,7 +115,11 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t
   const int m0 = blockIdx.x * 128;
   const int nq = lens ? lens[s] : (SCORES ? R - 1 : Lp);
   const int nk = lens ? lens[so] : (SCORES ? C - 1 : Lp);
-  if (m0 >= nq) return;
+  const uint32_t crank = AS_CL > 1 ? tc::cluster_ctarank() : 0;
+  constexpr uint16_t MC_MASK = (uint16_t)((1u << AS_CL) - 1);
+  if ((int)(blockIdx.x - crank) * 128 >= nq) return;  // the whole cluster is past the valid rows
+  // (a CTA whose own strip is past the valid rows but whose partner's is not runs the pipeline for the partner's
+  // sake -- its half of every B box -- and stores nothing: every store below is guarded by row < nq)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (nk + 127) / 128;
   if (n_tiles == 0) {
@@ -110,22 +133,24 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((tc::smem_u32(smem) & 1023u) != 0) __trap();  // swizzled tiles need a 1024-byte aligned base
   uint8_t* sA = smem;
-  uint8_t* sB = smem + AS_STAGE_OFF;  // 2 stages of AS_OPER
+  uint8_t* sB = smem + AS_STAGE_OFF;  // ring of AS_RING K-boxes
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AS_BAR_OFF);
   uint64_t* a_full = bars;
-  uint64_t* b_full = bars + 1;   // [2]
-  uint64_t* b_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;   // [2]
-  uint64_t* s_empty = bars + 7;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* b_full = bars + 1;              // [AS_RING]
+  uint64_t* b_empty = b_full + AS_RING;     // [AS_RING]
+  uint64_t* s_full = b_empty + AS_RING;     // [2]
+  uint64_t* s_empty = s_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + 2);
   float* xpose = reinterpret_cast<float*>(smem + AS_XPOSE_OFF);
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmMd);
     tc::mbar_init(a_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < AS_RING; ++i) {
       tc::mbar_init(&b_full[i], 1);
-      tc::mbar_init(&b_empty[i], 1);
+      tc::mbar_init(&b_empty[i], AS_CL);  // every CTA that reads the box releases it in every CTA that refills it
+    }
+    for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&s_full[i], 1);
       tc::mbar_init(&s_empty[i], AS_EPI_WARPS);
     }
@@ -134,6 +159,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t
   if (warp == 1) tc::tmem_alloc(tmem_slot, 256);
   tc::fence_before_sync();
   __syncthreads();
+  if (AS_CL > 1) tc::cluster_sync();  // the peer's barriers exist before anyone multicasts into them
   tc::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
 
@@ -141,12 +167,21 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t
     if (lane == 0) {
       tc::mbar_arrive_expect_tx(a_full, AS_OPER);
       for (int kb = 0; kb < 4; ++kb) tc::tma_load_2d(sA + kb * AS_TILE, &tmMd, a_full, kb * 64, s * Lp + m0);
+      int slot = 0;
+      uint32_t ph = 0;
       for (int j = 0; j < n_tiles; ++j) {
-        const int st = j & 1;
-        tc::mbar_wait(&b_empty[st], ((j >> 1) & 1) ^ 1);
-        tc::mbar_arrive_expect_tx(&b_full[st], AS_OPER);
-        for (int kb = 0; kb < 4; ++kb)
-          tc::tma_load_2d(sB + st * AS_OPER + kb * AS_TILE, &tmMd, &b_full[st], kb * 64, so * Lp + j * 128);
+        for (int kb = 0; kb < 4; ++kb) {
+          tc::mbar_wait(&b_empty[slot], ph ^ 1);
+          tc::mbar_arrive_expect_tx(&b_full[slot], AS_TILE);
+          if (AS_CL > 1) {
+            constexpr int SL = 128 / AS_CL;  // rows of the box this CTA fetches for everybody
+            tc::tma_load_2d_mc(sB + slot * AS_TILE + crank * SL * 128, &tmB, &b_full[slot], kb * 64,
+                               so * Lp + j * 128 + (int)crank * SL, MC_MASK);
+          } else {
+            tc::tma_load_2d(sB + slot * AS_TILE, &tmMd, &b_full[slot], kb * 64, so * Lp + j * 128);
+          }
+          if (++slot == AS_RING) { slot = 0; ph ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -155,29 +190,32 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t
     const uint64_t dA = tc::smem_desc_sw128(tc::smem_u32(sA), 0, 1024);
     const uint64_t dB0 = tc::smem_desc_sw128(tc::smem_u32(sB), 0, 1024);
     tc::mbar_wait(a_full, 0);
+    int slot = 0;
+    uint32_t bph = 0;
     for (int j = 0; j < n_tiles; ++j) {
       const int st = j & 1;
       const uint32_t ph = (j >> 1) & 1;
-      tc::mbar_wait(&b_full[st], ph);
       tc::mbar_wait(&s_empty[st], ph ^ 1);
-      tc::fence_after_sync();
-      const uint64_t dB = dB0 + (uint64_t)(st * (AS_OPER >> 4));
-      if (tc::elect_one()) {
-#pragma unroll
-        for (int kb = 0; kb < 4; ++kb)
+      for (int kb = 0; kb < 4; ++kb) {
+        tc::mbar_wait(&b_full[slot], bph);
+        tc::fence_after_sync();
+        const uint64_t dB = dB0 + (uint64_t)(slot * (AS_TILE >> 4));
+        if (tc::elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            tc::umma_ss(tmem + st * 128, dA + kb * (AS_TILE >> 4) + 2 * k, dB + kb * (AS_TILE >> 4) + 2 * k, idesc,
-                        (kb | k) != 0);
-        tc::umma_commit(&s_full[st]);
-        tc::umma_commit(&b_empty[st]);
+            tc::umma_ss(tmem + st * 128, dA + kb * (AS_TILE >> 4) + 2 * k, dB + 2 * k, idesc, (kb | k) != 0);
+          if (AS_CL > 1) tc::umma_commit_mc(&b_empty[slot], MC_MASK);
+          else tc::umma_commit(&b_empty[slot]);
+          if (kb == 3) tc::umma_commit(&s_full[st]);
+        }
+        __syncwarp();
+        if (++slot == AS_RING) { slot = 0; bph ^= 1; }
       }
-      __syncwarp();
     }
   } else {
     const int ew = warp - 2;
     const int quarter = warp & 3;   // TMEM lane quarter this warp may read
-    const int half = ew >> 2;       // 64-column half of every tile
+    const int half = ew >> 2;       // column part of every tile (AS_PCOLS columns)
     const int r = quarter * 32 + lane;
     const int row = m0 + r;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
@@ -191,58 +229,59 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t
     float a_pos = 0.f, a_cnt = 0.f, a_exp = 0.f;  // LOSS: this thread's row, this warp's columns
     const bool gt16 = LOSS && ((C - 1) % 16 == 0) && ((reinterpret_cast<uintptr_t>(ls.gt) & 15) == 0);
     float pf_z = 0.f, pf_lse = 0.f;  // prefetched z / lse of the next 32-column chunk (lane = column)
-    if (SCORES && half * 64 + lane < nk) {
-      pf_z = z[(size_t)so * Lp + half * 64 + lane];
-      pf_lse = lse_in[(size_t)so * Lp + half * 64 + lane];
+    if (SCORES && half * AS_PCOLS + lane < nk) {
+      pf_z = z[(size_t)so * Lp + half * AS_PCOLS + lane];
+      pf_lse = lse_in[(size_t)so * Lp + half * AS_PCOLS + lane];
     }
     for (int j = 0; j < n_tiles; ++j) {
       const int st = j & 1;
       tc::mbar_wait(&s_full[st], (j >> 1) & 1);
       tc::fence_after_sync();
       if constexpr (!SCORES) {
-        const int valid = nk - j * 128 - half * 64;  // valid keys among this thread's 64 columns
-        uint32_t sv[64];
-        tc::tmem_ld32(tmem + lane_base + st * 128 + half * 64, sv);
-        tc::tmem_ld32(tmem + lane_base + st * 128 + half * 64 + 32, sv + 32);
+        const int valid = nk - j * 128 - half * AS_PCOLS;  // valid keys among this thread's columns
+        uint32_t sv[AS_PCOLS];
+#pragma unroll
+        for (int c = 0; c < AS_PCOLS; c += 32) tc::tmem_ld32(tmem + lane_base + st * 128 + half * AS_PCOLS + c, sv + c);
         tc::tmem_ld_wait();
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&s_empty[st]);
-        if (valid < 64) {
+        if (valid < AS_PCOLS) {
 #pragma unroll
-          for (int i = 0; i < 64; ++i)
+          for (int i = 0; i < AS_PCOLS; ++i)
             if (i >= valid) sv[i] = 0xff800000u;
         }
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int i = 0; i < 64; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv[i]));
+        for (int i = 0; i < AS_PCOLS; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv[i]));
         const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         if (mx > -INFINITY) {  // (a fully masked half keeps its running state)
           const float m_new = fmaxf(m_run, mx);
           const float ml2 = m_new * 1.4426950408889634f;
           float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int i = 0; i < 64; ++i) rs4[i & 3] += ex2a(fmaf(__uint_as_float(sv[i]), 1.4426950408889634f, -ml2));
+          for (int i = 0; i < AS_PCOLS; ++i) rs4[i & 3] += ex2a(fmaf(__uint_as_float(sv[i]), 1.4426950408889634f, -ml2));
           l_run = l_run * ex2a((m_run - m_new) * 1.4426950408889634f) + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
           m_run = m_new;
         }
       } else {
 #pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < AS_PCOLS / 32; ++c) {
           uint32_t v[32];
-          tc::tmem_ld32(tmem + lane_base + st * 128 + half * 64 + c * 32, v);
-          const int cb = j * 128 + half * 64 + c * 32;  // first column of this chunk
+          tc::tmem_ld32(tmem + lane_base + st * 128 + half * AS_PCOLS + c * 32, v);
+          const int cb = j * 128 + half * AS_PCOLS + c * 32;  // first column of this chunk
           const int col = cb + lane;                    // this lane's column in the transposed phase
           // column constant of this chunk from the values fetched one chunk ago; fetch the next chunk's now
           // (an un-prefetched global load here cost ~1000 cycles per chunk on the critical path)
           float colconst = -INFINITY;                   // -inf: the column takes no part in the row max
           if (col < nk) colconst = lg_logsigmoid(pf_z) - pf_lse;
           {
-            const int ncol = (c == 0 ? cb + 32 : cb + 96) + lane;  // next chunk: same tile, or next tile
+            // next chunk of this warp: same tile, or the same part of the next tile
+            const int ncol = (c + 1 < AS_PCOLS / 32 ? cb + 32 : cb + 128 - (AS_PCOLS - 32)) + lane;
             if (ncol < nk) { pf_z = z[(size_t)so * Lp + ncol]; pf_lse = lse_in[(size_t)so * Lp + ncol]; }
           }
           tc::tmem_ld_wait();
-          if (c == 1) {
+          if (c == AS_PCOLS / 32 - 1) {
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&s_empty[st]);
@@ -296,7 +335,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t
           __syncwarp();
           // column phase (thread = column): every warp store is one contiguous 128-byte row segment
           float* out = LOSS ? nullptr : scores + ((size_t)blockIdx.y * R + m0 + quarter * 32) * C + col;
-          const int rows_here = min(32, nq - (m0 + quarter * 32));
+          const int rows_here = max(0, min(32, nq - (m0 + quarter * 32)));
           if (col < nk) {
             float cbest = -INFINITY;
             int cidx = 0;
@@ -330,14 +369,18 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t
       }
     }
     if constexpr (!SCORES) {
-      // combine the two column halves of a row: half 1 publishes (m, l), half 0 merges and writes
+      // combine the column parts of a row: parts 1.. publish (m, l), part 0 merges (in part order) and writes
       float* ex = xpose + (ew & 3) * (AS_XP + 32);
-      if (half == 1) { ex[2 * lane] = m_run; ex[2 * lane + 1] = l_run; }
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+      if (half > 0) { ex[(half - 1) * 64 + 2 * lane] = m_run; ex[(half - 1) * 64 + 2 * lane + 1] = l_run; }
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "n"(32 * AS_PARTS) : "memory");
       if (half == 0 && row < nq) {
-        const float m1 = ex[2 * lane], l1 = ex[2 * lane + 1];
-        const float m = fmaxf(m_run, m1);
-        const float l = l_run * ex2a((m_run - m) * 1.4426950408889634f) + l1 * ex2a((m1 - m) * 1.4426950408889634f);
+        float m = m_run;
+#pragma unroll
+        for (int pp = 0; pp < AS_PARTS - 1; ++pp) m = fmaxf(m, ex[pp * 64 + 2 * lane]);
+        float l = l_run * ex2a((m_run - m) * 1.4426950408889634f);
+#pragma unroll
+        for (int pp = 0; pp < AS_PARTS - 1; ++pp)
+          l += ex[pp * 64 + 2 * lane + 1] * ex2a((ex[pp * 64 + 2 * lane] - m) * 1.4426950408889634f);
         lse_out[(size_t)s * Lp + row] = m + logf(l);
       }
     } else {
@@ -356,6 +399,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap tmMd, int Lp, const int32_t
   }
   tc::fence_before_sync();
   __syncthreads();
+  if (AS_CL > 1) tc::cluster_sync();  // nobody retires while the peer may still multicast into its shared memory
   if (warp == 1) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem, 256);
@@ -413,10 +457,33 @@ __global__ void __launch_bounds__(256) assign_border_kernel(const float* __restr
   }
 }
 
-int make_md_map(CUtensorMap* tm, const __nv_bfloat16* md, int S, int Lp) {
+int make_md_map(CUtensorMap* tm, const __nv_bfloat16* md, int S, int Lp, int rows = 128) {
   const uint64_t d[2] = {256, (uint64_t)S * Lp}, sb[1] = {512};
-  const uint32_t box[2] = {64, 128};
+  const uint32_t box[2] = {64, (uint32_t)rows};
   return lg_make_tmap_bf16(tm, md, 2, d, sb, box);
+}
+
+// strips are launched as clusters of AS_CL along x (the grid is rounded up; a strip past Lp returns with its cluster
+// or, next to a valid partner, only fetches its half of the B boxes)
+template <typename Kern, typename... Args>
+int launch_strips(Kern kern, dim3 grid, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  grid.x = (grid.x + AS_CL - 1) / AS_CL * AS_CL;
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(AS_THREADS);
+  cfg.dynamicSmemBytes = AS_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = AS_CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args...);
+  if (e != cudaSuccess) return (int)e;
+  LG_LAUNCH_CHECK();
+  return LGB200_OK;
 }
 
 }  // namespace
@@ -428,11 +495,11 @@ int lg_tc_assign_lse(const __nv_bfloat16* md, int S, int Lp, const int32_t* lens
   if (rc) return rc;
   cudaError_t e = cudaFuncSetAttribute(tc_assign_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AS_SMEM);
   if (e != cudaSuccess) return (int)e;
-  dim3 grid(Lp / 128, S);
-  tc_assign_kernel<0><<<grid, AS_THREADS, AS_SMEM, st>>>(tm, Lp, lens, nullptr, nullptr, lse, 0, 0, nullptr, nullptr,
-                                                          nullptr, AsLoss{});
-  LG_LAUNCH_CHECK();
-  return LGB200_OK;
+  CUtensorMap tb;
+  if ((rc = make_md_map(&tb, md, S, Lp, 128 / AS_CL))) return rc;
+  return launch_strips(tc_assign_kernel<0>, dim3(Lp / 128, S), st, tm, tb, Lp, lens, (const float*)nullptr,
+                       (const float*)nullptr, lse, 0, 0, (float*)nullptr, (unsigned long long*)nullptr,
+                       (unsigned long long*)nullptr, AsLoss{});
 }
 
 int lg_tc_assign_scores(const __nv_bfloat16* md, const float* z, const float* lse, int B, int Lp,
@@ -451,10 +518,10 @@ int lg_tc_assign_scores(const __nv_bfloat16* md, const float* z, const float* ls
     if (e != cudaSuccess) return (int)e;
   }
   if (R > 1 && C > 1) {
-    dim3 grid((R - 1 + 127) / 128, B);
-    tc_assign_kernel<1><<<grid, AS_THREADS, AS_SMEM, st>>>(tm, Lp, lens, z, lse, nullptr, R, C, scores, best0, best1,
-                                                            AsLoss{});
-    LG_LAUNCH_CHECK();
+    CUtensorMap tb;
+    if ((rc = make_md_map(&tb, md, 2 * B, Lp, 128 / AS_CL))) return rc;
+    return launch_strips(tc_assign_kernel<1>, dim3((R - 1 + 127) / 128, B), st, tm, tb, Lp, lens, z, lse, (float*)nullptr, R,
+                         C, scores, best0, best1, AsLoss{});
   }
   return LGB200_OK;
 }
@@ -475,10 +542,11 @@ int lg_tc_assign_loss(const __nv_bfloat16* md, const float* z, const float* lse,
   if ((e = cudaMemsetAsync(row_cnt, 0, nrow, st)) != cudaSuccess) return (int)e;
   if ((e = cudaMemsetAsync(row_exp, 0, nrow, st)) != cudaSuccess) return (int)e;
   if (R > 1 && C > 1) {
-    dim3 grid((R - 1 + 127) / 128, B);
-    tc_assign_kernel<2><<<grid, AS_THREADS, AS_SMEM, st>>>(tm, Lp, lens, z, lse, nullptr, R, C, nullptr, best0, best1,
-                                                            AsLoss{gt, row_pos, row_cnt, row_exp});
-    LG_LAUNCH_CHECK();
+    CUtensorMap tb;
+    if ((rc = make_md_map(&tb, md, 2 * B, Lp, 128 / AS_CL))) return rc;
+    if ((rc = launch_strips(tc_assign_kernel<2>, dim3((R - 1 + 127) / 128, B), st, tm, tb, Lp, lens, z, lse, (float*)nullptr,
+                            R, C, (float*)nullptr, best0, best1, AsLoss{gt, row_pos, row_cnt, row_exp})))
+      return rc;
   }
   const int nmax = (R > C ? R : C) - 1;
   if (nmax > 0) {

@@ -6,13 +6,15 @@ from glue_factory_colon_b200 import _abi
 from glue_factory_colon_b200._abi import BF16, ptr
 lib = _abi.load(Path(os.environ["LGB200_LIB"]).resolve()) if os.environ.get("LGB200_LIB") else _abi.load()
 B, Lp = 64, 2048
-S, R, C = 2 * B, Lp + 1, Lp + 1
+S = 2 * B
+R = C = int(os.environ.get('ASSIGN_RC', Lp + 1))  # ASSIGN_RC=2048: rows of 8192 bytes (aligned stores), n = 2047
 g = torch.Generator(device="cuda").manual_seed(0)
 md = (torch.randn(S * Lp, 256, device="cuda", generator=g) * 0.25).to(torch.bfloat16)
 z = torch.randn(S * Lp, device="cuda", generator=g)
 lse = torch.empty(S * Lp, device="cuda")
 scores = torch.empty(B, R, C, device="cuda")
 ws = torch.empty(B * (R + C), device="cuda", dtype=torch.int64)
+print(f"R = C = {R}")
 m0 = torch.empty(B, Lp, device="cuda", dtype=torch.int64); m1 = torch.empty_like(m0)
 s0 = torch.empty(B, Lp, device="cuda"); s1 = torch.empty_like(s0)
 st = torch.cuda.current_stream().cuda_stream
