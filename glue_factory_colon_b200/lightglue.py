@@ -180,7 +180,6 @@ class LightGlue(nn.Module):
         # measurement hook (bench.py): a list to which the forward appends (start, end) CUDA events around every
         # self-attention launch, i.e. the dominant kernel timed inside the running step
         self._attn_events = None
-        self._warned_nograd = False
 
     # ---- reference-compatible helpers ------------------------------------------------
 
@@ -221,7 +220,8 @@ class LightGlue(nn.Module):
 
     # ---- loss (forward values) ------------------------------------------
 
-    def _log_assignment_of(self, lib, prec, d0, d1, layer: int, gt, token_layer: Optional[int] = None):
+    def _log_assignment_of(self, lib, prec, d0, d1, layer: int, gt, token_layer: Optional[int] = None,
+                           keep: Optional[dict] = None):
         """MatchAssignment `layer` applied to descriptors d0 [B,m,256] / d1 [B,n,256] (lightglue.py:279-288 as called
         from loss_params, :589-595) and the loss reductions on its output.  fp32: the forward's assignment kernels
         write scores [B,m+1,n+1], lgb200_loss_reduce reads them.  bf16: lgb200_assign_loss, the tcgen05 pass 2 with the
@@ -261,6 +261,8 @@ class LightGlue(nn.Module):
         check(lib.lgb200_rowdot(prec, ptr(x), ptr(a["m_w"]), ptr(a["m_b"]), S, Lp, ptr(lens), 0, ptr(z), st), "rowdot")
         check(lib.lgb200_assign_lse(prec, ptr(md), S, Lp, ptr(lens), ptr(lse), st), "assign_lse")
         R, C = m + 1, n + 1
+        if keep is not None:  # what the backward pass (train.AssignFn) and the training forward need
+            keep.update(z=z, lse=lse, Lp=Lp, lens=lens)
         if bf:
             rows = torch.empty(3, B, m, **f32)
             row_arg = torch.empty(B, m, device=dev, dtype=torch.int32)
@@ -278,6 +280,8 @@ class LightGlue(nn.Module):
                   "assign_scores")
             pos_sum, pos_cnt, row_exp, row_arg, col_arg = self._reduce(lib, scores, gt, st)
             dust0, dust1 = scores[:, :m, n], scores[:, m, :n]
+            if keep is not None:
+                keep["scores"] = scores
         logits = None
         if token_layer is not None:
             tk = W["token"][token_layer]
@@ -301,17 +305,23 @@ class LightGlue(nn.Module):
         return rows[0].sum(1), rows[1].sum(1), rows[2], row_arg, col_arg
 
     def loss(self, pred, data):
-        self._warn_no_autograd()
-        with torch.no_grad():
-            return self._loss_nograd(pred, data)
+        from . import train as _train
 
-    def _loss_nograd(self, pred, data):
-        """LightGlue.loss (lightglue.py:588-637) -> (losses, metrics) with the reference's keys, FORWARD VALUES ONLY:
-        the B200 kernels have no backward pass, so the returned tensors carry no autograd graph (use them for
-        validation, `do_evaluation` in the reference's train.py:100-170; optimisation needs the reference module).
+        r0 = pred["ref_descriptors0"]
+        if torch.is_grad_enabled() and (r0.requires_grad or _train.wants_grad(self)):
+            return self._loss_impl(pred, data, True)  # training step: the result carries an autograd graph
+        with torch.no_grad():
+            return self._loss_impl(pred, data, False)
+
+    def _loss_impl(self, pred, data, with_grad: bool):
+        """LightGlue.loss (lightglue.py:588-637) -> (losses, metrics) with the reference's keys.
         The dense [B,M+1,N+1] work -- MatchAssignment of every collected layer, the NLL sums of weight_loss
         (models/utils/losses.py:6-26), row_norm and the arg-maxima of TokenConfidence.loss (:82-95) -- runs in the
-        library's kernels; what is left here is arithmetic on [B] and [B,N] vectors."""
+        library's kernels; what is left here is arithmetic on [B] and [B,N] vectors.  with_grad: every layer's
+        MatchAssignment goes through train.AssignFn (fp32; backward = lgb200_assign_dsim + cuBLAS GEMMs), the vector
+        arithmetic below is tracked by autograd, and the token-confidence logits are a torch matrix-vector product on
+        the detached descriptors (lightglue.py:83-84), so `losses["total"].mean().backward()` reaches every parameter
+        the reference's does."""
         lib = _abi.load()
         conf = self.conf
         r0, r1 = pred["ref_descriptors0"], pred["ref_descriptors1"]
@@ -321,7 +331,7 @@ class LightGlue(nn.Module):
         B, N, m, _ = r0.shape
         n = r1.shape[2]
         prec = self._precision()
-        if prec == F32X3:  # the loss reductions of the fp32 mode run in the CUDA-core fp32 kernels
+        if prec == F32X3 or with_grad:  # the loss reductions of the fp32 mode run in the CUDA-core fp32 kernels
             prec = F32
         st = torch.cuda.current_stream(dev).cuda_stream
         L = conf.n_layers
@@ -333,8 +343,23 @@ class LightGlue(nn.Module):
         bal = float(conf.loss.nll_balancing)
 
         def nll_of(layer_idx, mod, token_layer=None):  # weight_loss + NLLLoss.forward (losses.py:6-26, :44-60)
-            pos_sum, pos_cnt, _, row_arg, col_arg, dust0, dust1, logits = self._log_assignment_of(
-                lib, prec, r0[:, layer_idx], r1[:, layer_idx], mod, gt, token_layer)
+            if with_grad:
+                from .train import AssignFn
+
+                a = self.log_assignment[mod]
+                d0_, d1_ = r0[:, layer_idx], r1[:, layer_idx]
+                pos_sum, dust0, dust1, pos_cnt, _, row_arg, col_arg = AssignFn.apply(
+                    self, mod, gt, d0_, d1_, a.final_proj.weight, a.final_proj.bias, a.matchability.weight,
+                    a.matchability.bias)
+                logits = None
+                if token_layer is not None:  # TokenConfidence.loss reads detached descriptors (lightglue.py:83-84)
+                    tk = self.token_confidence[token_layer].token[0]
+                    lin = torch.nn.functional.linear
+                    logits = (lin(d0_.detach().float(), tk.weight, tk.bias).squeeze(-1),
+                              lin(d1_.detach().float(), tk.weight, tk.bias).squeeze(-1))
+            else:
+                pos_sum, pos_cnt, _, row_arg, col_arg, dust0, dust1, logits = self._log_assignment_of(
+                    lib, prec, r0[:, layer_idx], r1[:, layer_idx], mod, gt, token_layer)
             num_pos = pos_cnt.clamp(min=1.0)
             nll_pos = -pos_sum / num_pos
             nll_neg = (-(dust0 * neg0).sum(-1) - (dust1 * neg1).sum(-1)) / (num_neg0 + num_neg1)
@@ -343,12 +368,12 @@ class LightGlue(nn.Module):
 
         nll, nll_pos, nll_neg, num_pos, _, _, _ = nll_of(-1, L - 1)
         losses = {
-            "total": nll, "last": nll.clone(), "assignment_nll": nll, "nll_pos": nll_pos, "nll_neg": nll_neg,
+            "total": nll, "last": nll.clone().detach(), "assignment_nll": nll, "nll_pos": nll_pos, "nll_neg": nll_neg,
             "num_matchable": num_pos, "num_unmatchable": (num_neg0 + num_neg1) / 2.0,
         }
         if self.training:
             losses["confidence"] = torch.zeros_like(nll)
-        la_pred = pred["log_assignment"].to(torch.float32).contiguous()
+        la_pred = pred["log_assignment"].detach().to(torch.float32).contiguous()
         _, _, row_exp_f, row_arg_f, col_arg_f = self._reduce(lib, la_pred, None, st)
         losses["row_norm"] = row_exp_f.mean(1)  # lightglue.py:606
         bce = torch.nn.functional.binary_cross_entropy_with_logits
@@ -489,24 +514,79 @@ class LightGlue(nn.Module):
             buf = self._snap_buf = torch.zeros(max(rows, 16), max(cols, 64), dtype=torch.int32).pin_memory()
         return buf[:rows, :cols]
 
-    def _warn_no_autograd(self) -> None:
-        """The kernels have no backward pass: a training loop that expects gradients (train.py of the reference selects
-        the matcher by name and calls loss.backward()) must be told, once, instead of silently training nothing."""
-        if self._warned_nograd or not (self.training and torch.is_grad_enabled()):
-            return
-        if any(p.requires_grad for p in self.parameters()):
-            import warnings
-
-            warnings.warn(
-                "glue_factory_colon_b200.LightGlue computes forward values only: outputs and losses carry no autograd "
-                "graph (conf.checkpointed is ignored).  Use it for inference / validation; optimisation needs the "
-                "reference module.", RuntimeWarning, stacklevel=3)
-            self._warned_nograd = True
-
     def forward(self, data: dict) -> dict:
-        self._warn_no_autograd()
+        from . import train as _train
+
+        if _train.wants_grad(self, data):
+            return self._forward_train(data)
         with torch.no_grad():
             return self._forward_nograd(data)
+
+    def _forward_train(self, data: dict) -> dict:
+        """Training step (module in training mode, autograd on): the transformer stack runs through
+        train.TransformerFn -- fp32 kernels forward, hand-written backward kernels + cuBLAS GEMMs backward -- so that
+        `ref_descriptors0/1` carry an autograd graph to the descriptors and to every parameter
+        (lightglue.py:484-498, :546-547).  conf.checkpointed is implied: only the two block inputs of every layer are
+        kept, the rest is recomputed in the backward pass.  The matches / log_assignment of the last layer are
+        computed without a graph (the reference's loss reads pred["log_assignment"] detached, :606, :625-630)."""
+        from . import train as _train
+
+        for key in self.required_data_keys:
+            assert key in data, f"Missing key {key} in data"
+        conf = self.conf
+        kpts0, kpts1 = data["keypoints0"], data["keypoints1"]
+        if not kpts0.is_cuda:
+            raise _abi.LightGlueB200Error(
+                "glue_factory_colon_b200.LightGlue runs on CUDA (sm_100a) tensors only; there is no CPU path")
+        if "num_keypoints0" in data or "num_keypoints1" in data:
+            raise NotImplementedError("per-pair keypoint counts are an inference extension; train on full batches")
+        lib = _abi.load()
+        dev = kpts0.device
+        B, m, _ = kpts0.shape
+        n = kpts1.shape[1]
+
+        def size_of(v):
+            sz = data[v].get("image_size") if v in data else None
+            if sz is None:
+                return None
+            if not isinstance(sz, torch.Tensor):
+                sz = torch.tensor(sz)
+            return sz.to(device=dev, dtype=torch.float32).reshape(-1, 2).expand(B, 2).contiguous()
+
+        def kpts_of(idx, k):
+            k = k.detach().to(torch.float32)
+            if conf.add_scale_ori:  # lightglue.py:436-454
+                sc, ori = data[f"scales{idx}"], data[f"oris{idx}"]
+                sc = sc if sc.dim() == 3 else sc[..., None]
+                ori = ori if ori.dim() == 3 else ori[..., None]
+                k = torch.cat([k, sc.to(k), ori.to(k)], -1)
+            return k.contiguous()
+
+        geom = {"k0": kpts_of(0, kpts0), "k1": kpts_of(1, kpts1), "size0": size_of("view0"), "size1": size_of("view1")}
+        desc0 = data["descriptors0"].to(torch.float32)
+        desc1 = data["descriptors1"].to(torch.float32)
+        assert desc0.shape[-1] == conf.input_dim and desc1.shape[-1] == conf.input_dim
+        params = [p for _, p in _train.transformer_params(self)]
+        r0, r1 = _train.TransformerFn.apply(self, geom, desc0, desc1, *params)
+        L = conf.n_layers
+        with torch.no_grad():
+            keep: Dict = {}
+            self._log_assignment_of(lib, F32, r0[:, -1], r1[:, -1], L - 1, None, keep=keep)
+            scores = keep["scores"]
+            m0 = torch.empty(B, m, device=dev, dtype=torch.int64)
+            m1 = torch.empty(B, n, device=dev, dtype=torch.int64)
+            ms0 = torch.empty(B, m, device=dev, dtype=torch.float32)
+            ms1 = torch.empty(B, n, device=dev, dtype=torch.float32)
+            fm_ws = torch.empty(B * (m + n + 2), device=dev, dtype=torch.int64)
+            st = torch.cuda.current_stream(dev).cuda_stream
+            check(lib.lgb200_filter_matches(ptr(scores), B, m + 1, n + 1, ptr(keep["lens"]),
+                                            float(conf.filter_threshold), None, None, 0, m, n, ptr(m0), ptr(m1),
+                                            ptr(ms0), ptr(ms1), ptr(fm_ws), 0, st), "filter_matches")
+        return {
+            "matches0": m0, "matches1": m1, "matching_scores0": ms0, "matching_scores1": ms1,
+            "ref_descriptors0": r0, "ref_descriptors1": r1, "log_assignment": scores,
+            "prune0": torch.full((B, m), float(L), device=dev), "prune1": torch.full((B, n), float(L), device=dev),
+        }
 
     def _forward_nograd(self, data: dict) -> dict:
         for key in self.required_data_keys:

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define LGB200_ABI_VERSION 4
+#define LGB200_ABI_VERSION 5
 
 enum { LGB200_F32 = 0, LGB200_BF16 = 1, LGB200_F32X3 = 2 };
 
@@ -276,6 +276,43 @@ int lgb200_x3_assign_lse(const float* sim, int B, int Lp, const int32_t* lens, i
 /* scores [B][R][C] (lightglue.py:257-269) from sim, z (matchability logits [S*Lp]) and lse. */
 int lgb200_x3_assign_scores(const float* sim, const float* z, const float* lse, int B, int Lp,
                             const int32_t* lens, int R, int C, float* scores, void* stream);
+
+/* ---- training path: backward kernels -------------------------------------
+ * The reference trains through this path with autograd (train.py -> LightGlue.forward, lightglue.py:484-498, and
+ * LightGlue.loss, :588-637).  fp32 (the layouts of LGB200_F32).  Plain GEMMs of the backward pass (dX = dY.W,
+ * dW = dY^T.X) are cuBLAS calls on the host side (glue_factory_colon_b200/train.py); the fused forward ops have
+ * these fused backward ops:
+ *
+ * lgb200_attention_bwd: backward of lgb200_attention (flash-style: the score matrix is recomputed tile by tile,
+ *   nothing N x M is stored).  Q, K, V [S,4,Lp,64] as given to the forward (Q pre-scaled, log2 domain), ctx / dctx
+ *   [S,Lp,256] = forward output and its gradient.  dQ, dK, dV [S,4,Lp,64]: gradients w.r.t. the given (scaled) Q,
+ *   K and V; with kv_xor = 1, dK / dV of sequence s collect the queries of sequence s ^ 1.  Rows >= lens are zero.
+ *   workspace: 2 * S * 4 * Lp floats (row log-sum-exp and <dO, O>).
+ * lgb200_heads_bwd: backward of the HEADS epilogue of lgb200_linear (unflatten + rotary + scale, lightglue.py:43-50,
+ *   157-161, 196-201).  n_parts = 3: out [T,768] = [scale0 R^T dQ | scale1 R^T dK | scale2 dV] in the packed column
+ *   order part*256 + head*64 + d, R^T = inverse rotation by the angles in rot [T,64]; dtheta [T,32] (nullable) +=
+ *   the gradient of the rotary angles summed over heads and q / k (accumulates over layers; feeds posenc.Wr).
+ *   n_parts = 2 (cross block): out [T,512] = [scale0 (dQ + dK) | scale1 dV]; Q, K, rot, dtheta unused.
+ * lgb200_ln_gelu_bwd: backward of GELU(LayerNorm(h) gamma + beta) on rows of 512 (lightglue.py:144-149): h = the
+ *   pre-LayerNorm activations, da = gradient of the GELU output; dh = gradient of h, act (nullable) = the GELU
+ *   output recomputed (the A operand of d W2); partials [n_partials][1024] receives per-CTA column sums of
+ *   (d gamma | d beta) -- the caller adds the n_partials rows.  Rows >= lens get zeros.
+ * lgb200_assign_dsim: backward of sigmoid_log_double_softmax (lightglue.py:257-269) w.r.t. the similarity, for a
+ *   loss that is linear in log_assignment (NLLLoss, losses.py:6-26): sim [B,m,n] is replaced in place by
+ *   2 g_pos[b] gt - r[b,i] exp(sim - lse0[i]) - c[b,j] exp(sim - lse1[j]); lse as written by lgb200_assign_lse
+ *   ([S,Lp]: rows of image 0, columns of image 1), r / c = g_pos times the row / column sums of gt. */
+int lgb200_attention_bwd(const float* Q, const float* K, const float* V, const float* ctx, const float* dctx,
+                         int S, int Lp, const int32_t* lens, int kv_xor, float* dQ, float* dK, float* dV,
+                         float* workspace, void* stream);
+int lgb200_heads_bwd(const float* dQ, const float* dK, const float* dV, const float* Q, const float* K,
+                     const float* rot, int S, int Lp, const int32_t* lens, int n_parts, float scale0,
+                     float scale1, float scale2, float* out, float* dtheta, void* stream);
+int lgb200_ln_gelu_bwd(const float* h, const float* gamma, const float* beta, const float* da, int T, int Lp,
+                       const int32_t* lens, float* dh, float* act, float* partials, int n_partials,
+                       void* stream);
+int lgb200_assign_dsim(float* sim, int B, int m, int n, const float* lse, int Lp,
+                       const uint8_t* gt_assignment, const float* g_pos, const float* r, const float* c,
+                       void* stream);
 
 #ifdef __cplusplus
 }

@@ -43,8 +43,9 @@ def nll_terms(la: torch.Tensor, data: dict, balancing: float = 0.5) -> Dict[str,
 def confidence_loss(sd, i: int, desc0, desc1, la_now, la_final) -> torch.Tensor:
     """lightglue.py:82-95: BCE of the token logits against "this layer's arg-max already equals the final one"."""
     w, b = sd[f"token_confidence.{i}.token.0.weight"], sd[f"token_confidence.{i}.token.0.bias"]
-    logit0 = F.linear(desc0, w, b).squeeze(-1)
-    logit1 = F.linear(desc1, w, b).squeeze(-1)
+    logit0 = F.linear(desc0.detach(), w, b).squeeze(-1)  # lightglue.py:83-84: the heads do not train the descriptors
+    logit1 = F.linear(desc1.detach(), w, b).squeeze(-1)
+    la_now, la_final = la_now.detach(), la_final.detach()
     c0 = la_final[:, :-1, :].max(-1).indices == la_now[:, :-1, :].max(-1).indices
     c1 = la_final[:, :, :-1].max(-2).indices == la_now[:, :, :-1].max(-2).indices
     bce = F.binary_cross_entropy_with_logits
@@ -70,12 +71,17 @@ def matcher_metrics(pred: dict, data: dict) -> Dict[str, torch.Tensor]:
     return {"match_recall": rec, "match_precision": prec, "accuracy": acc, "average_precision": ap}
 
 
-def loss(sd: Dict[str, torch.Tensor], conf: dict, pred: dict, data: dict, training: bool):
-    """lightglue.py:588-637.  pred: ref_descriptors0/1 [B, N, n, 256], log_assignment, matches0, matching_scores0."""
+def loss(sd: Dict[str, torch.Tensor], conf: dict, pred: dict, data: dict, training: bool, keep_graph: bool = False):
+    """lightglue.py:588-637.  pred: ref_descriptors0/1 [B, N, n, 256], log_assignment, matches0, matching_scores0.
+    keep_graph: sd / pred are used as given (CPU tensors, any float dtype), so that torch autograd differentiates the
+    restatement -- the checker of the hand-written backward pass (tests/test_gpu_grad.py)."""
     c = {**lg.DEFAULT_CONF, **{k: v for k, v in conf.items() if k in lg.DEFAULT_CONF}}
     lc = {"gamma": 1.0, "fn": "nll", "nll_balancing": 0.5, **conf.get("loss", {})}
-    sd = {k: v.detach().cpu().float() for k, v in sd.items()}
-    r0, r1 = pred["ref_descriptors0"].float().cpu(), pred["ref_descriptors1"].float().cpu()
+    if keep_graph:
+        r0, r1 = pred["ref_descriptors0"], pred["ref_descriptors1"]
+    else:
+        sd = {k: v.detach().cpu().float() for k, v in sd.items()}
+        r0, r1 = pred["ref_descriptors0"].float().cpu(), pred["ref_descriptors1"].float().cpu()
     N = r0.shape[1]
     n_layers = c["n_layers"]
 
@@ -85,10 +91,10 @@ def loss(sd: Dict[str, torch.Tensor], conf: dict, pred: dict, data: dict, traini
 
     la_last = la_of(-1)
     terms = nll_terms(la_last, data, lc["nll_balancing"])
-    losses = {"total": terms["assignment_nll"].clone(), "last": terms["assignment_nll"].clone(), **terms}
+    losses = {"total": terms["assignment_nll"].clone(), "last": terms["assignment_nll"].clone().detach(), **terms}
     if training:
         losses["confidence"] = torch.zeros_like(losses["total"])
-    la_pred = pred["log_assignment"].float().cpu()
+    la_pred = pred["log_assignment"].detach().to(r0.dtype).cpu()
     losses["row_norm"] = la_pred.exp()[:, :-1].sum(2).mean(1)
     sum_w = 1.0
     for i in range(N - 1):
@@ -105,23 +111,24 @@ def loss(sd: Dict[str, torch.Tensor], conf: dict, pred: dict, data: dict, traini
     return losses, metrics
 
 
-def forward_collect(sd, conf: dict, data: dict) -> dict:
+def forward_collect(sd, conf: dict, data: dict, keep_graph: bool = False, dtype=torch.float32) -> dict:
     """Training-mode forward (lightglue.py:483-498, :541-553): all layers' descriptors are collected, no early exit /
-    pruning.  Returns the batched prediction dict (full-size pairs only)."""
+    pruning.  Returns the batched prediction dict (full-size pairs only).  keep_graph: sd is used as given."""
     outs: List[dict] = []
     traces = []
-    sd_c = {k: v.detach().cpu() for k, v in sd.items()}
+    sd_c = sd if keep_graph else {k: v.detach().cpu() for k, v in sd.items()}
     B = data["keypoints0"].shape[0]
     conf_t = {**conf, "depth_confidence": -1, "width_confidence": -1}
     size0 = data.get("view0", {}).get("image_size")
     size1 = data.get("view1", {}).get("image_size")
+    k0, k1 = lg._kpts_with_scale_ori(data, 0, conf), lg._kpts_with_scale_ori(data, 1, conf)  # lightglue.py:436-454
     for b in range(B):
         tr: dict = {}
         outs.append(
             lg.forward_pair(
-                sd_c, conf_t, data["keypoints0"][b], data["keypoints1"][b], data["descriptors0"][b],
+                sd_c, conf_t, k0[b], k1[b], data["descriptors0"][b],
                 data["descriptors1"][b], None if size0 is None else size0[b].float(),
-                None if size1 is None else size1[b].float(), trace=tr,
+                None if size1 is None else size1[b].float(), dtype=dtype, trace=tr,
             )
         )
         traces.append(tr)

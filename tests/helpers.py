@@ -87,3 +87,20 @@ def load_c1_fixture(path):
         "view1": {"image_size": torch.tensor([fx["image_size1"]])},
     }
     return fx, model, data
+
+
+def oracle_training_step(sd, conf, data, dtype=torch.float32):
+    """One training step through the CPU oracle with torch autograd (test infrastructure): forward in training mode,
+    LightGlue.loss, `total.mean().backward()`.  Returns (total [B], {state-dict name: gradient}, d descriptors0,
+    d descriptors1)."""
+    from oracle import loss_oracle
+
+    leaves = {k: v.detach().cpu().to(dtype).clone().requires_grad_(True) for k, v in sd.items()
+              if v.is_floating_point() and k != "confidence_thresholds"}
+    d = dict(data)
+    d["descriptors0"] = data["descriptors0"].detach().cpu().to(dtype).clone().requires_grad_(True)
+    d["descriptors1"] = data["descriptors1"].detach().cpu().to(dtype).clone().requires_grad_(True)
+    pred = loss_oracle.forward_collect(leaves, conf, d, keep_graph=True, dtype=dtype)
+    losses, _ = loss_oracle.loss(leaves, conf, pred, d, True, keep_graph=True)
+    losses["total"].mean().backward()
+    return losses["total"].detach(), {k: v.grad for k, v in leaves.items()}, d["descriptors0"].grad, d["descriptors1"].grad

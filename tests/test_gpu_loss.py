@@ -49,17 +49,24 @@ def test_loss_reduce_against_torch():
     assert lib.lgb200_loss_reduce(None, B, R, C, None, None, None, None, None, None, _stream()) == -2
 
 
+@pytest.mark.parametrize("grad", [False, True], ids=["values", "autograd"])
 @pytest.mark.parametrize("name", ["loss_train", "loss_train_gamma", "loss_eval"])
-def test_forward_and_loss_fp32_against_reference_golden(name, golden_dir):
+def test_forward_and_loss_fp32_against_reference_golden(name, grad, golden_dir):
+    """grad=False: the forward-values path (torch.no_grad(), e.g. validation inside the reference's training loop);
+    grad=True: the training path of glue_factory_colon_b200/train.py (same values, with an autograd graph)."""
     fx = torch.load(golden_dir / f"{name}.pt", weights_only=False)
     model = _model(fx, "fp32")
     data = to_device(make_pairs(with_gt=True, **fx["data_kwargs"]), DEV)
-    pred = model(data)
+    with torch.set_grad_enabled(grad):
+        pred = model(data)
+        losses, metrics = model.loss(pred, data)
+    assert pred["ref_descriptors0"].requires_grad == (grad and fx["training"])
+    pred = {k: v.detach() for k, v in pred.items()}
+    losses = {k: v.detach() for k, v in losses.items()}
     assert tuple(pred["ref_descriptors0"].shape) == fx["ref_desc_shape"]
     for i, am in enumerate(fx["ref_desc_absmean"]):
         assert abs(float(pred["ref_descriptors0"][:, i].abs().mean()) - am) < 1e-4 * am
     torch.testing.assert_close(pred["log_assignment"].cpu(), fx["pred"]["log_assignment"], atol=1e-3, rtol=0)
-    losses, metrics = model.loss(pred, data)
     assert set(losses) == set(fx["losses"])
     for k, v in fx["losses"].items():
         torch.testing.assert_close(losses[k].reshape(-1).cpu(), v.reshape(-1).float(), atol=5e-4, rtol=1e-4,
@@ -85,9 +92,10 @@ def test_forward_and_loss_bf16_within_the_bf16_envelope(golden_dir):
     fx = torch.load(golden_dir / "loss_train.pt", weights_only=False)
     model = _model(fx, "bf16")
     data = to_device(make_pairs(with_gt=True, **fx["data_kwargs"]), DEV)
-    pred = model(data)
+    with torch.no_grad():  # (with autograd on, a training-mode forward takes the fp32 training path)
+        pred = model(data)
+        losses, metrics = model.loss(pred, data)
     assert tuple(pred["ref_descriptors0"].shape) == fx["ref_desc_shape"] and pred["ref_descriptors0"].dtype == torch.bfloat16
-    losses, metrics = model.loss(pred, data)
     assert metrics == {} and set(losses) == set(fx["losses"])
     for k in ("total", "last", "nll_pos", "nll_neg", "confidence", "row_norm"):
         torch.testing.assert_close(losses[k].cpu(), fx["losses"][k].float(), atol=0.05, rtol=0.02, msg=lambda m: f"{k}: {m}")

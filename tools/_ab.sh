@@ -1,2 +1,2 @@
 cd /root/repo
-for rc in 2049 2048 2045; do ASSIGN_RC=$rc timeout 120 python tools/assign_bench.py 2>&1 | grep -E "R = C|pass 2"; done
+timeout 900 python -m pytest tests/test_gpu_grad.py tests/test_gpu_loss.py -m gpu -q > gpurun_out/gputest_grad.log 2>&1; tail -40 gpurun_out/gputest_grad.log
