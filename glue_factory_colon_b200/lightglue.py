@@ -526,8 +526,8 @@ class LightGlue(nn.Module):
         """Training step (module in training mode, autograd on): the transformer stack runs through
         train.TransformerFn -- fp32 kernels forward, hand-written backward kernels + cuBLAS GEMMs backward -- so that
         `ref_descriptors0/1` carry an autograd graph to the descriptors and to every parameter
-        (lightglue.py:484-498, :546-547).  conf.checkpointed is implied: only the two block inputs of every layer are
-        kept, the rest is recomputed in the backward pass.  The matches / log_assignment of the last layer are
+        (lightglue.py:484-498, :546-547).  conf.checkpointed (:485-494) selects recomputation of the attention
+        operands in the backward pass instead of keeping them.  The matches / log_assignment of the last layer are
         computed without a graph (the reference's loss reads pred["log_assignment"] detached, :606, :625-630)."""
         from . import train as _train
 

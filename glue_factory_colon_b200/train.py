@@ -5,10 +5,11 @@ layer's descriptors in training mode, :588-637 turns them into the deep-supervis
 `loss.backward()`).  Here the same contract is met by two `torch.autograd.Function`s whose backward is written by hand:
 
   * `TransformerFn`  descriptors (+ every transformer / posenc / input_proj parameter) -> ref_descriptors0/1
-    [B, n_layers, N, 256].  Forward = the library's fp32 kernels (lgb200_linear, lgb200_attention, ...), keeping only
-    the two block inputs of every layer (2 x T x 256 floats per layer); backward recomputes a layer's q / k / v /
-    context / message / pre-LayerNorm activations with the same kernels ("checkpointed" by construction, cf.
-    conf.checkpointed, lightglue.py:485-494) and runs the hand-written backward kernels of csrc/lg_bwd.cu:
+    [B, n_layers, N, 256].  Forward = the library's fp32 kernels (lgb200_linear; attention in the fp32-accurate
+    tensor-core mode), keeping the two block inputs of every layer plus -- unless conf.checkpointed
+    (lightglue.py:485-494) -- q / k / v / context / message; with conf.checkpointed those are recomputed in the
+    backward pass with the same kernels.  The pre-LayerNorm activations are always recomputed (one GEMM).  Backward =
+    the hand-written kernels of csrc/lg_bwd.cu:
     flash-attention backward (lgb200_attention_bwd), rotary / head-split backward incl. the gradient of the rotary
     angles (lgb200_heads_bwd), GELU . LayerNorm backward (lgb200_ln_gelu_bwd).
   * `AssignFn`       MatchAssignment of one layer (lightglue.py:272-288) reduced to what NLLLoss reads
@@ -22,18 +23,20 @@ kernels are inference kernels); CPU tensors raise as everywhere else in this pac
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Tuple
 
 import torch
 from torch import nn
 
 from . import _abi
-from ._abi import EPI_HEADS, EPI_LN_GELU, EPI_ROWMAJOR, F32, check, ptr
+from ._abi import EPI_HEADS, EPI_LN_GELU, EPI_ROWMAJOR, F32, F32X3, check, ptr
 
 LOG2E = 1.4426950408889634
 Q_SCALE = LOG2E / math.sqrt(64.0)   # folded into q: the attention kernels work in the log2 domain
 C_SCALE = math.sqrt(Q_SCALE)        # cross block: to_qk feeds both sides (lightglue.py:208)
 N_PARTIALS = 296                    # CTAs of lgb200_ln_gelu_bwd (2 per SM)
+_SIMT_ATTN = os.environ.get("LGB200_TRAIN_SIMT_ATTN", "0") == "1"
 # packed Wqkv row r holds reference row _PERM[r] (lightglue.py:158: head*192 + d*3 + part -> part*256 + head*64 + d)
 _PERM = torch.arange(768).view(4, 64, 3).permute(2, 0, 1).reshape(-1)
 
@@ -69,9 +72,28 @@ class _Kern:
                                      None, ptr(rot), None, n_rot, ptr(outp[0]), ptr(outp[1]), ptr(outp[2]), ptr(gamma),
                                      ptr(beta), self.st), "lgb200_linear")
 
+    def split(self, t):
+        """fp32 -> split-fp16 planes [2][n] (x * 64 = hi + lo), the operand format of the LGB200_F32X3 kernels."""
+        out = torch.empty(2, t.numel(), device=self.dev, dtype=torch.float16)
+        check(self.lib.lgb200_split_rows(ptr(t), t.numel(), ptr(out), self.st), "lgb200_split_rows")
+        return out
+
     def attention(self, q, k, v, kv_xor, ctx):
-        check(self.lib.lgb200_attention(F32, ptr(q), ptr(k), ptr(v), self.S, self.Lp, ptr(self.lens), kv_xor, ptr(ctx),
+        """Forward attention on the tensor cores in the fp32-accurate mode (lg_x3_attn.cu: split-fp16 operands, three
+        tcgen05 MMAs per product, fp32 softmax) -- 12x faster than the CUDA-core fp32 kernel at 2048 keypoints, same
+        1e-6-level agreement with float64.  LGB200_TRAIN_SIMT_ATTN=1 selects the CUDA-core kernel."""
+        if _SIMT_ATTN:
+            check(self.lib.lgb200_attention(F32, ptr(q), ptr(k), ptr(v), self.S, self.Lp, ptr(self.lens), kv_xor, ptr(ctx),
+                                            self.st), "lgb200_attention")
+            return
+        qp = self.split(q)
+        kp = qp if k is q else self.split(k)
+        vp = self.split(v)
+        cp = torch.zeros(2, self.T, 256, device=self.dev, dtype=torch.float16)
+        check(self.lib.lgb200_attention(F32X3, ptr(qp), ptr(kp), ptr(vp), self.S, self.Lp, ptr(self.lens), kv_xor, ptr(cp),
                                         self.st), "lgb200_attention")
+        torch.add(cp[0].float(), cp[1].float(), out=ctx)
+        ctx.mul_(1.0 / 64.0)
 
     def attention_bwd(self, q, k, v, ctx, dctx, kv_xor):
         dq, dk, dv = self.empty(self.T * 256), self.empty(self.T * 256), self.empty(self.T * 256)
@@ -218,18 +240,22 @@ class TransformerFn(torch.autograd.Function):
         for img, kk, cnt, sz in ((0, geom["k0"], m, geom["size0"]), (1, geom["k1"], n, geom["size1"])):
             check(k.lib.lgb200_posenc(ptr(kk), B, cnt, kdim, ptr(sz), ptr(W["wr"]), ptr(k.lens), img, k.Lp, ptr(rot),
                                       None, k.st), "lgb200_posenc")
-        xs_in, xs_mid, outs = [], [], []
+        # conf.checkpointed (lightglue.py:485-494): keep only the block inputs and recompute q / k / v / context /
+        # message in the backward pass (26 x T KB per layer less); otherwise they are kept, as autograd would
+        keep = not bool(model.conf.checkpointed)
+        xs_in, xs_mid, outs, kept = [], [], [], []
         for i in range(L):
             w = W["layers"][i]
             xs_in.append(x)
-            _, _, _, _, msg = _self_attend(k, w, x, rot)
-            x = _ffn(k, w, "s", x, msg)
+            sa = _self_attend(k, w, x, rot)
+            x = _ffn(k, w, "s", x, sa[-1])
             xs_mid.append(x)
-            _, _, _, msg = _cross_attend(k, w, x)
-            x = _ffn(k, w, "c", x, msg)
+            ca = _cross_attend(k, w, x)
+            x = _ffn(k, w, "c", x, ca[-1])
             outs.append(x)
+            kept.append((sa, ca) if keep else None)
         ctx.k, ctx.W, ctx.geom, ctx.model = k, W, geom, model
-        ctx.xs_in, ctx.xs_mid, ctx.rot, ctx.xin = xs_in, xs_mid, rot, xin
+        ctx.xs_in, ctx.xs_mid, ctx.rot, ctx.xin, ctx.kept = xs_in, xs_mid, rot, xin, kept
         ctx.keys = [key for key, _ in transformer_params(model)]
         r0 = torch.stack([k.unpack(o)[0] for o in outs], 1)
         r1 = torch.stack([k.unpack(o)[1] for o in outs], 1)
@@ -248,7 +274,7 @@ class TransformerFn(torch.autograd.Function):
             dx = dx + k.pack2(g0[:, i], g1[:, i])
             x_in, x_mid = ctx.xs_in[i], ctx.xs_mid[i]
             # ---- cross block (lightglue.py:193-222) ----
-            qk, v, c, msg = _cross_attend(k, w, x_mid)
+            qk, v, c, msg = ctx.kept[i][1] if ctx.kept[i] is not None else _cross_attend(k, w, x_mid)
             dxa, dmsg, g = _ffn_bwd(k, w, "c", x_mid, msg, dx)
             for name, val in g.items():
                 grads[(i, name)] = val
@@ -261,7 +287,8 @@ class TransformerFn(torch.autograd.Function):
             grads[(i, "cqk_b")], grads[(i, "cv_b")] = gb[:256], gb[256:]
             dxm = dx + dxa + dqv @ w["cqv_w"]
             # ---- self block (lightglue.py:151-164) ----
-            q, kk, v, c, msg = _self_attend(k, w, x_in, rot)
+            q, kk, v, c, msg = ctx.kept[i][0] if ctx.kept[i] is not None else _self_attend(k, w, x_in, rot)
+            ctx.kept[i] = None
             dxa, dmsg, g = _ffn_bwd(k, w, "s", x_in, msg, dxm)
             for name, val in g.items():
                 grads[(i, name)] = val

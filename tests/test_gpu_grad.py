@@ -170,11 +170,12 @@ def _training_step(model, data):
     return pred, losses, metrics
 
 
+@pytest.mark.parametrize("checkpointed", [False, True], ids=["kept", "recompute"])
 @pytest.mark.parametrize("name", ["grad_train", "grad_train_sift"])
-def test_training_step_gradients_against_oracle_autograd_and_reference_golden(name, golden_dir):
+def test_training_step_gradients_against_oracle_autograd_and_reference_golden(name, checkpointed, golden_dir):
     fx = torch.load(golden_dir / f"{name}.pt", weights_only=False)
     torch.manual_seed(fx["seed"])
-    model = LightGlue(fx["conf"])
+    model = LightGlue({**fx["conf"], "checkpointed": checkpointed})
     sd = {k: v.clone() for k, v in model.state_dict().items()}
     fp = float(sum(v.double().abs().sum() for v in sd.values()))
     assert abs(fp - fx["fingerprint"]) < 1e-6 * fx["fingerprint"]
