@@ -593,11 +593,16 @@ class LightGlue(nn.Module):
             assert key in data, f"Missing key {key} in data"
         conf = self.conf
         graphable = (
-            conf.cuda_graph and not self.training and conf.depth_confidence <= 0 and conf.width_confidence <= 0
+            conf.cuda_graph and not self.training
             and "num_keypoints0" not in data and "num_keypoints1" not in data and data["keypoints0"].is_cuda
         )
         if not graphable:
             return self._forward_impl(data)
+        # adaptive depth / width: the transformer stack (all layers; the kernels skip finished pairs and pruned rows
+        # from device-side counts) is captured, the data-dependent tail -- one host read of the exit layers and the
+        # pruned counts, MatchAssignment of the exit layer at the pruned shape, filter_matches -- runs eagerly behind
+        # every replay (lightglue.py:501-536)
+        adaptive = conf.depth_confidence > 0 or conf.width_confidence > 0
         # ---- CUDA-graph path: static copies of the inputs, one captured forward per input signature ----
         ins = {k: data[k] for k in self._GRAPH_INPUTS if isinstance(data.get(k), torch.Tensor)}
         for v in ("view0", "view1"):
@@ -607,7 +612,8 @@ class LightGlue(nn.Module):
         dev = data["keypoints0"].device
         prec = self._precision()
         self._pack(prec, dev)
-        sig = (prec, self._pack_key) + tuple((k, tuple(t.shape), t.dtype) for k, t in sorted(ins.items()))
+        sig = (prec, self._pack_key, float(conf.depth_confidence), float(conf.width_confidence)) + tuple(
+            (k, tuple(t.shape), t.dtype) for k, t in sorted(ins.items()))
         entry = self._graphs.get(sig)
         if entry is None:
             static = {k: t.to(dev).clone() for k, t in ins.items()}
@@ -618,11 +624,13 @@ class LightGlue(nn.Module):
                 d["view1"] = {"image_size": static["view1"]} if "view1" in static else {}
                 return d
 
-            self._forward_impl(as_data())  # warm-up outside the capture: lazy initialisation, allocator pools
+            warm = self._forward_impl(as_data(), static=adaptive)  # outside the capture: lazy initialisation, pools
+            if adaptive:
+                warm()
             torch.cuda.synchronize(dev)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                out = self._forward_impl(as_data())
+                out = self._forward_impl(as_data(), static=adaptive)  # adaptive: the tail closure
             if len(self._graphs) >= 8:  # a handful of signatures at most; drop the oldest
                 self._graphs.pop(next(iter(self._graphs)))
             # the captured launches carry raw device pointers (and TMA tensor maps) into the weight pack: the entry
@@ -632,11 +640,13 @@ class LightGlue(nn.Module):
         for k, t in ins.items():
             static[k].copy_(t, non_blocking=True)
         graph.replay()
+        if adaptive:
+            return out()  # fresh output tensors
         if conf.get("graph_static_outputs", False):  # caller consumes the results before the next call: no copies
             return dict(out)
         return {k: v.clone() for k, v in out.items()}  # the graph's output buffers are overwritten by the next replay
 
-    def _forward_impl(self, data: dict) -> dict:
+    def _forward_impl(self, data: dict, static: bool = False):
         lib = _abi.load()
         conf = self.conf
         kpts0, kpts1 = data["keypoints0"], data["keypoints1"]
@@ -813,7 +823,10 @@ class LightGlue(nn.Module):
                 state[B:].copy_(lens)
                 lens = state[B:]
                 lens_act = lens.clone()
-            total = torch.from_numpy(lens_host.sum(1).astype(np.int32)).to(dev)
+            if variable:
+                total = torch.from_numpy(lens_host.sum(1).astype(np.int32)).to(dev)
+            else:  # filled on the device: no host copy inside a graph capture
+                total = torch.full((B,), m + n, **i32)
             snaps = self._pinned_snapshots(L + 1, B + S)
             snap_ev = []
             polled = 0
@@ -881,16 +894,19 @@ class LightGlue(nn.Module):
                 # of later layers skip finished pairs by themselves (lens_active == 0), so the host only needs to
                 # learn about the exit EVENTUALLY, to stop launching.  The flags are copied to pinned memory behind
                 # the check and older snapshots are polled without blocking.
-                snaps[i, :B].copy_(done, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record()
-                snap_ev.append(ev)
-                stop = False
-                while polled < len(snap_ev) and snap_ev[polled].query():
-                    stop = stop or bool((snaps[polled, :B] != 0).all())
-                    polled += 1
-                if stop:
-                    break
+                # (static: the whole stack is being captured into a CUDA graph -- all layers are launched, finished
+                # pairs cost empty kernels)
+                if not static:
+                    snaps[i, :B].copy_(done, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    snap_ev.append(ev)
+                    stop = False
+                    while polled < len(snap_ev) and snap_ev[polled].query():
+                        stop = stop or bool((snaps[polled, :B] != 0).all())
+                        polled += 1
+                    if stop:
+                        break
             if do_prune:  # lightglue.py:506-521
                 ma = W["assign"][i]
                 rowdot(x, (ma["m_w"], ma["m_b"]), la, 1, msig)
@@ -908,91 +924,99 @@ class LightGlue(nn.Module):
                 rot16, rot16_b = rot16_b, rot16
                 ind, ind_b = ind_b, ind
 
-        if adaptive:
-            # the one blocking read of an adaptive forward: exit flags and (pruned) counts together
-            snaps[L].copy_(state, non_blocking=True)
-            torch.cuda.current_stream(dev).synchronize()
-            st_h = snaps[L].numpy()
-            done_h = st_h[:B]
-            exit_layer = np.where(done_h != 0, done_h - 1, L - 1).astype(np.int64)
-            lens_final = st_h[B:].reshape(B, 2).copy()
-        # ---- log assignment (lightglue.py:523-524) ----
-        md = msg  # reuse: [T,256] in the activation dtype (x3: split planes)
-        sim = None
-        z = torch.zeros(T, **f32)
-        lse = torch.zeros(T, **f32)
-        for e in np.unique(exit_layer):
-            if adaptive and lens is not None and len(np.unique(exit_layer)) > 1:
-                sel = torch.from_numpy(np.repeat(exit_layer == e, 2)).to(dev)
-                lens_g = torch.where(sel, lens, torch.zeros_like(lens))
+        def tail():
+            """Everything behind the transformer stack: the one host read of an adaptive forward, MatchAssignment of
+            the exit layer(s), filter_matches, the output dict.  With static=True (CUDA-graph capture of an adaptive
+            forward) it is returned instead of run: the graph holds the stack, the tail runs eagerly after a replay."""
+            nonlocal exit_layer, st
+            st = torch.cuda.current_stream(dev).cuda_stream  # (a captured stack was recorded on the capture stream)
+            if adaptive:
+                # the one blocking read of an adaptive forward: exit flags and (pruned) counts together
+                snaps[L].copy_(state, non_blocking=True)
+                torch.cuda.current_stream(dev).synchronize()
+                st_h = snaps[L].numpy()
+                done_h = st_h[:B]
+                exit_layer = np.where(done_h != 0, done_h - 1, L - 1).astype(np.int64)
+                lens_final = st_h[B:].reshape(B, 2).copy()
+            # ---- log assignment (lightglue.py:523-524) ----
+            md = msg  # reuse: [T,256] in the activation dtype (x3: split planes)
+            sim = None
+            z = torch.zeros(T, **f32)
+            lse = torch.zeros(T, **f32)
+            for e in np.unique(exit_layer):
+                if adaptive and lens is not None and len(np.unique(exit_layer)) > 1:
+                    sel = torch.from_numpy(np.repeat(exit_layer == e, 2)).to(dev)
+                    lens_g = torch.where(sel, lens, torch.zeros_like(lens))
+                else:
+                    lens_g = lens
+                a = W["assign"][int(e)]
+                linear(EPI_ROWMAJOR, xs if x3 else x, a["fp_w"], a["fp_b"], 256, 256, scale=(0.25, 1.0, 1.0), out=md,
+                       lens_=lens_g)
+                rowdot(x, (a["m_w"], a["m_b"]), lens_g, 0, z)
+                if x3:
+                    if sim is None:
+                        sim = torch.empty(B, Lp, Lp, **f32)
+                    check(lib.lgb200_x3_similarity(ptr(md), B, Lp, ptr(lens_g), ptr(sim), st), "x3_similarity")
+                    check(lib.lgb200_x3_assign_lse(ptr(sim), B, Lp, ptr(lens_g), m, n, ptr(lse), st), "x3_assign_lse")
+                else:
+                    check(lib.lgb200_assign_lse(prec, ptr(md), S, Lp, ptr(lens_g), ptr(lse), st), "assign_lse")
+            if do_prune:  # pruned shape is data dependent (lightglue.py:285 note)
+                R, C = int(lens_final[:, 0].max()) + 1, int(lens_final[:, 1].max()) + 1
             else:
-                lens_g = lens
-            a = W["assign"][int(e)]
-            linear(EPI_ROWMAJOR, xs if x3 else x, a["fp_w"], a["fp_b"], 256, 256, scale=(0.25, 1.0, 1.0), out=md,
-                   lens_=lens_g)
-            rowdot(x, (a["m_w"], a["m_b"]), lens_g, 0, z)
+                R, C = m + 1, n + 1
+            scores = torch.empty(B, R, C, **f32)
+            fm_ws = torch.empty(B * (R + C), device=dev, dtype=torch.int64)
+            # bf16: the assignment epilogue also emits the row/column arg-maxima, so filter_matches never
+            # re-reads the 1 GB score matrix
             if x3:
-                if sim is None:
-                    sim = torch.empty(B, Lp, Lp, **f32)
-                check(lib.lgb200_x3_similarity(ptr(md), B, Lp, ptr(lens_g), ptr(sim), st), "x3_similarity")
-                check(lib.lgb200_x3_assign_lse(ptr(sim), B, Lp, ptr(lens_g), m, n, ptr(lse), st), "x3_assign_lse")
+                check(lib.lgb200_x3_assign_scores(ptr(sim), ptr(z), ptr(lse), B, Lp, ptr(lens), R, C, ptr(scores), st),
+                      "x3_assign_scores")
             else:
-                check(lib.lgb200_assign_lse(prec, ptr(md), S, Lp, ptr(lens_g), ptr(lse), st), "assign_lse")
-        if do_prune:  # pruned shape is data dependent (lightglue.py:285 note)
-            R, C = int(lens_final[:, 0].max()) + 1, int(lens_final[:, 1].max()) + 1
-        else:
-            R, C = m + 1, n + 1
-        scores = torch.empty(B, R, C, **f32)
-        fm_ws = torch.empty(B * (R + C), device=dev, dtype=torch.int64)
-        # bf16: the assignment epilogue also emits the row/column arg-maxima, so filter_matches never
-        # re-reads the 1 GB score matrix
-        if x3:
-            check(lib.lgb200_x3_assign_scores(ptr(sim), ptr(z), ptr(lse), B, Lp, ptr(lens), R, C, ptr(scores), st),
-                  "x3_assign_scores")
-        else:
-            check(lib.lgb200_assign_scores(prec, ptr(md), ptr(z), ptr(lse), B, Lp, ptr(lens), R, C, ptr(scores),
-                                           ptr(fm_ws) if bf else None, st), "assign_scores")
+                check(lib.lgb200_assign_scores(prec, ptr(md), ptr(z), ptr(lse), B, Lp, ptr(lens), R, C, ptr(scores),
+                                               ptr(fm_ws) if bf else None, st), "assign_scores")
 
-        # ---- filter_matches (lightglue.py:525-536) ----
-        m0 = torch.empty(B, m, device=dev, dtype=torch.int64)
-        m1 = torch.empty(B, n, device=dev, dtype=torch.int64)
-        ms0 = torch.empty(B, m, **f32)
-        ms1 = torch.empty(B, n, **f32)
-        check(
-            lib.lgb200_filter_matches(
-                ptr(scores), B, R, C, ptr(lens), float(conf.filter_threshold),
-                ptr(ind) if do_prune else None, ptr(ind[1:]) if do_prune else None, 2 * Lp,
-                m, n, ptr(m0), ptr(m1), ptr(ms0), ptr(ms1), ptr(fm_ws), 1 if bf else 0, st,
-            ),
-            "filter_matches",
-        )
+            # ---- filter_matches (lightglue.py:525-536) ----
+            m0 = torch.empty(B, m, device=dev, dtype=torch.int64)
+            m1 = torch.empty(B, n, device=dev, dtype=torch.int64)
+            ms0 = torch.empty(B, m, **f32)
+            ms1 = torch.empty(B, n, **f32)
+            check(
+                lib.lgb200_filter_matches(
+                    ptr(scores), B, R, C, ptr(lens), float(conf.filter_threshold),
+                    ptr(ind) if do_prune else None, ptr(ind[1:]) if do_prune else None, 2 * Lp,
+                    m, n, ptr(m0), ptr(m1), ptr(ms0), ptr(ms1), ptr(fm_ws), 1 if bf else 0, st,
+                ),
+                "filter_matches",
+            )
 
-        xv = x.view(B, 2, Lp, 256)
-        if do_prune:
-            pc = prune_cnt.view(B, 2, Lp)
-            prune0, prune1 = pc[:, 0, :m].to(torch.int64), pc[:, 1, :n].to(torch.int64)
-            k0f, k1f = R - 1, C - 1
-            ref0, ref1 = xv[:, 0:1, :k0f], xv[:, 1:2, :k1f]
-        else:  # lightglue.py:538-539
-            prune0 = torch.full((B, m), float(L), **f32)
-            prune1 = torch.full((B, n), float(L), **f32)
-            ref0, ref1 = xv[:, 0:1, :m], xv[:, 1:2, :n]
-        if self.training:  # [B, n_layers, N, 256] (lightglue.py:546-547)
-            ref0, ref1 = torch.stack(collected0, 1), torch.stack(collected1, 1)
-        return {
-            "matches0": m0,
-            "matches1": m1,
-            "matching_scores0": ms0,
-            "matching_scores1": ms1,
-            # activation dtype, like the reference: fp32 by default, half precision under mp / autocast
-            # (lightglue.py:466-468 casts desc to half; :541-553 returns the stacked layer outputs as they are).
-            # Zero-copy views of the residual stream; the two fp32 copies cost 0.2 ms per 64-pair batch.
-            "ref_descriptors0": ref0,
-            "ref_descriptors1": ref1,
-            "log_assignment": scores,
-            "prune0": prune0,
-            "prune1": prune1,
-        }
+            xv = x.view(B, 2, Lp, 256)
+            if do_prune:
+                pc = prune_cnt.view(B, 2, Lp)
+                prune0, prune1 = pc[:, 0, :m].to(torch.int64), pc[:, 1, :n].to(torch.int64)
+                k0f, k1f = R - 1, C - 1
+                ref0, ref1 = xv[:, 0:1, :k0f], xv[:, 1:2, :k1f]
+            else:  # lightglue.py:538-539
+                prune0 = torch.full((B, m), float(L), **f32)
+                prune1 = torch.full((B, n), float(L), **f32)
+                ref0, ref1 = xv[:, 0:1, :m], xv[:, 1:2, :n]
+            if self.training:  # [B, n_layers, N, 256] (lightglue.py:546-547)
+                ref0, ref1 = torch.stack(collected0, 1), torch.stack(collected1, 1)
+            return {
+                "matches0": m0,
+                "matches1": m1,
+                "matching_scores0": ms0,
+                "matching_scores1": ms1,
+                # activation dtype, like the reference: fp32 by default, half precision under mp / autocast
+                # (lightglue.py:466-468 casts desc to half; :541-553 returns the stacked layer outputs as they are).
+                # Zero-copy views of the residual stream; the two fp32 copies cost 0.2 ms per 64-pair batch.
+                "ref_descriptors0": ref0,
+                "ref_descriptors1": ref1,
+                "log_assignment": scores,
+                "prune0": prune0,
+                "prune1": prune1,
+            }
 
+
+        return tail if static else tail()
 
 __main_model__ = LightGlue

@@ -224,7 +224,7 @@ def test_training_reduces_the_loss():
         loss = losses["total"].mean()
         loss.backward()
         opt.step()
-        hist.append(float(loss))
+        hist.append(float(loss.detach()))
     assert all(math.isfinite(x) for x in hist) and hist[-1] < hist[0] - 0.05, hist
 
 

@@ -65,3 +65,32 @@ def test_graph_survives_precision_switches():
     model.conf.graph_static_outputs = True
     o = model(data)
     assert torch.equal(o["log_assignment"], want["fp32"])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["depth+width", "width"])
+def test_adaptive_graph_replay_equals_eager(precision, mode):
+    """Adaptive depth / width under conf.cuda_graph: the transformer stack is replayed from a graph (all layers; the
+    kernels skip finished pairs from the device-side counts), the data-dependent tail runs eagerly.  Same results as
+    the eager adaptive forward, including the pruned log_assignment shape, prune layers and matches."""
+    conf = {"precision": precision, "filter_threshold": 0.1, "width_confidence": 0.99}
+    if mode == "depth+width":
+        conf["depth_confidence"] = 0.95
+    torch.manual_seed(6)
+    eager = LightGlue(conf).eval()
+    sd = eager.state_dict()
+    for i in range(8):  # heads that actually prune and (depth) exit at layer 4, as in tools/adaptive_bench.py
+        sd[f"token_confidence.{i}.token.0.bias"].fill_(3.0 if i >= 4 else -3.0)
+        sd[f"log_assignment.{i}.matchability.bias"].fill_(-4.5 if i % 2 == 0 else 0.0)
+    eager = eager.to(DEV)
+    graphed = LightGlue({**conf, "cuda_graph": True}).eval().to(DEV)
+    graphed.load_state_dict(eager.state_dict())
+    for B, n0, n1, seed in [(1, 512, 480, 51), (1, 512, 480, 52), (3, 384, 384, 53), (1, 512, 480, 54)]:
+        data = make_pairs(B, n0, n1, seed=seed, device=DEV)
+        want, got = eager(data), graphed(data)
+        assert set(want) == set(got)
+        for k in want:
+            assert got[k].shape == want[k].shape and got[k].dtype == want[k].dtype, k
+            assert torch.equal(got[k], want[k]), k
+        assert float(want["prune0"].float().mean()) < 9.0  # something was pruned / exited early
+    assert len(graphed._graphs) == 2

@@ -24,9 +24,9 @@ for label, conf, bias in (
     ("depth+width, exit at layer 4", {"depth_confidence": 0.95, "width_confidence": 0.99}, None),
     ("width only, every layer prunes", {"width_confidence": 0.99}, -4.0),
 ):
-    for B in (1, 16):
+    for B, graph in ((1, False), (1, True), (16, False), (16, True)):
         torch.manual_seed(0)
-        m = LightGlue({"precision": "bf16", "filter_threshold": 0.1, **conf}).eval()
+        m = LightGlue({"precision": "bf16", "filter_threshold": 0.1, "cuda_graph": graph, **conf}).eval()
         sd = m.state_dict()
         for i in range(8):
             sd[f"token_confidence.{i}.token.0.bias"].fill_(3.0 if i >= 4 else -3.0)
@@ -34,6 +34,6 @@ for label, conf, bias in (
         m = m.cuda()
         data = make_pairs(B, 2048, 2048, seed=400, device="cuda")
         ms, out = timeit(m, data, 20 if B == 1 else 5)
-        print(json.dumps({"lib": os.environ.get("LGB200_LIB", "default"), "case": label, "pairs": B, "ms_per_forward": round(ms, 3),
+        print(json.dumps({"lib": os.environ.get("LGB200_LIB", "default"), "case": label, "cuda_graph": graph, "pairs": B, "ms_per_forward": round(ms, 3),
                           "pairs_per_s": round(B / ms * 1e3, 1), "log_assignment": list(out["log_assignment"].shape),
                           "mean_prune0": round(float(out["prune0"].float().mean()), 2)}), flush=True)
