@@ -1,3 +1,4 @@
 cd /root/repo
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/gputest.log 2>&1; tail -8 gpurun_out/gputest.log | cut -c1-300
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+python tools/profile_hbm.py assign 64 > gpurun_out/profile_hbm_assign.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:tc_assign -c 2 -o gpurun_out/assign_r2 -f python tools/profile_hbm.py assign 64 > gpurun_out/ncu_assign.log 2>&1
+tail -3 gpurun_out/ncu_assign.log; ls -la gpurun_out/assign_r2.ncu-rep
