@@ -1,4 +1,4 @@
 cd /root/repo
-python tools/profile_hbm.py assign 64 > gpurun_out/profile_hbm_assign.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:tc_assign -c 2 -o gpurun_out/assign_r2 -f python tools/profile_hbm.py assign 64 > gpurun_out/ncu_assign.log 2>&1
-tail -3 gpurun_out/ncu_assign.log; ls -la gpurun_out/assign_r2.ncu-rep
+for seed in 2 3; do
+timeout 1200 python tools/fuzz_parity.py 100 $seed 2>&1 | grep -v Warning > gpurun_out/fuzz$seed.log; grep '"ok": false' gpurun_out/fuzz$seed.log | cut -c1-700 | head -10; tail -1 gpurun_out/fuzz$seed.log
+done
