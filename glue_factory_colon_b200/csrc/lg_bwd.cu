@@ -20,17 +20,19 @@ constexpr int AB_T = 64;          // rows per tile on both sides
 constexpr int AB_LD = AB_T + 4;   // padded leading dimension (keeps float4 alignment, spreads banks)
 constexpr float LN2 = 0.69314718055994530942f;
 
+// 6 x 17 KB + 512 B = 102.5 KB: two CTAs (16 warps) per SM.  The transposed other-tiles Yt / Wt are dead once the two
+// score products are in registers; dS^T and P^T are written over them (one extra barrier per tile) -- with separate
+// buffers (139 KB, one CTA per SM) the kernels ran at 28 TFLOP/s of fp32 FMA.
 struct AbSmem {
   float Xt[LG_DH][AB_LD];  // own X   [d][row]
   float Ut[LG_DH][AB_LD];  // own U   [d][row]
-  float Yt[LG_DH][AB_LD];  // other Y [d][n]
-  float Wt[LG_DH][AB_LD];  // other W [d][n]
+  float Yt[LG_DH][AB_LD];  // other Y [d][n]; then dS^T [n][m]
+  float Wt[LG_DH][AB_LD];  // other W [d][n]; then P^T  [n][m] (dK/dV only)
   float Ys[AB_T][AB_LD];   // other Y [n][d]
   float Ws[AB_T][AB_LD];   // other W [n][d]   (dK/dV only)
-  float Dt[AB_T][AB_LD];   // dS^T [n][m]
-  float Pt[AB_T][AB_LD];   // P^T  [n][m]      (dK/dV only)
   float lse[AB_T], dlt[AB_T];  // statistics of the query rows of the current other-tile (dK/dV only)
 };
+static_assert(LG_DH == AB_T, "dS^T / P^T reuse the [d][n] buffers");
 
 // 64 rows x 64 floats -> transposed [d][row] and (optionally) row-major [row][d]
 __device__ __forceinline__ void ab_load(const float* __restrict__ src, size_t row_stride, float (*T_)[AB_LD],
@@ -59,7 +61,7 @@ __device__ __forceinline__ void ab_mma_t(const float (*A)[AB_LD], const float (*
   }
 }
 
-__global__ void __launch_bounds__(256) attn_bwd_stats_kernel(const float* __restrict__ Q, const float* __restrict__ K,
+__global__ void __launch_bounds__(256, 2) attn_bwd_stats_kernel(const float* __restrict__ Q, const float* __restrict__ K,
                                                              const float* __restrict__ O, const float* __restrict__ dO,
                                                              int Lp, const int32_t* __restrict__ lens, int kv_xor,
                                                              float* __restrict__ lse2, float* __restrict__ dlt) {
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(256) attn_bwd_stats_kernel(const float* __rest
 // With logits a = ln2 . <q', k'> (q' carries log2(e)/sqrt(d)): P = exp2(<q',k'> - lse2[query]),
 // dS = P (<dO, v> - delta[query]), dq' = ln2 . dS k', dk' = ln2 . dS^T q', dv = P^T dO.
 template <bool DKV>
-__global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__ Q, const float* __restrict__ K,
+__global__ void __launch_bounds__(256, 2) attn_bwd_kernel(const float* __restrict__ Q, const float* __restrict__ K,
                                                        const float* __restrict__ V, const float* __restrict__ dO,
                                                        int Lp, const int32_t* __restrict__ lens, int kv_xor,
                                                        const float* __restrict__ lse2, const float* __restrict__ dlt,
@@ -177,6 +179,9 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__
     float sc[4][4] = {}, dp[4][4] = {};
     ab_mma_t(sm.Xt, sm.Yt, ty, tx, sc);
     ab_mma_t(sm.Ut, sm.Wt, ty, tx, dp);
+    float (*Dt)[AB_LD] = sm.Yt;  // dS^T [n][m]
+    float (*Pt)[AB_LD] = sm.Wt;  // P^T  [n][m]
+    __syncthreads();             // every thread has read Yt / Wt
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -186,13 +191,13 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__
         const float dq = DKV ? sm.dlt[tx * 4 + j] : dlt_own[i];
         const float p = valid ? exp2f(sc[i][j] - lq) : 0.f;
         const float ds = valid ? p * (dp[i][j] - dq) : 0.f;
-        sm.Dt[tx * 4 + j][ty * 4 + i] = ds;
-        if (DKV) sm.Pt[tx * 4 + j][ty * 4 + i] = p;
+        Dt[tx * 4 + j][ty * 4 + i] = ds;
+        if (DKV) Pt[tx * 4 + j][ty * 4 + i] = p;
       }
     __syncthreads();
 #pragma unroll 8
     for (int n = 0; n < AB_T; ++n) {
-      const float4 a = *reinterpret_cast<const float4*>(&sm.Dt[n][ty * 4]);
+      const float4 a = *reinterpret_cast<const float4*>(&Dt[n][ty * 4]);
       const float4 b = *reinterpret_cast<const float4*>(&sm.Ys[n][tx * 4]);
       const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
@@ -200,7 +205,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc1[i][j] = fmaf(av[i], bv[j], acc1[i][j]);
       if (DKV) {
-        const float4 p = *reinterpret_cast<const float4*>(&sm.Pt[n][ty * 4]);
+        const float4 p = *reinterpret_cast<const float4*>(&Pt[n][ty * 4]);
         const float4 w = *reinterpret_cast<const float4*>(&sm.Ws[n][tx * 4]);
         const float pv[4] = {p.x, p.y, p.z, p.w}, wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll

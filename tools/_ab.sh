@@ -1,4 +1,4 @@
 cd /root/repo
-for seed in 2 3; do
-timeout 1200 python tools/fuzz_parity.py 100 $seed 2>&1 | grep -v Warning > gpurun_out/fuzz$seed.log; grep '"ok": false' gpurun_out/fuzz$seed.log | cut -c1-700 | head -10; tail -1 gpurun_out/fuzz$seed.log
-done
+timeout 900 python -m pytest tests/test_gpu_grad.py -m gpu -q > gpurun_out/gputest_grad.log 2>&1; tail -2 gpurun_out/gputest_grad.log
+timeout 600 python tools/train_bench.py 32 512 5 2>&1 | grep -v Warning | tail -4
+timeout 600 python tools/train_bench.py 8 2048 3 2>&1 | grep -v Warning | tail -4
