@@ -102,11 +102,51 @@ __device__ __forceinline__ TileRef tile_ref(const X3Args& g, int t) {
   return r;
 }
 
-template <int MODE>
+// Work items of one CTA.  CL == 1: tiles blockIdx.x, blockIdx.x + gridDim.x, ...  CL > 1: the CTAs of a cluster walk
+// GROUPS of CL consecutive row tiles x one column block together (rank r takes row tile G*CL + r), so that every W
+// stage is needed by all of them at the same time: each fetches 1/CL of it and multicasts.  A group is skipped only if
+// all of its row tiles are padding; a padded tile inside a live group is computed like any other (finite junk in rows
+// nobody reads) because its CTA has to take part in the W stream anyway.
+template <int MODE, int CL>
+struct TileWalk {
+  const X3Args& g;
+  int it, step, rank, n_items;
+  __device__ TileWalk(const X3Args& g_, int rank_) : g(g_), rank(rank_) {
+    if (CL == 1) {
+      it = blockIdx.x; step = gridDim.x; n_items = g.m_tiles * g.n_tiles;
+    } else {
+      it = blockIdx.x / CL; step = gridDim.x / CL; n_items = (g.m_tiles / CL) * g.n_tiles;
+    }
+  }
+  __device__ bool next(TileRef& tr) {
+    while (it < n_items) {
+      const int cur = it;
+      it += step;
+      if (CL == 1) {
+        tr = tile_ref<MODE>(g, cur);
+        if (!tr.skip) return true;
+      } else {
+        const int G = cur / g.n_tiles, nt = cur - G * g.n_tiles;
+        bool all_skip = true;
+        for (int r = 0; r < CL; ++r) all_skip = all_skip && tile_ref<MODE>(g, (G * CL + r) * g.n_tiles + nt).skip;
+        if (all_skip) continue;
+        tr = tile_ref<MODE>(g, (G * CL + rank) * g.n_tiles + nt);
+        tr.skip = false;
+        return true;
+      }
+    }
+    return false;
+  }
+};
+
+template <int MODE, int CL>
 __global__ void __launch_bounds__(192, 1)
 x3_linear_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmW, X3Args g, LgEpi epi) {
   constexpr bool LN = MODE == X_LN;
+  constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
+  constexpr int WSL = XN / CL;           // W rows this CTA fetches for the whole cluster
+  const uint32_t crank = CL > 1 ? tc::cluster_ctarank() : 0;
   // The tensor core rounds its fp32 accumulator TOWARD ZERO after every MMA (tools/x3_micro.py: K = 512 loses 1.5e-6
   // relative, one-sidedly; the CUDA-core kernel 3e-10).  Where the result feeds the residual stream or the score matrix
   // directly (X_ROW: FFN layer 2, final_proj; X_SIM) the two small products go to a SECOND accumulator, so that the large
@@ -129,13 +169,13 @@ x3_linear_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   float* s_par = reinterpret_cast<float*>(smem + XSTAGES * XSTAGE + 256);  // bias | gamma | beta (LN)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = g.m_tiles * g.n_tiles;
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmA0);
     tc::prefetch_tmap(&tmA1);
     tc::prefetch_tmap(&tmW);
-    for (int i = 0; i < XSTAGES; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+    // (cluster: a stage is refilled by every CTA's slice, so each CTA's MMAs release it in all of them)
+    for (int i = 0; i < XSTAGES; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], CL); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 4); }
     tc::fence_barrier_init();
   }
@@ -149,6 +189,7 @@ x3_linear_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
   tc::fence_before_sync();
   __syncthreads();
+  if (CL > 1) tc::cluster_sync();  // the peers' barriers exist before anyone multicasts into them
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -157,9 +198,9 @@ x3_linear_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileRef tr = tile_ref<MODE>(g, t);
-        if (tr.skip) continue;
+      TileWalk<MODE, CL> walk(g, (int)crank);
+      TileRef tr;
+      while (walk.next(tr)) {
         for (int sub = 0; sub < NSUB; ++sub) {
           for (int kb = 0; kb < g.kb_total; ++kb) {
             tc::mbar_wait(&empty[stage], phase ^ 1);
@@ -170,8 +211,14 @@ x3_linear_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const int ka = (kb < g.kb_a0 ? kb : kb - g.kb_a0) * XK;
             tc::tma_load_3d(sa, ta, &full[stage], ka, tr.a_row, 0);
             tc::tma_load_3d(sa + PA, ta, &full[stage], ka, tr.a_row, 1);
-            tc::tma_load_3d(sw, &tmW, &full[stage], kb * XK, tr.w_row + sub * XN, 0);
-            tc::tma_load_3d(sw + PW, &tmW, &full[stage], kb * XK, tr.w_row + sub * XN, 1);
+            if (CL > 1) {
+              const int wr = tr.w_row + sub * XN + (int)crank * WSL;
+              tc::tma_load_3d_mc(sw + crank * (WSL * 128), &tmW, &full[stage], kb * XK, wr, 0, MC_MASK);
+              tc::tma_load_3d_mc(sw + PW + crank * (WSL * 128), &tmW, &full[stage], kb * XK, wr, 1, MC_MASK);
+            } else {
+              tc::tma_load_3d(sw, &tmW, &full[stage], kb * XK, tr.w_row + sub * XN, 0);
+              tc::tma_load_3d(sw + PW, &tmW, &full[stage], kb * XK, tr.w_row + sub * XN, 1);
+            }
             if (++stage == XSTAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -182,9 +229,9 @@ x3_linear_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     constexpr uint32_t idesc = idesc_f16(XM, XN, 0);
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const TileRef tr = tile_ref<MODE>(g, t);
-      if (tr.skip) continue;
+    TileWalk<MODE, CL> walk(g, (int)crank);
+    TileRef tr;
+    while (walk.next(tr)) {
       tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc::fence_after_sync();
       for (int sub = 0; sub < NSUB; ++sub) {
@@ -206,7 +253,8 @@ x3_linear_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               tc::umma_ss(d_tmem + LO_OFF, a_hi, w_lo, idesc, 1);
               tc::umma_ss(d_tmem, a_hi, w_hi, idesc, SPLIT_ACC ? (kb | k) != 0 : 1);
             }
-            tc::umma_commit(&empty[stage]);  // smem stage reusable once these MMAs retire
+            if (CL > 1) tc::umma_commit_mc(&empty[stage], MC_MASK);  // stage reusable once these MMAs retire
+            else tc::umma_commit(&empty[stage]);
           }
           __syncwarp();
           if (++stage == XSTAGES) { stage = 0; phase ^= 1; }
@@ -221,9 +269,9 @@ x3_linear_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const TileRef tr = tile_ref<MODE>(g, t);
-      if (tr.skip) continue;
+    TileWalk<MODE, CL> walk(g, (int)crank);
+    TileRef tr;
+    while (walk.next(tr)) {
       tc::mbar_wait(&tfull[acc], acc_phase);
       tc::fence_after_sync();
       const int rt = quarter * 32 + lane;          // row within the tile
@@ -371,6 +419,7 @@ x3_linear_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
   tc::fence_before_sync();
   __syncthreads();
+  if (CL > 1) tc::cluster_sync();  // nobody retires while a peer may still multicast into its shared memory
   if (warp == 1) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem_base, 512);
@@ -384,19 +433,55 @@ int make_split_map(CUtensorMap* tm, const __half* base, uint64_t rows, uint64_t 
   return lg_make_tmap_bf16(tm, base, 3, d, s, b);  // (2-byte elements: the bf16 encoder serves fp16 as well)
 }
 
-template <int MODE>
-int launch_x3(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, X3Args g, LgEpi epi, cudaStream_t st) {
-  auto kern = x3_linear_kernel<MODE>;
+#ifndef LG_X3_CL
+#define LG_X3_CL 1
+#endif
+// Row tiles that share a W stream (cluster size of the linear modes; opt-in with -DLG_X3_CL=2|4).  One CTA per 128-row
+// tile streams the whole weight matrix (both planes: 512 KB at K = 512, N = 256) next to 256 KB of activations, 1.6 GB of
+// L2 -> SM traffic per FFN2 launch at 64 x 2048 keypoints, so W multicast across a cluster looked like the fix.
+// Measured on B200 (whole fp32-mode step, same box): cluster 1 61.0 ms, cluster 2 60.6 ms, cluster 4 76.8 ms -- the
+// kernel is not L2-bound but SHARED-MEMORY-bound: the 12 MMAs of a stage read 144 KB of operands and the stage's TMA
+// fill writes 96 KB, 240 KB per 1 536 tensor cycles = 156 B/clk against the SM's 128 B/clk; lockstep with only two
+// stages then costs more than the halved L2 stream saves.  The fix for that is cta_group::2 (half of B per CTA, as in
+// the bf16 pair kernels of lg_tc_gemm2.cu), not multicast.  With a cluster, padded row tiles inside a live group are
+// computed (finite junk in rows nobody reads) instead of skipped.
+constexpr int X_CL = LG_X3_CL;
+
+template <int MODE, int CL>
+int launch_x3_cl(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, X3Args g, LgEpi epi, cudaStream_t st) {
+  auto kern = x3_linear_kernel<MODE, CL>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, X_SMEM);
   if (e != cudaSuccess) return (int)e;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int tiles = g.m_tiles * g.n_tiles;
-  const int grid = tiles < sms ? tiles : sms;
-  kern<<<grid, 192, X_SMEM, st>>>(a0, a1, w, g, epi);
+  const int items = (g.m_tiles / CL) * g.n_tiles;           // groups of CL row tiles x column blocks
+  const int clusters = items < sms / CL ? items : sms / CL;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * CL);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = X_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  e = cudaLaunchKernelEx(&cfg, kern, a0, a1, w, g, epi);
+  if (e != cudaSuccess) return (int)e;
   LG_LAUNCH_CHECK();
   return LGB200_OK;
+}
+
+// cluster size a launch can use: the row tiles must split into whole groups
+inline int x3_cluster(int mode, int m_tiles) { return (mode != X_SIM && X_CL > 1 && m_tiles % X_CL == 0) ? X_CL : 1; }
+
+template <int MODE>
+int launch_x3(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, X3Args g, LgEpi epi, cudaStream_t st) {
+  if (x3_cluster(MODE, g.m_tiles) > 1) return launch_x3_cl<MODE, X_CL>(a0, a1, w, g, epi, st);
+  return launch_x3_cl<MODE, 1>(a0, a1, w, g, epi, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -513,7 +598,8 @@ int lg_x3_linear(int epilogue, const void* A0, const void* A1, int K0, const voi
   } else {
     tA1 = tA0;
   }
-  if ((rc = make_split_map(&tW, (const __half*)W, N, K, XN))) return rc;
+  const int mode = ln ? X_LN : (epilogue == LGB200_EPI_HEADS ? X_HEADS : X_ROW);
+  if ((rc = make_split_map(&tW, (const __half*)W, N, K, XN / x3_cluster(mode, T / XM)))) return rc;  // box = one CTA's slice
   X3Args g{};
   g.kb_total = K / XK;
   g.kb_a0 = K0 / XK;
