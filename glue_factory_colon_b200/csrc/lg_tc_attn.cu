@@ -255,9 +255,9 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     reinterpret_cast<uint4*>(sQx)[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
     reinterpret_cast<uint4*>(sKx)[threadIdx.x] = make_uint4(0x3f803f80u, 0u, 0u, 0u);  // two leading ones
   }
+#endif
   for (int i = threadIdx.x; i < 4 * 128 * NP / 4; i += blockDim.x) reinterpret_cast<uint4*>(s_sum)[i] = make_uint4(0u, 0u, 0u, 0u);
   tc::fence_proxy_async();
-#endif
   if (warp == 1) tc::tmem_alloc(tmem_slot, TM_COLS);
   if (threadIdx.x == 64 && stagger_ns > 0) {
     unsigned smid;
@@ -478,6 +478,9 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const float4 v = *reinterpret_cast<const float4*>(sum_row + (j & 1) * (128 * NP));
           mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
         }
+#if !LG_ATTN_MSUB
+        mx -= m_ref;  // (the scores arrive raw: relative to the reference here)
+#endif
         move = j == 0 || mx > 8.f;
         up = mx;
         any_move = __any_sync(0xffffffffu, move);  // rare after the first tile
@@ -500,11 +503,13 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const float m_abs = __bfloat162float(hi) + __bfloat162float(lo);
           delta = m_abs - m_ref;
           m_ref = m_abs;
+#if LG_ATTN_MSUB
           if (part == 0) {  // row r of Q_ext: 32-byte rows, (-hi, -lo) in the first two elements of the row
             const uint32_t bits = ((uint32_t)(*reinterpret_cast<const unsigned short*>(&hi)) |
                                    ((uint32_t)(*reinterpret_cast<const unsigned short*>(&lo)) << 16)) ^ 0x80008000u;
             *reinterpret_cast<uint32_t*>(sQx + r * 32) = bits;
           }
+#endif
         }
         tc::fence_proxy_async();  // generic-proxy write -> visible to the next QK^T (async proxy)
         alpha = j == 0 ? 0.f : ex2(-delta);
@@ -520,7 +525,11 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         float rsum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < COLS / 2; ++i) {
+#if LG_ATTN_MSUB
           float p0 = __uint_as_float(sv[2 * i]) - delta, p1 = __uint_as_float(sv[2 * i + 1]) - delta;
+#else
+          float p0 = __uint_as_float(sv[2 * i]) - m_ref, p1 = __uint_as_float(sv[2 * i + 1]) - m_ref;
+#endif
           if (LG_POLY_PAIR(i)) {
             pmax = max3(pmax, p0, p1);
             const float2 pp = ex2_poly2(make_float2(p0, p1));
@@ -555,7 +564,14 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #if LG_ATTN_EARLY_POLL && LG_ATTN_PRELOAD
             if (i == LG_ATTN_PVTEST_AT) pv_ok = tc::mbar_test(pv_done, (j - 1) & 1);  // P.V(j-1) was released at the top of this step (j = 0: not consumed)
 #endif
+#if LG_ATTN_MSUB
             float p0 = __uint_as_float(sv[2 * i]), p1 = __uint_as_float(sv[2 * i + 1]);
+#else  // no subtraction slice in the MMA: one packed add per pair (saves 1/9 of the MMA work, i.e. energy under the
+       // power cap, for half an issue slot per element)
+            const float2 q2 = __fadd2_rn(make_float2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])),
+                                         make_float2(-m_ref, -m_ref));
+            float p0 = q2.x, p1 = q2.y;
+#endif
             if (LG_POLY_PAIR(i)) {
               pmax = max3(pmax, p0, p1);
               const float2 pp = ex2_poly2(make_float2(p0, p1));
@@ -672,7 +688,9 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   // restart in the exact mode: every TMA load and MMA of pass 0 has been consumed (the softmax warps waited for the
   // last P.V); fresh barrier set, Q_ext back to zero, O is overwritten by the first P.V (accumulate flag)
   tc::fence_after_sync();
+#if LG_ATTN_MSUB
   if (threadIdx.x < 256) reinterpret_cast<uint4*>(sQx)[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
+#endif
   tc::fence_proxy_async();
   tc::fence_before_sync();
   __syncthreads();

@@ -42,3 +42,28 @@ def test_checkpoint_containers_and_prefixes():
         unwrap_checkpoint({"model": 3})
     with pytest.raises(ValueError):
         unwrap_checkpoint([1, 2])
+
+
+def test_training_path_covers_every_parameter():
+    """train.transformer_params (what TransformerFn differentiates) + the MatchAssignment and token-confidence heads
+    (AssignFn / torch in LightGlue.loss) = every parameter of the module, each exactly once."""
+    import torch
+
+    from glue_factory_colon_b200 import LightGlue
+    from glue_factory_colon_b200.train import transformer_params
+
+    for conf in ({}, {"input_dim": 128, "add_scale_ori": True, "n_layers": 3}):
+        model = LightGlue(conf)
+        covered = [p for _, p in transformer_params(model)]
+        covered += [p for a in model.log_assignment for p in a.parameters()]
+        covered += [p for t in model.token_confidence for p in t.parameters()]
+        ids = [id(p) for p in covered]
+        assert len(ids) == len(set(ids))
+        assert set(ids) == {id(p) for p in model.parameters()}
+        keys = [k for k, _ in transformer_params(model)]
+        assert len(keys) == len(set(keys))
+    # the packed Wqkv order used by the backward pass is a permutation of the reference's rows
+    from glue_factory_colon_b200.train import _PERM
+
+    assert sorted(_PERM.tolist()) == list(range(768))
+    assert int(_PERM[0]) == 0 and int(_PERM[1]) == 3 and int(_PERM[256]) == 1  # part*256 + head*64 + d <- head*192 + d*3 + part

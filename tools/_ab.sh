@@ -1,5 +1,11 @@
 cd /root/repo
-timeout 900 python -m pytest tests -m gpu -q -k "x3 or golden or c1 or c2 or c3" > gpurun_out/gputest_x3.log 2>&1; tail -3 gpurun_out/gputest_x3.log | cut -c1-300
-for lib in "" glue_factory_colon_b200/lib/var/x3cl2.so glue_factory_colon_b200/lib/var/x3cl1.so ""; do
-echo "lib=$lib"; LGB200_LIB=$lib python bench.py --steps 5 --warmup 3 --precision fp32 --no-cpu-baseline --no-gpu-library 2>/dev/null | cut -c1-160
+LGB200_LIB=glue_factory_colon_b200/lib/var/a_msub0.so timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "attention" -x 2>&1 | tail -3
+for lib in "" a_msub0 a_msub0_p4 ""; do
+L=""; [ -n "$lib" ] && L=glue_factory_colon_b200/lib/var/$lib.so
+echo -n "lib=$lib  "; LGB200_LIB=$L timeout 240 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-gpu-library --no-fp32-mode 2>/dev/null | python -c "
+import sys,json
+d=json.loads(sys.stdin.read())
+r=d['roofline']
+print(round(d['value'],1), round(d['ms_per_step'],3), 'frac', round(r['frac'],4), 'alone', r.get('alone',{}).get('frac'), d['clocks']['sm_mhz'])
+"
 done
