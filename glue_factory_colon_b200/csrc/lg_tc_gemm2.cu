@@ -76,6 +76,9 @@ struct Args {
   int m_tiles;
   int Lp;
   int prefetch_tiles;  // L2 prefetch distance in M tiles (0 = off)
+  int reverse;   // 1: the M tiles are walked from the last to the first.  Consecutive layers alternate the direction, so
+                 // that a kernel starts on the rows its predecessor wrote last -- the part of a 134-268 MB activation
+                 // that is still in the 126 MB L2
   int has_in;    // rotary table (HEADS) or residual (ROW) present
   int n_rot;
   float scale[3];
@@ -181,6 +184,9 @@ __device__ __forceinline__ float gelu_act(float x) { return gelu_fast(x); }
 __device__ __forceinline__ float gelu_act(float x) { return gelu_tanh(x); }
 #endif
 
+// tile index inside [0, m_tiles): one unsigned compare serves both walking directions
+#define MT_IN(x) ((unsigned)(x) < (unsigned)g.m_tiles)
+
 __device__ __forceinline__ bool tile_skipped(const Args& g, int m_tile) {
   if (!g.lens) return false;
   const int r0 = m_tile * BM;
@@ -214,8 +220,8 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
   const uint32_t crank = CL > 1 ? cluster_rank() : 0;
   const int cid = (int)cluster_id_x(), ncl = (int)n_clusters_x();
   const int group = cid % g.n_groups;       // which CL-wide set of column blocks
-  const int m_first = cid / g.n_groups;
-  const int m_step = ncl / g.n_groups;
+  const int m_first = g.reverse ? g.m_tiles - 1 - cid / g.n_groups : cid / g.n_groups;
+  const int m_step = g.reverse ? -(ncl / g.n_groups) : ncl / g.n_groups;
   const int nb = group * CL + (int)crank;   // 128-column block of this CTA
   const int n0 = nb * BN;
 
@@ -268,7 +274,7 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
     tc::pdl_wait();  // activations (and lens) come from the predecessor; the weight block above does not
     int stage = 0;
     uint32_t phase = 0;
-    for (int mt = m_first; mt < g.m_tiles; mt += m_step) {
+    for (int mt = m_first; MT_IN(mt); mt += m_step) {
       if (tile_skipped(g, mt)) continue;
       const int row = mt * BM + crank * SLICE_ROWS;
       for (int kb = 0; kb < g.kb_total; ++kb) {
@@ -282,7 +288,7 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
           else tc::tma_load_2d(dst, tm, &full[stage], kc, row);
           if (g.prefetch_tiles > 0) {
             const int mp = mt + g.prefetch_tiles * m_step;  // same k-block, a few M tiles ahead
-            if (mp < g.m_tiles) tma_prefetch_l2(tm, kc, mp * BM + crank * SLICE_ROWS);
+            if (MT_IN(mp)) tma_prefetch_l2(tm, kc, mp * BM + crank * SLICE_ROWS);
           }
         }
         __syncwarp();
@@ -307,7 +313,7 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
 #define GT0()
 #define GT1(v)
 #endif
-    for (int mt = m_first; mt < g.m_tiles; mt += m_step) {
+    for (int mt = m_first; MT_IN(mt); mt += m_step) {
       if (tile_skipped(g, mt)) continue;
       GT0();
       LG_PI_WAIT(&tempty[acc], acc_phase ^ 1);
@@ -368,24 +374,24 @@ tc_ws_linear_kernel(const __grid_constant__ Maps maps, const Args g) {
     // was already waiting (the QKV projection was epilogue-bound: the issuer waited 38 % of its time for TMEM).
     constexpr bool PF = MODE == MODE_HEADS && !KBIG;
     auto next_tile = [&](int mt) {
-      for (mt += m_step; mt < g.m_tiles && tile_skipped(g, mt); mt += m_step) {}
+      for (mt += m_step; MT_IN(mt) && tile_skipped(g, mt); mt += m_step) {}
       return mt;
     };
     if (PF && use_in && lane == 0) {
       int mt0 = m_first;
-      if (mt0 < g.m_tiles && tile_skipped(g, mt0)) mt0 = next_tile(mt0);
-      if (mt0 < g.m_tiles) {
+      if (MT_IN(mt0) && tile_skipped(g, mt0)) mt0 = next_tile(mt0);
+      if (MT_IN(mt0)) {
         tc::mbar_arrive_expect_tx(&in_bar[ew], STG);
         tc::tma_load_2d(stg_in, &maps.in, &in_bar[ew], 0, mt0 * BM + quarter * 32);
       }
     }
-    for (int mt = m_first; mt < g.m_tiles; mt += m_step) {
+    for (int mt = m_first; MT_IN(mt); mt += m_step) {
       if (tile_skipped(g, mt)) continue;
       const int row0 = mt * BM + quarter * 32;  // first global row of this warp
       if (PF) {
         if (use_in && lane == 0) {
           const int mn = next_tile(mt);
-          if (mn < g.m_tiles) {  // buffer (iter+1)&1 was read in the previous iteration (all lanes, then __syncwarp)
+          if (MT_IN(mn)) {  // buffer (iter+1)&1 was read in the previous iteration (all lanes, then __syncwarp)
             const int nb_ = (iter + 1) & 1;
             tc::mbar_arrive_expect_tx(&in_bar[nb_ * 8 + ew], STG);
             tc::tma_load_2d(stg_in + nb_ * 8 * STG, &maps.in, &in_bar[nb_ * 8 + ew], 0, mn * BM + quarter * 32);
@@ -625,8 +631,8 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
   const uint32_t crank = cluster_rank();  // 0 = leader
   const int cid = (int)cluster_id_x(), ncl = (int)n_clusters_x();
   const int group = cid % g.n_groups;     // which 256-column block
-  const int m_first = cid / g.n_groups;
-  const int m_step = ncl / g.n_groups;
+  const int m_first = g.reverse ? g.m_tiles - 1 - cid / g.n_groups : cid / g.n_groups;
+  const int m_step = g.reverse ? -(ncl / g.n_groups) : ncl / g.n_groups;
   const int n0 = (group * 2 + (int)crank) * BN;  // this CTA's resident 128-column block of W
   const int pair_col0 = group * BN2;
 
@@ -675,7 +681,7 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
     tc::pdl_wait();  // activations (and lens) come from the predecessor; the weight block above does not
     int stage = 0;
     uint32_t phase = 0;
-    for (int mt = m_first; mt < g.m_tiles; mt += m_step) {
+    for (int mt = m_first; MT_IN(mt); mt += m_step) {
       if (pair_skipped(g, mt)) continue;
       const int row = mt * 2 * BM + (int)crank * BM;
       for (int kb = 0; kb < g.kb_total; ++kb) {
@@ -687,7 +693,7 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
           tc::tma_load_2d(sA + stage * A_STAGE, tm, &full[stage], kc, row);
           if (g.prefetch_tiles > 0) {
             const int mp = mt + g.prefetch_tiles * m_step;
-            if (mp < g.m_tiles) tma_prefetch_l2(tm, kc, mp * 2 * BM + (int)crank * BM);
+            if (MT_IN(mp)) tma_prefetch_l2(tm, kc, mp * 2 * BM + (int)crank * BM);
           }
         }
         __syncwarp();
@@ -710,7 +716,7 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
       int n_t = 0;
       const bool rec = blockIdx.x == 0 && lane == 0;
 #endif
-      for (int mt = m_first; mt < g.m_tiles; mt += m_step) {
+      for (int mt = m_first; MT_IN(mt); mt += m_step) {
         if (pair_skipped(g, mt)) continue;
         GT0();
         mbar_wait_cluster(&tempty[acc], acc_phase ^ 1);
@@ -747,7 +753,7 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
     } else {
       // ---------------------------------------------------------------- relay (peer CTA): tell the leader what has landed here
       if (lane == 0) mbar_arrive_remote(peer_w, 0);
-      for (int mt = m_first; mt < g.m_tiles; mt += m_step) {
+      for (int mt = m_first; MT_IN(mt); mt += m_step) {
         if (pair_skipped(g, mt)) continue;
         for (int kb = 0; kb < g.kb_total; ++kb) {
           LG_PI_WAIT(&full[stage], phase);
@@ -779,27 +785,27 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
       const float sc = g.scale[part];
       const int col_in_head = (half & 1) * 32;  // column of this slice inside its 64-wide head row
       auto next_tile = [&](int mt) {
-        for (mt += m_step; mt < g.m_tiles && pair_skipped(g, mt); mt += m_step) {}
+        for (mt += m_step; MT_IN(mt) && pair_skipped(g, mt); mt += m_step) {}
         return mt;
       };
       int acc = 0, iter = 0;
       uint32_t acc_phase = 0;
       if (use_rot && lane == 0) {
         int mt0 = m_first;
-        if (mt0 < g.m_tiles && pair_skipped(g, mt0)) mt0 = next_tile(mt0);
-        if (mt0 < g.m_tiles) {
+        if (MT_IN(mt0) && pair_skipped(g, mt0)) mt0 = next_tile(mt0);
+        if (MT_IN(mt0)) {
           tc::mbar_arrive_expect_tx(&in_bar[ew], STGW);
           tc::tma_load_2d(stg_in, &maps.in, &in_bar[ew], col_in_head, mt0 * 2 * BM + (int)crank * BM + quarter * 32);
         }
       }
-      for (int mt = m_first; mt < g.m_tiles; mt += m_step) {
+      for (int mt = m_first; MT_IN(mt); mt += m_step) {
         if (pair_skipped(g, mt)) continue;
         const int r0 = mt * 2 * BM + (int)crank * BM;       // first row of this CTA's 128-row half (inside one sequence)
         const bool store_rows = !tile_skipped(g, 2 * mt + (int)crank);
         const int seq = r0 / g.Lp, l0 = r0 - seq * g.Lp;
         if (use_rot && lane == 0) {
           const int mn = next_tile(mt);
-          if (mn < g.m_tiles) {  // buffer (iter+1)&1 was read during the previous super-tile
+          if (MT_IN(mn)) {  // buffer (iter+1)&1 was read during the previous super-tile
             const int nb_ = (iter + 1) & 1;
             tc::mbar_arrive_expect_tx(&in_bar[nb_ * NEW + ew], STGW);
             tc::tma_load_2d(stg_in + nb_ * NEW * STGW, &maps.in, &in_bar[nb_ * NEW + ew], col_in_head,
@@ -870,7 +876,7 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
     const bool use_in = g.has_in != 0;
     int acc = 0;
     uint32_t acc_phase = 0, n_in = 0;
-    for (int mt = m_first; mt < g.m_tiles; mt += m_step) {
+    for (int mt = m_first; MT_IN(mt); mt += m_step) {
       if (pair_skipped(g, mt)) continue;
       const int row0 = mt * 2 * BM + (int)crank * BM + quarter * 32;
       const bool store_rows = !tile_skipped(g, 2 * mt + (int)crank);  // rows of a fully padded half stay untouched
@@ -999,6 +1005,8 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
   const uint32_t pair = crank >> 1;             // column half of the 512-wide output
   const uint32_t partner = crank ^ 2;           // same rows, other 256 columns
   const int cid = (int)cluster_id_x(), ncl = (int)n_clusters_x();
+  const int m_first = g.reverse ? g.m_tiles - 1 - cid : cid;  // (see Args::reverse)
+  const int m_step = g.reverse ? -ncl : ncl;
   const int n0 = (int)crank * BN;               // resident W block
   const int pair_col0 = (int)pair * BN2;
   const uint16_t mc_mask = (uint16_t)((1u << crank) | (1u << partner));
@@ -1049,7 +1057,7 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
     tc::pdl_wait();  // activations (and lens) come from the predecessor; the weight block above does not
     int stage = 0;
     uint32_t phase = 0;
-    for (int mt = cid; mt < g.m_tiles; mt += ncl) {
+    for (int mt = m_first; MT_IN(mt); mt += m_step) {
       if (pair_skipped(g, mt)) continue;
       const int row = mt * 2 * BM + (int)parity * BM + (int)pair * 64;  // this CTA loads 64 of the 128 rows
       for (int kb = 0; kb < g.kb_total; ++kb) {
@@ -1060,8 +1068,8 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
           tc::mbar_arrive_expect_tx(&full[stage], A_STAGE);
           tma_load_2d_mc(sA + stage * A_STAGE + (int)pair * (64 * 128), tm, &full[stage], kc, row, mc_mask);
           if (g.prefetch_tiles > 0) {
-            const int mp = mt + g.prefetch_tiles * ncl;
-            if (mp < g.m_tiles) tma_prefetch_l2(tm, kc, mp * 2 * BM + (int)parity * BM + (int)pair * 64);
+            const int mp = mt + g.prefetch_tiles * m_step;
+            if (MT_IN(mp)) tma_prefetch_l2(tm, kc, mp * 2 * BM + (int)parity * BM + (int)pair * 64);
           }
         }
         __syncwarp();
@@ -1085,7 +1093,7 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
       int n_t = 0;
       const bool rec = blockIdx.x == 0 && lane == 0;
 #endif
-      for (int mt = cid; mt < g.m_tiles; mt += ncl) {
+      for (int mt = m_first; MT_IN(mt); mt += m_step) {
         if (pair_skipped(g, mt)) continue;
         GT0();
         mbar_wait_cluster(&tempty[acc], acc_phase ^ 1);
@@ -1122,7 +1130,7 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
     } else {
       // ---------------------------------------------------------------- relay (odd rank): tell the pair's leader what has landed here
       if (lane == 0) mbar_arrive_remote(peer_w, crank - 1);
-      for (int mt = cid; mt < g.m_tiles; mt += ncl) {
+      for (int mt = m_first; MT_IN(mt); mt += m_step) {
         if (pair_skipped(g, mt)) continue;
         for (int kb = 0; kb < g.kb_total; ++kb) {
           LG_PI_WAIT(&full[stage], phase);
@@ -1151,7 +1159,7 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
     long long e_wait = 0, e_stats = 0, e_begin = clock64(), tt;
     const bool rec = blockIdx.x == 0 && ew == 0 && lane == 0;
 #endif
-    for (int mt = cid; mt < g.m_tiles; mt += ncl) {
+    for (int mt = m_first; MT_IN(mt); mt += m_step) {
       if (pair_skipped(g, mt)) continue;
       const int row0 = mt * 2 * BM + (int)parity * BM + quarter * 32;
       const bool store_rows = !tile_skipped(g, 2 * mt + (int)parity);  // rows of a fully padded half stay untouched
@@ -1418,6 +1426,12 @@ int lg_tc_linear_v2(int epilogue, const __nv_bfloat16* A0, const __nv_bfloat16* 
   g.has_in = 0;
   static const int pf = getenv("LGB200_GEMM_PREFETCH") ? atoi(getenv("LGB200_GEMM_PREFETCH")) : 1;
   g.prefetch_tiles = pf;
+  // walking direction of the M tiles (Args::reverse), bit 0: LayerNorm layer (FFN1), bit 1: HEADS projections, bit 2: the
+  // K = 512 ROW layer (FFN2).  Attention writes ctx ascending, so FFN1 walks down (the last-written ctx rows are still in
+  // L2), FFN2 walks up (FFN1 wrote the low rows of `hid` last and has just read the low rows of x), the projection of the
+  // next block walks down again (FFN2 wrote the high rows of x last).
+  static const int rev_mask = getenv("LGB200_GEMM_REVERSE") ? atoi(getenv("LGB200_GEMM_REVERSE")) : 3;
+  g.reverse = ln ? (rev_mask & 1) : epilogue == LGB200_EPI_HEADS ? ((rev_mask >> 1) & 1) : kbig ? ((rev_mask >> 2) & 1) : 0;
   maps.in = maps.a0;
   if (epilogue == LGB200_EPI_HEADS) {
     const uint64_t rows = (uint64_t)T * LG_HEADS;  // [S*4*Lp, 64]

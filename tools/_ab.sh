@@ -1,4 +1,8 @@
 cd /root/repo
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/gputest.log 2>&1; tail -3 gpurun_out/gputest.log | cut -c1-200
-timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r2_final.json 2> gpurun_out/bench_r2_final.err; cut -c1-300 gpurun_out/bench_r2_final.json
-timeout 600 python bench.py --impl reference --steps 8 --warmup 3 > gpurun_out/bench_r2_reference.json 2> gpurun_out/bench_r2_reference.err; cut -c1-400 gpurun_out/bench_r2_reference.json
+timeout 600 python -m pytest tests -m gpu -q -x -k "linear or golden or full_size or ragged" > gpurun_out/gputest_rev.log 2>&1; tail -3 gpurun_out/gputest_rev.log | cut -c1-200
+for r in 0 3 0 3 1 2 4 5 7; do
+  echo "REVERSE=$r $(LGB200_GEMM_REVERSE=$r timeout 300 python tools/profile_step.py --iters 30 2>&1 | tail -1)"
+done 2>&1 | tee gpurun_out/rev_ab.log
+for p in 0 2 3; do
+  echo "PREFETCH=$p $(LGB200_GEMM_PREFETCH=$p timeout 300 python tools/profile_step.py --iters 30 2>&1 | tail -1)"
+done 2>&1 | tee -a gpurun_out/rev_ab.log
