@@ -1,8 +1,4 @@
 cd /root/repo
-timeout 600 python -m pytest tests -m gpu -q -x -k "linear or golden or full_size or ragged" > gpurun_out/gputest_rev.log 2>&1; tail -3 gpurun_out/gputest_rev.log | cut -c1-200
-for r in 0 3 0 3 1 2 4 5 7; do
-  echo "REVERSE=$r $(LGB200_GEMM_REVERSE=$r timeout 300 python tools/profile_step.py --iters 30 2>&1 | tail -1)"
-done 2>&1 | tee gpurun_out/rev_ab.log
-for p in 0 2 3; do
-  echo "PREFETCH=$p $(LGB200_GEMM_PREFETCH=$p timeout 300 python tools/profile_step.py --iters 30 2>&1 | tail -1)"
-done 2>&1 | tee -a gpurun_out/rev_ab.log
+timeout 900 python -m pytest tests/test_gpu_grad.py -q -x > gpurun_out/gputest_bwd.log 2>&1; tail -15 gpurun_out/gputest_bwd.log | cut -c1-300
+(timeout 600 python tools/train_bench.py 32 512 5; timeout 600 python tools/train_bench.py 8 2048 3) 2>&1 | grep -v Warn | tee gpurun_out/train_tc.log | cut -c1-260
+(LGB200_ATTN_BWD_SIMT=1 timeout 600 python tools/train_bench.py 8 2048 3) 2>&1 | grep -v Warn | head -2 | tee gpurun_out/train_simt.log | cut -c1-260
