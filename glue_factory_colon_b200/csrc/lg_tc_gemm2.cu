@@ -86,6 +86,7 @@ struct Args {
   const float* bias;
   const float* gamma;
   const float* beta;
+  void* out16;   // bf16 [T, N] row-major output (the LayerNorm pair kernel stores from registers)
 };
 
 // ---- cluster / DSMEM / bulk-copy primitives --------------------------------------------------
@@ -967,16 +968,32 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
 // LayerNorm: a row's 512 columns live in CTAs r and r^2 (256 each); per-row (sum, sum^2) partials are exchanged
 // with st.async.  The 256 accumulator columns of a CTA do not fit in registers, so the epilogue reads TMEM twice:
 // pass 1 statistics, pass 2 normalise + GELU + store.
+#ifndef LG_FFN1_DIRECT_STORE
+// 1 (experiment, measured and not adopted): the epilogue writes its bf16 rows straight from registers with 256-bit global
+// stores (STG.256: a lane owns 32 consecutive columns of one row = two full 32-byte sectors) instead of staging 16 x 2 KB
+// in shared memory for TMA stores, and the 32 KB go to the A ring (3 -> 5 stages of 16 KB; the issuer spends 2 655 of its
+// 7 227 cycles per 256-row super-tile waiting for A stages).  B200, T = 262 144: 190 us against 141 us with the TMA stores
+// (whole step 21.6 vs 21.2 ms) -- a warp store that touches 32 different rows costs the LSU more than the deeper ring
+// gains (profiles/r2_ffn1_direct_store_ab.txt).
+#define LG_FFN1_DIRECT_STORE 0
+#endif
 struct LayPL {
-  static constexpr int NSTAGE = 3;
+  static constexpr int NSTAGE = LG_FFN1_DIRECT_STORE ? 5 : 3;
   static constexpr int W_BYTES = 128 * 1024;
   static constexpr int OFF_A = W_BYTES;
   static constexpr int OFF_SOUT = OFF_A + NSTAGE * A_STAGE;
-  static constexpr int OFF_PAR = OFF_SOUT + 16 * 2048;      // 16 epilogue warps x (32 rows x 64 B); then bias | gamma | beta, 3 x 256 floats
+  static constexpr int OFF_PAR = OFF_SOUT + (LG_FFN1_DIRECT_STORE ? 0 : 16 * 2048);  // 16 epilogue warps x (32 rows x 64 B); then bias | gamma | beta, 3 x 256 floats
   static constexpr int OFF_STATS = OFF_PAR + 3 * 256 * 4;   // [2 bufs][2 CTAs][128 rows] float2 | local scratch [4][128] float2
   static constexpr int OFF_BAR = OFF_STATS + 2 * 2 * 128 * 8 + 2 * 4 * 128 * 8;  // exchanged partials + 2 local scratch buffers
   static constexpr int SMEM = OFF_BAR + 256;
 };
+static_assert(LayPL::SMEM <= 227 * 1024, "pair-LN kernel: shared memory");
+
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 
 __global__ void __launch_bounds__(576, 1)
 tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
@@ -1148,9 +1165,11 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
     const int ew = warp - 2;        // 0..15
     const int quarter = warp & 3;
     const int cq = ew >> 2;         // 0..3
+#if !LG_FFN1_DIRECT_STORE
     uint8_t* stg_out = smem + L::OFF_SOUT + ew * 2048;  // 32 rows x 64 B, 64-byte swizzle
     const uint32_t my_row_off = (uint32_t)lane * 64u;
     const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+#endif
     const int r_in_tile = quarter * 32 + lane;
     float2* s_local0 = s_stats + 2 * 2 * 128;  // [2 bufs][4 cq][128 rows] partials of this CTA
     int acc = 0, iter = 0;
@@ -1232,6 +1251,13 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
           const float b = gelu_act(fmaf(fmaf(x1, rstd, nmr), s_par[BN2 + c + 1], s_par[2 * BN2 + c + 1]));
           pk[j] = tc::pack_bf16(a, b);
         }
+#if LG_FFN1_DIRECT_STORE
+        if (store_rows) {
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.out16) + (size_t)(row0 + lane) * (2 * BN2) + pair_col0 + cw;
+          st_global_256(dst, pk);
+          st_global_256(dst + 16, pk + 8);
+        }
+#else
         if (lane == 0) bulk_wait_read0();  // previous store has finished reading stg_out
         __syncwarp();
 #pragma unroll
@@ -1244,6 +1270,7 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
           tma_store_2d(&maps.out1, stg_out, pair_col0 + cw, row0);  // out1: 32-column boxes, 64-byte swizzle
           bulk_commit();
         }
+#endif
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       ++iter;
@@ -1421,6 +1448,7 @@ int lg_tc_linear_v2(int epilogue, const __nv_bfloat16* A0, const __nv_bfloat16* 
   g.bias = epi.bias;
   g.gamma = epi.gamma;
   g.beta = epi.beta;
+  g.out16 = epi.out16;
   g.scale[0] = epi.scale[0]; g.scale[1] = epi.scale[1]; g.scale[2] = epi.scale[2];
   g.n_rot = epi.n_rot;
   g.has_in = 0;
