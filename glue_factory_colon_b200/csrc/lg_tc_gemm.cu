@@ -54,7 +54,10 @@ int lg_make_tmap_bf16_sw(CUtensorMap* out, const void* base, int rank, const uin
   }
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr,
                    bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   swizzle_bytes == 0    ? CU_TENSOR_MAP_SWIZZLE_NONE
+                   : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                   : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                         : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? LGB200_OK : LGB200_ERR_DRIVER;
 }

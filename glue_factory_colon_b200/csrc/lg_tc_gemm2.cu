@@ -977,12 +977,20 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
 // gains (profiles/r2_ffn1_direct_store_ab.txt).
 #define LG_FFN1_DIRECT_STORE 0
 #endif
+#ifndef LG_FFN1_HALF_STAGING
+// 1 (experiment, measured and not adopted): the 16 epilogue warps stage 16 columns at a time (32 rows x 32 B, 32-byte
+// swizzle, two TMA stores per 32-column chunk) instead of 32: 16 KB instead of 32 KB of staging, which buys a fourth A
+// stage.  B200: 156 us against 141 us under ncu, whole step 20.79 / 20.85 vs 20.78 / 20.85 ms -- the second
+// wait-for-read + store per chunk costs what the deeper ring gains.
+#define LG_FFN1_HALF_STAGING 0
+#endif
 struct LayPL {
-  static constexpr int NSTAGE = LG_FFN1_DIRECT_STORE ? 5 : 3;
+  static constexpr int NSTAGE = LG_FFN1_DIRECT_STORE ? 5 : LG_FFN1_HALF_STAGING ? 4 : 3;
+  static constexpr int STG_W = LG_FFN1_HALF_STAGING ? 1024 : 2048;  // staging bytes per epilogue warp
   static constexpr int W_BYTES = 128 * 1024;
   static constexpr int OFF_A = W_BYTES;
   static constexpr int OFF_SOUT = OFF_A + NSTAGE * A_STAGE;
-  static constexpr int OFF_PAR = OFF_SOUT + (LG_FFN1_DIRECT_STORE ? 0 : 16 * 2048);  // 16 epilogue warps x (32 rows x 64 B); then bias | gamma | beta, 3 x 256 floats
+  static constexpr int OFF_PAR = OFF_SOUT + (LG_FFN1_DIRECT_STORE ? 0 : 16 * STG_W);  // 16 epilogue warps x (32 rows x 64 B); then bias | gamma | beta, 3 x 256 floats
   static constexpr int OFF_STATS = OFF_PAR + 3 * 256 * 4;   // [2 bufs][2 CTAs][128 rows] float2 | local scratch [4][128] float2
   static constexpr int OFF_BAR = OFF_STATS + 2 * 2 * 128 * 8 + 2 * 4 * 128 * 8;  // exchanged partials + 2 local scratch buffers
   static constexpr int SMEM = OFF_BAR + 256;
@@ -1166,9 +1174,14 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
     const int quarter = warp & 3;
     const int cq = ew >> 2;         // 0..3
 #if !LG_FFN1_DIRECT_STORE
-    uint8_t* stg_out = smem + L::OFF_SOUT + ew * 2048;  // 32 rows x 64 B, 64-byte swizzle
+    uint8_t* stg_out = smem + L::OFF_SOUT + ew * L::STG_W;  // 32 rows x 64 B, 64-byte swizzle (half staging: 32 B rows)
+#if LG_FFN1_HALF_STAGING
+    const uint32_t my_row_off = (uint32_t)lane * 32u;
+    const uint32_t sw = (uint32_t)((lane >> 2) & 1);
+#else
     const uint32_t my_row_off = (uint32_t)lane * 64u;
     const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+#endif
 #endif
     const int r_in_tile = quarter * 32 + lane;
     float2* s_local0 = s_stats + 2 * 2 * 128;  // [2 bufs][4 cq][128 rows] partials of this CTA
@@ -1256,6 +1269,22 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
           __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.out16) + (size_t)(row0 + lane) * (2 * BN2) + pair_col0 + cw;
           st_global_256(dst, pk);
           st_global_256(dst + 16, pk + 8);
+        }
+#elif LG_FFN1_HALF_STAGING
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          if (lane == 0) bulk_wait_read0();  // previous store has finished reading stg_out
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            *reinterpret_cast<uint4*>(stg_out + my_row_off + ((j ^ sw) << 4)) =
+                make_uint4(pk[8 * hh + 4 * j], pk[8 * hh + 4 * j + 1], pk[8 * hh + 4 * j + 2], pk[8 * hh + 4 * j + 3]);
+          tc::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && store_rows) {
+            tma_store_2d(&maps.out1, stg_out, pair_col0 + cw + 16 * hh, row0);  // out1: 16-column boxes, 32-byte swizzle
+            bulk_commit();
+          }
         }
 #else
         if (lane == 0) bulk_wait_read0();  // previous store has finished reading stg_out
@@ -1494,8 +1523,13 @@ int lg_tc_linear_v2(int epilogue, const __nv_bfloat16* A0, const __nv_bfloat16* 
     if ((rc = make_map(&pm.a1, A1, K - K0, T, 64))) return rc;
     {  // output boxes of 32 rows x 32 columns, 64-byte swizzle (one per epilogue warp and column block)
       const uint64_t d[2] = {(uint64_t)N, (uint64_t)T}, sb[1] = {(uint64_t)N * 2};
+#if LG_FFN1_HALF_STAGING
+      const uint32_t bx[2] = {16, 32};
+      if ((rc = lg_make_tmap_bf16_sw(&pm.out1, epi.out16, 2, d, sb, bx, 32))) return rc;
+#else
       const uint32_t bx[2] = {32, 32};
       if ((rc = lg_make_tmap_bf16_sw(&pm.out1, epi.out16, 2, d, sb, bx, 64))) return rc;
+#endif
     }
     return launch_pair_ln(pm, g, st);
   }
