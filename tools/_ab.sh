@@ -1,7 +1,7 @@
 cd /root/repo
-timeout 600 python -m pytest tests -m gpu -q -x -k "linear or golden or full_size or ragged or c2_bf16 or c3" > gpurun_out/gputest_ffn1.log 2>&1; tail -3 gpurun_out/gputest_ffn1.log | cut -c1-200
-for i in 1 2; do
-  echo "32-col staging, 3 stages: $(LGB200_LIB=glue_factory_colon_b200/lib/var/ffn1_full.so timeout 300 python tools/profile_step.py --iters 30 2>&1 | tail -1)"
-  echo "16-col staging, 4 stages: $(timeout 300 python tools/profile_step.py --iters 30 2>&1 | tail -1)"
-done 2>&1 | tee gpurun_out/ffn1_ab2.log
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:tc_pair_ln -c 6 --csv --log-file gpurun_out/ffn1_ncu.csv python tools/profile_step.py --pairs 64 > /dev/null 2>&1; tail -3 gpurun_out/ffn1_ncu.csv | cut -c1-60,200-400
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/gputest.log 2>&1; tail -3 gpurun_out/gputest.log | cut -c1-200
+timeout 600 python tools/fuzz_parity.py 60 777 > gpurun_out/fuzz4.log 2>&1; tail -4 gpurun_out/fuzz4.log | cut -c1-300
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r2_final.json 2> gpurun_out/bench_r2_final.err; cut -c1-300 gpurun_out/bench_r2_final.json
+timeout 600 python bench.py --impl reference --steps 8 --warmup 3 > gpurun_out/bench_r2_reference.json 2> gpurun_out/bench_r2_reference.err; cut -c1-200 gpurun_out/bench_r2_reference.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r2_bf16.csv python tools/profile_step.py --iters 1 > gpurun_out/ncu_ll.log 2>&1; tail -1 gpurun_out/ncu_ll.log
