@@ -266,7 +266,7 @@ def run_reference_arm(args):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -533,13 +533,37 @@ def run_gpu_arm(args):
             "fp32_mode": fp32_tc,
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """Rank 0 prints ONE JSON line on stdout and nothing else: keep a private duplicate of file descriptor 1 for that
+    line and point fd 1 at stderr, so that whatever native libraries write to "stdout" (NCCL prints its version banner
+    there under torchrun when NCCL_DEBUG is set) lands on stderr instead of next to the result."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
