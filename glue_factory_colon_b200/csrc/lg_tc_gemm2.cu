@@ -127,6 +127,31 @@ __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, 
       "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
       : "memory");
 }
+#ifndef LG_PAIR_2SM_TMA
+// 1 (experiment, parity-green, no gain): in the CTA-pair kernels the A loads of BOTH CTAs of a pair complete on the LEADER's
+// `full` barrier (cp.async.bulk.tensor ... .cta_group::2 with the pair bit of the barrier address cleared -- with multicast
+// each destination's copy signals the leader of THAT destination's pair; the leader expects the bytes of both stages), so
+// the issuer does not wait for a relay warp in the peer CTA to poll its own barrier and arrive remotely.  B200: the step is
+// unchanged (20.93 / 20.94 vs 20.94 ms; FFN1 149 us, QKV 119 us under ncu) -- the relay's hand-over (1 047 of the FFN1
+// issuer's 7 227 cycles per super-tile) overlaps the wait for the leader's own stage.  0: the relay (default).
+#define LG_PAIR_2SM_TMA 0
+#endif
+constexpr uint32_t PAIR_LEADER_MASK = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the pair's even CTA
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(tc::smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(bar) & PAIR_LEADER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc_2sm(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                   uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(tc::smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(bar) & PAIR_LEADER_MASK), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                    tc::smem_u32(bar)),
@@ -690,8 +715,13 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
         const CUtensorMap* tm = kb < g.kb_a0 ? &maps.a0 : &maps.a1;
         const int kc = (kb < g.kb_a0 ? kb : kb - g.kb_a0) * BK;
         if (tc::elect_one()) {
+#if LG_PAIR_2SM_TMA
+          if (crank == 0) tc::mbar_arrive_expect_tx(&full[stage], 2 * A_STAGE);  // this stage here and in the peer
+          tma_load_2d_2sm(sA + stage * A_STAGE, tm, &full[stage], kc, row);
+#else
           tc::mbar_arrive_expect_tx(&full[stage], A_STAGE);
           tc::tma_load_2d(sA + stage * A_STAGE, tm, &full[stage], kc, row);
+#endif
           if (g.prefetch_tiles > 0) {
             const int mp = mt + g.prefetch_tiles * m_step;
             if (MT_IN(mp)) tma_prefetch_l2(tm, kc, mp * 2 * BM + (int)crank * BM);
@@ -728,9 +758,11 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
           GT0();
           LG_PI_WAIT(&full[stage], phase);
           GT1(w_full_c);
+#if !LG_PAIR_2SM_TMA
           GT0();
           mbar_wait_cluster(&peer_full[stage], phase);
           GT1(w_peer);
+#endif
           tc::fence_after_sync();
           const uint64_t dA = dA0 + (uint64_t)(stage * (A_STAGE >> 4));
           const uint64_t dW = dW0 + (uint64_t)(kb * (WB_BYTES >> 4));
@@ -754,6 +786,7 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
     } else {
       // ---------------------------------------------------------------- relay (peer CTA): tell the leader what has landed here
       if (lane == 0) mbar_arrive_remote(peer_w, 0);
+#if !LG_PAIR_2SM_TMA
       for (int mt = m_first; MT_IN(mt); mt += m_step) {
         if (pair_skipped(g, mt)) continue;
         for (int kb = 0; kb < g.kb_total; ++kb) {
@@ -763,6 +796,7 @@ tc_pair_row_kernel(const __grid_constant__ Maps maps, const Args g) {
           if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
       }
+#endif
     }
   } else {
     tc::pdl_wait();  // residual / rotary rows, lens and the output buffers belong to the predecessor until here
@@ -1090,8 +1124,15 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
         const CUtensorMap* tm = kb < g.kb_a0 ? &maps.a0 : &maps.a1;
         const int kc = (kb < g.kb_a0 ? kb : kb - g.kb_a0) * BK;
         if (tc::elect_one()) {
+#if LG_PAIR_2SM_TMA
+          // each destination's copy completes on the barrier of that destination's pair leader: a leader collects its own
+          // stage (two 8 KB halves, from ranks r and r^2) and its peer's
+          if (parity == 0) tc::mbar_arrive_expect_tx(&full[stage], 2 * A_STAGE);
+          tma_load_2d_mc_2sm(sA + stage * A_STAGE + (int)pair * (64 * 128), tm, &full[stage], kc, row, mc_mask);
+#else
           tc::mbar_arrive_expect_tx(&full[stage], A_STAGE);
           tma_load_2d_mc(sA + stage * A_STAGE + (int)pair * (64 * 128), tm, &full[stage], kc, row, mc_mask);
+#endif
           if (g.prefetch_tiles > 0) {
             const int mp = mt + g.prefetch_tiles * m_step;
             if (MT_IN(mp)) tma_prefetch_l2(tm, kc, mp * 2 * BM + (int)parity * BM + (int)pair * 64);
@@ -1129,9 +1170,11 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
           GT0();
           LG_PI_WAIT(&full[stage], phase);
           GT1(w_full_c);
+#if !LG_PAIR_2SM_TMA
           GT0();
           mbar_wait_cluster(&peer_full[stage], phase);
           GT1(w_peer);
+#endif
           tc::fence_after_sync();
           const uint64_t dA = dA0 + (uint64_t)(stage * (A_STAGE >> 4));
           const uint64_t dW = dW0 + (uint64_t)(kb * (WB_BYTES >> 4));
@@ -1155,6 +1198,7 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
     } else {
       // ---------------------------------------------------------------- relay (odd rank): tell the pair's leader what has landed here
       if (lane == 0) mbar_arrive_remote(peer_w, crank - 1);
+#if !LG_PAIR_2SM_TMA
       for (int mt = m_first; MT_IN(mt); mt += m_step) {
         if (pair_skipped(g, mt)) continue;
         for (int kb = 0; kb < g.kb_total; ++kb) {
@@ -1164,6 +1208,7 @@ tc_pair_ln_kernel(const __grid_constant__ Maps maps, const Args g) {
           if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
       }
+#endif
     }
   } else {
     tc::pdl_wait();  // residual / rotary rows, lens and the output buffers belong to the predecessor until here
