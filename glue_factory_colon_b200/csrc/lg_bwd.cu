@@ -1,8 +1,10 @@
 // Backward kernels of the training path ("training forward + loss", the part the reference
-// gets from autograd, lightglue.py:484-498, 588-637).  fp32, CUDA cores: the training step is not the benchmarked path,
-// what counts here is that the fused forward ops have fused backward ops (nothing N x M is materialised by the
-// attention backward either) and that gradients agree with the reference's autograd.  Plain GEMMs of the backward
-// (dX = dY.W, dW = dY^T.X) are left to cuBLAS through torch.matmul on the host side (glue_factory_colon_b200/train.py).
+// gets from autograd, lightglue.py:484-498, 588-637).  Everything is fp32-accurate; the training step is not the
+// benchmarked path, what counts here is that the fused forward ops have fused backward ops (nothing N x M is materialised
+// by the attention backward either) and that gradients agree with the reference's autograd.  The attention backward runs
+// on the tensor cores (3xTF32 warp MMAs, `*_tc_kernel` below; the CUDA-core versions are kept behind
+// LGB200_ATTN_BWD_SIMT=1); plain GEMMs of the backward (dX = dY.W, dW = dY^T.X) are left to cuBLAS through torch.matmul
+// on the host side (glue_factory_colon_b200/train.py).
 //
 //   attn_bwd_stats_kernel   per query row: lse (log2 domain) and delta = <dO, O>          (flash-attention backward,
 //   attn_bwd_kernel<false>  dQ for 64 queries, sweeping the keys                           recomputing S tile by tile)
