@@ -1,5 +1,6 @@
 cd /root/repo
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/gputest.log 2>&1; tail -3 gpurun_out/gputest.log | cut -c1-200
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r2_final.json 2> gpurun_out/bench_r2_final.err; wc -l gpurun_out/bench_r2_final.json; cut -c1-200 gpurun_out/bench_r2_final.json
-timeout 600 python bench.py --impl reference --steps 8 --warmup 3 > gpurun_out/bench_r2_reference.json 2> gpurun_out/bench_r2_reference.err; cut -c1-200 gpurun_out/bench_r2_reference.json
+echo "token: $(timeout 120 python tools/attn_bwd_bench.py 16 2048 10 2>&1 | tail -1)"
+echo "no token: $(LGB200_ATTN_BWD_TOKEN=0 timeout 120 python tools/attn_bwd_bench.py 16 2048 10 2>&1 | tail -1)"
+echo "token 64x512: $(timeout 120 python tools/attn_bwd_bench.py 64 512 10 2>&1 | tail -1)"
+echo "no token 64x512: $(LGB200_ATTN_BWD_TOKEN=0 timeout 120 python tools/attn_bwd_bench.py 64 512 10 2>&1 | tail -1)"
+timeout 600 python -m pytest tests/test_gpu_grad.py -q -x 2>&1 | tail -2 | cut -c1-300
