@@ -5,8 +5,9 @@ layer's descriptors in training mode, :588-637 turns them into the deep-supervis
 `loss.backward()`).  Here the same contract is met by two `torch.autograd.Function`s whose backward is written by hand:
 
   * `TransformerFn`  descriptors (+ every transformer / posenc / input_proj parameter) -> ref_descriptors0/1
-    [B, n_layers, N, 256].  Forward = the library's fp32 kernels (lgb200_linear; attention in the fp32-accurate
-    tensor-core mode), keeping the two block inputs of every layer plus -- unless conf.checkpointed
+    [B, n_layers, N, 256].  Forward = the library's fp32-accurate tensor-core kernels (linear layers and attention in the
+    split-fp16 / three-MMA mode of lg_x3.cu / lg_x3_attn.cu; LGB200_TRAIN_SIMT_LINEAR=1 selects the CUDA-core fp32 linear
+    kernels), keeping the two block inputs of every layer plus -- unless conf.checkpointed
     (lightglue.py:485-494) -- q / k / v / context / message; with conf.checkpointed those are recomputed in the
     backward pass with the same kernels.  The pre-LayerNorm activations are always recomputed (one GEMM).  Backward =
     the hand-written kernels of csrc/lg_bwd.cu:
@@ -17,8 +18,9 @@ layer's descriptors in training mode, :588-637 turns them into the deep-supervis
     the library's assignment + reduction kernels; backward = lgb200_assign_dsim (d similarity of the double softmax).
 
 Plain GEMMs of the backward pass (dX = dY.W, dW = dY^T.X) go to cuBLAS through torch.matmul -- they are library
-GEMMs with nothing to fuse.  Everything runs in fp32 whatever conf.precision says (the bf16 / split-fp16 tensor-core
-kernels are inference kernels); CPU tensors raise as everywhere else in this package.
+GEMMs with nothing to fuse, and gradients span a range (1e-8 ... 1e-2) that the split-fp16 operand format does not
+cover.  Everything is fp32-accurate whatever conf.precision says (the bf16 kernels are inference kernels); CPU tensors
+raise as everywhere else in this package.
 """
 from __future__ import annotations
 
@@ -37,6 +39,8 @@ Q_SCALE = LOG2E / math.sqrt(64.0)   # folded into q: the attention kernels work 
 C_SCALE = math.sqrt(Q_SCALE)        # cross block: to_qk feeds both sides (lightglue.py:208)
 N_PARTIALS = 296                    # CTAs of lgb200_ln_gelu_bwd (2 per SM)
 _SIMT_ATTN = os.environ.get("LGB200_TRAIN_SIMT_ATTN", "0") == "1"
+_SIMT_LINEAR = os.environ.get("LGB200_TRAIN_SIMT_LINEAR", "0") == "1"
+_X3_WEIGHTS = ("qkv_w", "so_w", "sf0_w", "sf3_w", "cqv_w", "co_w", "cf0_w", "cf3_w")
 # packed Wqkv row r holds reference row _PERM[r] (lightglue.py:158: head*192 + d*3 + part -> part*256 + head*64 + d)
 _PERM = torch.arange(768).view(4, 64, 3).permute(2, 0, 1).reshape(-1)
 
@@ -72,6 +76,22 @@ class _Kern:
                                      None, ptr(rot), None, n_rot, ptr(outp[0]), ptr(outp[1]), ptr(outp[2]), ptr(gamma),
                                      ptr(beta), self.st), "lgb200_linear")
 
+    def linear3(self, epi, A0, W, b, N, K, A1=None, K0=None, scale=(1.0, 1.0, 1.0), resid=None, out=None, out32=None,
+                rot=None, n_rot=0, outp=(None, None, None), gamma=None, beta=None):
+        """The same layer in the fp32-accurate tensor-core mode (lg_x3.cu): A0 / A1 / W / out / outp are split-fp16
+        planes, resid / out32 / rot fp32."""
+        check(self.lib.lgb200_linear(F32X3, epi, ptr(A0), ptr(A1), K if K0 is None else K0, ptr(W), ptr(b), self.T, N, K,
+                                     ptr(self.lens), self.Lp, scale[0], scale[1], scale[2], ptr(resid), None, ptr(out32),
+                                     ptr(out), ptr(rot), None, n_rot, ptr(outp[0]), ptr(outp[1]), ptr(outp[2]), ptr(gamma),
+                                     ptr(beta), self.st), "lgb200_linear (x3)")
+
+    def planes(self, *shape):
+        return torch.zeros(2, *shape, device=self.dev, dtype=torch.float16)
+
+    def unsplit(self, p, *shape):
+        """split planes (x * 64 = hi + lo) -> fp32"""
+        return torch.add(p[0].float(), p[1].float()).mul_(1.0 / 64.0).view(*shape)
+
     def split(self, t):
         """fp32 -> split-fp16 planes [2][n] (x * 64 = hi + lo), the operand format of the LGB200_F32X3 kernels."""
         out = torch.empty(2, t.numel(), device=self.dev, dtype=torch.float16)
@@ -86,14 +106,18 @@ class _Kern:
             check(self.lib.lgb200_attention(F32, ptr(q), ptr(k), ptr(v), self.S, self.Lp, ptr(self.lens), kv_xor, ptr(ctx),
                                             self.st), "lgb200_attention")
             return
-        qp = self.split(q)
-        kp = qp if k is q else self.split(k)
-        vp = self.split(v)
+        if q.dtype == torch.float16:  # already split planes (x3 projections)
+            qp, kp, vp = q, k, v
+        else:
+            qp = self.split(q)
+            kp = qp if k is q else self.split(k)
+            vp = self.split(v)
         cp = torch.zeros(2, self.T, 256, device=self.dev, dtype=torch.float16)
         check(self.lib.lgb200_attention(F32X3, ptr(qp), ptr(kp), ptr(vp), self.S, self.Lp, ptr(self.lens), kv_xor, ptr(cp),
                                         self.st), "lgb200_attention")
         torch.add(cp[0].float(), cp[1].float(), out=ctx)
         ctx.mul_(1.0 / 64.0)
+        return cp
 
     def attention_bwd(self, q, k, v, ctx, dctx, kv_xor):
         dq, dk, dv = self.empty(self.T * 256), self.empty(self.T * 256), self.empty(self.T * 256)
@@ -169,42 +193,90 @@ def transformer_params(model) -> List[Tuple[object, nn.Parameter]]:
 # ---- one transformer layer, forward pieces (lightglue.py:151-164, 193-222) ---------------------------------------
 
 
-def _self_attend(k: _Kern, w: Dict, x, rot):
-    T = k.T
-    q, kk, v = k.zeros(T * 256), k.zeros(T * 256), k.zeros(T * 256)
-    k.linear(EPI_HEADS, x, w["qkv_w"], w["qkv_b"], 768, 256, scale=(Q_SCALE, 1.0, 1.0), rot=rot, n_rot=2, outp=(q, kk, v))
-    ctx = k.zeros(T, 256)
-    k.attention(q, kk, v, 0, ctx)
-    msg = k.zeros(T, 256)
-    k.linear(EPI_ROWMAJOR, ctx, w["so_w"], w["so_b"], 256, 256, out=msg)
-    return q, kk, v, ctx, msg
+def x3_weights(w: Dict) -> Dict:
+    """Split-fp16 planes [2][N][K] of a layer's weight matrices (256 w = hi + lo, the operand format of lg_x3.cu)."""
+    out = {}
+    for name in _X3_WEIGHTS:
+        t = w[name].detach().float() * 256.0
+        hi = t.to(torch.float16)
+        out[name] = torch.stack([hi, (t - hi.float()).to(torch.float16)]).contiguous()
+    return out
 
 
-def _cross_attend(k: _Kern, w: Dict, x):
+def _self_attend(k: _Kern, w: Dict, x, rot, fp32_heads: bool = True):
+    """-> (q, k, v, ctx, msg); with the tensor-core linears q / k / v are None unless `fp32_heads` (the backward kernels
+    read them in fp32)."""
     T = k.T
-    qk, v = k.zeros(T * 256), k.zeros(T * 256)
-    k.linear(EPI_HEADS, x, w["cqv_w"], w["cqv_b"], 512, 256, scale=(C_SCALE, 1.0, 1.0), n_rot=0, outp=(qk, v, None))
+    if _SIMT_LINEAR:
+        q, kk, v = k.zeros(T * 256), k.zeros(T * 256), k.zeros(T * 256)
+        k.linear(EPI_HEADS, x, w["qkv_w"], w["qkv_b"], 768, 256, scale=(Q_SCALE, 1.0, 1.0), rot=rot, n_rot=2,
+                 outp=(q, kk, v))
+        ctx = k.zeros(T, 256)
+        k.attention(q, kk, v, 0, ctx)
+        msg = k.zeros(T, 256)
+        k.linear(EPI_ROWMAJOR, ctx, w["so_w"], w["so_b"], 256, 256, out=msg)
+        return q, kk, v, ctx, msg
+    wx = w["x3"]
+    qp, kp, vp = k.planes(T * 256), k.planes(T * 256), k.planes(T * 256)
+    k.linear3(EPI_HEADS, k.split(x), wx["qkv_w"], w["qkv_b"], 768, 256, scale=(Q_SCALE, 1.0, 1.0), rot=rot, n_rot=2,
+              outp=(qp, kp, vp))
     ctx = k.zeros(T, 256)
-    k.attention(qk, qk, v, 1, ctx)
+    cp = k.attention(qp, kp, vp, 0, ctx)
     msg = k.zeros(T, 256)
-    k.linear(EPI_ROWMAJOR, ctx, w["co_w"], w["co_b"], 256, 256, out=msg)
-    return qk, v, ctx, msg
+    k.linear3(EPI_ROWMAJOR, cp, wx["so_w"], w["so_b"], 256, 256, out32=msg)
+    if not fp32_heads:
+        return None, None, None, ctx, msg
+    return k.unsplit(qp, T * 256), k.unsplit(kp, T * 256), k.unsplit(vp, T * 256), ctx, msg
+
+
+def _cross_attend(k: _Kern, w: Dict, x, fp32_heads: bool = True):
+    T = k.T
+    if _SIMT_LINEAR:
+        qk, v = k.zeros(T * 256), k.zeros(T * 256)
+        k.linear(EPI_HEADS, x, w["cqv_w"], w["cqv_b"], 512, 256, scale=(C_SCALE, 1.0, 1.0), n_rot=0, outp=(qk, v, None))
+        ctx = k.zeros(T, 256)
+        k.attention(qk, qk, v, 1, ctx)
+        msg = k.zeros(T, 256)
+        k.linear(EPI_ROWMAJOR, ctx, w["co_w"], w["co_b"], 256, 256, out=msg)
+        return qk, v, ctx, msg
+    wx = w["x3"]
+    qp, vp = k.planes(T * 256), k.planes(T * 256)
+    k.linear3(EPI_HEADS, k.split(x), wx["cqv_w"], w["cqv_b"], 512, 256, scale=(C_SCALE, 1.0, 1.0), n_rot=0,
+              outp=(qp, vp, None))
+    ctx = k.zeros(T, 256)
+    cp = k.attention(qp, qp, vp, 1, ctx)
+    msg = k.zeros(T, 256)
+    k.linear3(EPI_ROWMAJOR, cp, wx["co_w"], w["co_b"], 256, 256, out32=msg)
+    if not fp32_heads:
+        return None, None, ctx, msg
+    return k.unsplit(qp, T * 256), k.unsplit(vp, T * 256), ctx, msg
 
 
 def _ffn(k: _Kern, w: Dict, pre: str, x, msg):
     """x + ffn(cat[x, msg]) (lightglue.py:164, 220-221)."""
-    hid = k.zeros(k.T, 512)
-    k.linear(EPI_LN_GELU, x, w[pre + "f0_w"], w[pre + "f0_b"], 512, 512, A1=msg, K0=256, gamma=w[pre + "ln_g"],
-             beta=w[pre + "ln_b"], out=hid)
     out = k.zeros(k.T, 256)
-    k.linear(EPI_ROWMAJOR, hid, w[pre + "f3_w"], w[pre + "f3_b"], 256, 512, resid=x, out=out)
+    if _SIMT_LINEAR:
+        hid = k.zeros(k.T, 512)
+        k.linear(EPI_LN_GELU, x, w[pre + "f0_w"], w[pre + "f0_b"], 512, 512, A1=msg, K0=256, gamma=w[pre + "ln_g"],
+                 beta=w[pre + "ln_b"], out=hid)
+        k.linear(EPI_ROWMAJOR, hid, w[pre + "f3_w"], w[pre + "f3_b"], 256, 512, resid=x, out=out)
+        return out
+    wx = w["x3"]
+    hp = k.planes(k.T, 512)
+    k.linear3(EPI_LN_GELU, k.split(x), wx[pre + "f0_w"], w[pre + "f0_b"], 512, 512, A1=k.split(msg), K0=256,
+              gamma=w[pre + "ln_g"], beta=w[pre + "ln_b"], out=hp)
+    k.linear3(EPI_ROWMAJOR, hp, wx[pre + "f3_w"], w[pre + "f3_b"], 256, 512, resid=x, out32=out)
     return out
 
 
 def _ffn_bwd(k: _Kern, w: Dict, pre: str, x, msg, dy):
     """Backward of y = ffn(cat[x, msg]) given dy [T,256]: (d x, d msg, parameter gradients)."""
     h = k.zeros(k.T, 512)  # pre-LayerNorm activations, recomputed
-    k.linear(EPI_ROWMAJOR, x, w[pre + "f0_w"], w[pre + "f0_b"], 512, 512, A1=msg, K0=256, out=h)
+    if _SIMT_LINEAR:
+        k.linear(EPI_ROWMAJOR, x, w[pre + "f0_w"], w[pre + "f0_b"], 512, 512, A1=msg, K0=256, out=h)
+    else:
+        k.linear3(EPI_ROWMAJOR, k.split(x), w["x3"][pre + "f0_w"], w[pre + "f0_b"], 512, 512, A1=k.split(msg), K0=256,
+                  out32=h)
     da = dy @ w[pre + "f3_w"]
     dh, act, gsum = k.ln_gelu_bwd(h, w[pre + "ln_g"], w[pre + "ln_b"], da)
     g = {
@@ -227,6 +299,10 @@ class TransformerFn(torch.autograd.Function):
         k = _Kern(dev, B, m, n)
         W = model._pack(F32, dev)
         L = model.conf.n_layers
+        if not _SIMT_LINEAR:  # split-fp16 planes of the weight matrices, cached with the pack (rebuilt when a weight changes)
+            for w in W["layers"]:
+                if "x3" not in w:
+                    w["x3"] = x3_weights(w)
         xin = None
         if isinstance(model.input_proj, nn.Linear):
             din = model.conf.input_dim
@@ -247,10 +323,10 @@ class TransformerFn(torch.autograd.Function):
         for i in range(L):
             w = W["layers"][i]
             xs_in.append(x)
-            sa = _self_attend(k, w, x, rot)
+            sa = _self_attend(k, w, x, rot, fp32_heads=keep)
             x = _ffn(k, w, "s", x, sa[-1])
             xs_mid.append(x)
-            ca = _cross_attend(k, w, x)
+            ca = _cross_attend(k, w, x, fp32_heads=keep)
             x = _ffn(k, w, "c", x, ca[-1])
             outs.append(x)
             kept.append((sa, ca) if keep else None)
