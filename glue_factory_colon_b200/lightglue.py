@@ -223,18 +223,22 @@ class LightGlue(nn.Module):
     def _log_assignment_of(self, lib, prec, d0, d1, layer: int, gt, token_layer: Optional[int] = None,
                            keep: Optional[dict] = None):
         """MatchAssignment `layer` applied to descriptors d0 [B,m,256] / d1 [B,n,256] (lightglue.py:279-288 as called
-        from loss_params, :589-595) and the loss reductions on its output.  fp32: the forward's assignment kernels
-        write scores [B,m+1,n+1], lgb200_loss_reduce reads them.  bf16: lgb200_assign_loss, the tcgen05 pass 2 with the
+        from loss_params, :589-595) and the loss reductions on its output.  fp32 (CUDA cores) / fp32-accurate tensor-core
+        mode (F32X3: split-fp16 final_proj and similarity GEMM): the forward's assignment kernels write scores
+        [B,m+1,n+1], lgb200_loss_reduce reads them.  bf16: lgb200_assign_loss, the tcgen05 pass 2 with the
         reductions in its epilogue -- the matrix is never written.  Returns (pos_sum, pos_cnt, row_exp, row_arg,
         col_arg, dustbin column la[:, :m, n], dustbin row la[:, m, :n], token logits of `token_layer` or None)."""
         bf = prec == BF16
+        x3 = prec == F32X3  # fp32-accurate tensor-core mode: split-fp16 final_proj + similarity GEMM, fp32 normalisers
+        hprec = F32 if x3 else prec  # the per-token heads read the fp32 rows in x3 mode
         dev = d0.device
         B, m, _ = d0.shape
         n = d1.shape[1]
         W = self._pack(prec, dev)
         st = torch.cuda.current_stream(dev).cuda_stream
         S = 2 * B
-        Lp = max(128, ((max(m, n) + 127) // 128) * 128)
+        pad = 256 if x3 else 128  # (the x3 similarity GEMM works on 256-column blocks)
+        Lp = max(pad, ((max(m, n) + pad - 1) // pad) * pad)
         T = S * Lp
         f32 = dict(device=dev, dtype=torch.float32)
         adt = dict(device=dev, dtype=torch.bfloat16 if bf else torch.float32)
@@ -242,24 +246,37 @@ class LightGlue(nn.Module):
         if m != Lp or n != Lp:
             lens = torch.tensor([m, n] * B, device=dev, dtype=torch.int32)
         x = torch.zeros(T, 256, **adt)
-        md = torch.zeros(T, 256, **adt)
         for img, dsc, cnt in ((0, d0, m), (1, d1, n)):
             dsc = dsc.to(torch.float32).contiguous()
             x32_, x16_ = (None, x) if bf else (x, None)
             check(lib.lgb200_pack_rows(ptr(dsc), B, cnt, 256, img, Lp, ptr(x32_), ptr(x16_), st), "pack_rows")
         a = W["assign"][layer]
-        o32, o16 = (None, md) if bf else (md, None)
+        if x3:
+            xs = torch.empty(2, T, 256, device=dev, dtype=torch.float16)
+            check(lib.lgb200_split_rows(ptr(x), x.numel(), ptr(xs), st), "split_rows")
+            md = torch.zeros(2, T, 256, device=dev, dtype=torch.float16)
+            a_in, o32, o16 = xs, None, md
+        else:
+            md = torch.zeros(T, 256, **adt)
+            a_in = x
+            o32, o16 = (None, md) if bf else (md, None)
         check(
             lib.lgb200_linear(
-                prec, EPI_ROWMAJOR, ptr(x), None, 256, ptr(a["fp_w"]), ptr(a["fp_b"]), T, 256, 256, ptr(lens), Lp,
+                prec, EPI_ROWMAJOR, ptr(a_in), None, 256, ptr(a["fp_w"]), ptr(a["fp_b"]), T, 256, 256, ptr(lens), Lp,
                 0.25, 1.0, 1.0, None, None, ptr(o32), ptr(o16), None, None, 0, None, None, None, None, None, st,
             ),
             "lgb200_linear",
         )
         z = torch.zeros(T, **f32)
         lse = torch.zeros(T, **f32)
-        check(lib.lgb200_rowdot(prec, ptr(x), ptr(a["m_w"]), ptr(a["m_b"]), S, Lp, ptr(lens), 0, ptr(z), st), "rowdot")
-        check(lib.lgb200_assign_lse(prec, ptr(md), S, Lp, ptr(lens), ptr(lse), st), "assign_lse")
+        check(lib.lgb200_rowdot(hprec, ptr(x), ptr(a["m_w"]), ptr(a["m_b"]), S, Lp, ptr(lens), 0, ptr(z), st), "rowdot")
+        sim = None
+        if x3:
+            sim = torch.empty(B, Lp, Lp, **f32)
+            check(lib.lgb200_x3_similarity(ptr(md), B, Lp, ptr(lens), ptr(sim), st), "x3_similarity")
+            check(lib.lgb200_x3_assign_lse(ptr(sim), B, Lp, ptr(lens), m, n, ptr(lse), st), "x3_assign_lse")
+        else:
+            check(lib.lgb200_assign_lse(prec, ptr(md), S, Lp, ptr(lens), ptr(lse), st), "assign_lse")
         R, C = m + 1, n + 1
         if keep is not None:  # what the backward pass (train.AssignFn) and the training forward need
             keep.update(z=z, lse=lse, Lp=Lp, lens=lens)
@@ -276,8 +293,12 @@ class LightGlue(nn.Module):
             dust0, dust1 = ls(-zv[:, 0, :m]), ls(-zv[:, 1, :n])  # lightglue.py:266-267
         else:
             scores = torch.empty(B, R, C, **f32)
-            check(lib.lgb200_assign_scores(prec, ptr(md), ptr(z), ptr(lse), B, Lp, ptr(lens), R, C, ptr(scores), None, st),
-                  "assign_scores")
+            if x3:
+                check(lib.lgb200_x3_assign_scores(ptr(sim), ptr(z), ptr(lse), B, Lp, ptr(lens), R, C, ptr(scores), st),
+                      "x3_assign_scores")
+            else:
+                check(lib.lgb200_assign_scores(prec, ptr(md), ptr(z), ptr(lse), B, Lp, ptr(lens), R, C, ptr(scores), None,
+                                               st), "assign_scores")
             pos_sum, pos_cnt, row_exp, row_arg, col_arg = self._reduce(lib, scores, gt, st)
             dust0, dust1 = scores[:, :m, n], scores[:, m, :n]
             if keep is not None:
@@ -286,7 +307,7 @@ class LightGlue(nn.Module):
         if token_layer is not None:
             tk = W["token"][token_layer]
             lg_ = torch.zeros(T, **f32)
-            check(lib.lgb200_rowdot(prec, ptr(x), ptr(tk["w"]), ptr(tk["b"]), S, Lp, ptr(lens), 0, ptr(lg_), st), "rowdot")
+            check(lib.lgb200_rowdot(hprec, ptr(x), ptr(tk["w"]), ptr(tk["b"]), S, Lp, ptr(lens), 0, ptr(lg_), st), "rowdot")
             lv = lg_.view(B, 2, Lp)
             logits = (lv[:, 0, :m], lv[:, 1, :n])
         return pos_sum, pos_cnt, row_exp, row_arg, col_arg, dust0, dust1, logits
@@ -331,7 +352,7 @@ class LightGlue(nn.Module):
         B, N, m, _ = r0.shape
         n = r1.shape[2]
         prec = self._precision()
-        if prec == F32X3 or with_grad:  # the loss reductions of the fp32 mode run in the CUDA-core fp32 kernels
+        if with_grad:  # (train.AssignFn picks the fp32-accurate kernels itself)
             prec = F32
         st = torch.cuda.current_stream(dev).cuda_stream
         L = conf.n_layers

@@ -405,7 +405,7 @@ class AssignFn(torch.autograd.Function):
         lib = _abi.load()
         keep: Dict = {}
         pos_sum, pos_cnt, row_exp, row_arg, col_arg, dust0, dust1, _ = model._log_assignment_of(
-            lib, F32, d0, d1, layer, gt, keep=keep)
+            lib, F32 if _SIMT_LINEAR else F32X3, d0, d1, layer, gt, keep=keep)
         ctx.save_for_backward(d0, d1, fp_w, fp_b, m_w, gt, keep["z"], keep["lse"])
         ctx.Lp = keep["Lp"]
         ctx.mark_non_differentiable(pos_cnt, row_exp, row_arg, col_arg)

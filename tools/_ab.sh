@@ -1,3 +1,3 @@
 cd /root/repo
-timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/train_ll.csv python tools/train_profile.py 8 2048 > gpurun_out/train_ll.log 2>&1; tail -2 gpurun_out/train_ll.log
-python tools/summarize_launches.py gpurun_out/train_ll.csv | head -40 | cut -c1-170
+timeout 900 python -m pytest tests/test_gpu_grad.py tests/test_gpu_loss.py tests/test_gpu_x3.py -q -x > gpurun_out/gputest_bwd.log 2>&1; tail -8 gpurun_out/gputest_bwd.log | cut -c1-300
+(timeout 600 python tools/train_bench.py 32 512 5; timeout 600 python tools/train_bench.py 8 2048 3) 2>&1 | grep -v Warn | grep glue_factory | tee gpurun_out/train_x3loss.log | cut -c1-230
