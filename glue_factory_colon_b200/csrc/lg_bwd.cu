@@ -663,6 +663,10 @@ extern "C" int lgb200_attention_bwd(const float* Q, const float* K, const float*
   if ((e = cudaMemsetAsync(dK, 0, nb, st)) != cudaSuccess) return (int)e;
   if ((e = cudaMemsetAsync(dV, 0, nb, st)) != cudaSuccess) return (int)e;
   static const int simt = getenv("LGB200_ATTN_BWD_SIMT") ? atoi(getenv("LGB200_ATTN_BWD_SIMT")) : 0;
+  // default: tcgen05 kernels on split-fp16 planes (lg_x3_attn_bwd.cu).  LGB200_ATTN_BWD_MMASYNC=1 selects the 3xTF32
+  // warp-MMA kernels below, LGB200_ATTN_BWD_SIMT=1 the CUDA-core ones (both kept as cross-checks).
+  static const int mmasync = getenv("LGB200_ATTN_BWD_MMASYNC") ? atoi(getenv("LGB200_ATTN_BWD_MMASYNC")) : 0;
+  if (!simt && !mmasync) return lg_x3_attention_bwd(Q, K, V, ctx, dctx, S, Lp, lens, kv_xor, dQ, dK, dV, workspace, st);
   const int smem = simt ? (int)sizeof(AbSmem) : (int)sizeof(TbSmem);
   auto k_stats = simt ? attn_bwd_stats_kernel : attn_bwd_stats_tc_kernel;
   auto k_dq = simt ? attn_bwd_kernel<false> : attn_bwd_tc_kernel<false>;
@@ -679,6 +683,13 @@ extern "C" int lgb200_attention_bwd(const float* Q, const float* K, const float*
   LG_LAUNCH_CHECK();
   k_dkv<<<grid, 256, smem, st>>>(Q, K, V, dctx, Lp, lens, kv_xor, lse2, dlt, dK, dV);
   LG_LAUNCH_CHECK();
+  return LGB200_OK;
+}
+
+extern "C" int lgb200_attention_bwd_workspace(int S, int Lp, long long* n_floats) {
+  if (!n_floats) return LGB200_ERR_NULL;
+  if (S <= 0 || Lp <= 0 || Lp % 128) return LGB200_ERR_SHAPE;
+  *n_floats = (long long)lg_x3_attention_bwd_ws_floats(S, Lp);
   return LGB200_OK;
 }
 

@@ -35,6 +35,11 @@ int lg_x3_linear(int epilogue, const void* A0, const void* A1, int K0, const voi
                  const int32_t* lens, LgEpi epi, void* outs, cudaStream_t st);
 int lg_x3_attention(const void* Q, const void* K, const void* V, int S, int Lp, const int32_t* lens, int kv_xor,
                     void* ctx, cudaStream_t st);
+// attention backward on tcgen05, split-fp16 operands (lg_x3_attn_bwd.cu)
+size_t lg_x3_attention_bwd_ws_floats(int S, int Lp);
+int lg_x3_attention_bwd(const float* Q, const float* K, const float* V, const float* ctx, const float* dctx, int S,
+                        int Lp, const int32_t* lens, int kv_xor, float* dQ, float* dK, float* dV, float* ws,
+                        cudaStream_t st);
 // x3 plane scaling: a plane pair stores x * 2^e so that the LOW plane stays a normal fp16 number (fp16 normals end at
 // 6.1e-5 and lo ~ 2^-11 |x|: unscaled, the low planes of all weights and of every activation below 0.12 are subnormal
 // (or flushed) and the pair carries ~12 bits instead of 22).  Powers of two: exact, undone in the consuming epilogue.

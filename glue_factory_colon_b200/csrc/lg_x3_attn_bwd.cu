@@ -1,0 +1,475 @@
+// Flash-attention backward on tcgen05 (sm_100a), fp32-accurate: split-fp16 operands ("x3", see lg_x3.cu / lg_x3_attn.cu),
+// head_dim 64.  Backward of Attention.forward (lightglue.py:112-129) as autograd would give it for the reference's
+// training step (lightglue.py:484-498); nothing N x M is stored, the scores are recomputed tile by tile.
+//
+// One kernel template, two roles -- "own" rows X, U (128 per CTA) against tiles of 64 "other" rows Y, W:
+//
+//   role   own X  own U  other Y  other W   sc = X.Y^T   dp = U.W^T    out1 += D.Y          out2 += P.W
+//   DQ     Q      dO     K        V         S            dP            dQ  (x ln 2)         --
+//   DKV    K      V      Q        dO        S^T          dP^T          dK  (x ln 2)         dV
+//
+//   P = 2^(sc - lse[query]),  D = P (dp - delta[query]),  delta = <dO, O>   (the query is the row in DQ, the column in DKV)
+//
+// Every product is three SS / TS MMAs on fp16 plane pairs (hi.hi + hi.lo + lo.hi, fp32 accumulation in TMEM): the
+// operands Q, K, V carry the activation scaling LG_X3_EA, dO a per-call power of two g chosen so that max |g dO| lies in
+// [256, 512) (gradients have no fixed range: a fixed scaling would push small ones into the fp16 subnormals), P the
+// scaling LG_X3_EP and D the scaling g / 64; all are powers of two and are undone exactly in the epilogue.
+// CTA = warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 "softmax" warps (two threads per own row, 32 score columns
+// each).  TMEM (512 columns, one CTA per SM): sc x 2 | dp x 2 (double-buffered: the score MMAs of tile j+1 run while the
+// warps work on tile j) | D hi, lo | P hi, lo | out1 | out2.  The DQ role first sweeps the other tiles once for the row
+// statistics (log-sum-exp in the log2 domain and delta; written to the workspace for the DKV role), then a second time
+// for dQ.
+#include "lg_internal.cuh"
+#include "lg_tc_common.cuh"
+#include <cuda_fp16.h>
+
+namespace {
+
+constexpr int XB_OT = 64;                       // other rows per tile
+constexpr int XB_TBO = 128 * 64 * 2;            // one plane of an own tile (128 x 64 fp16, 128-byte swizzle): 16 KB
+constexpr int XB_TBY = XB_OT * 64 * 2;          // one plane of an other tile: 8 KB
+constexpr int XB_NST = 3;                       // stages of (Yh | Yl | Wh | Wl)
+constexpr int XB_X = 0;                         // Xh | Xl
+constexpr int XB_U = 2 * XB_TBO;                // Uh | Ul
+constexpr int XB_Y = 4 * XB_TBO;                // XB_NST x 32 KB
+constexpr int XB_BAR = XB_Y + XB_NST * 4 * XB_TBY;  // 160 KB of tiles
+constexpr int XB_NBAR = 1 + 2 * XB_NST + 2 + 2 + 1 + 1;
+constexpr int XB_XCH = XB_BAR + 256;            // [128 rows][2 parts] float4 (max, sum, partial delta)
+constexpr int XB_SMEM = XB_XCH + 128 * 2 * 16;
+constexpr uint32_t XT_SC = 0, XT_DP = 128, XT_DH = 256, XT_DL = 288, XT_PH = 320, XT_PL = 352, XT_O1 = 384, XT_O2 = 448;
+constexpr float XB_DC = 1.f / 64.f;             // D planes hold (g / 64) D
+constexpr float XB_LN2 = 0.69314718055994530942f;
+
+__host__ __device__ constexpr uint32_t xb_idesc(int M, int N, int b_mn_major) {  // kind::f16, fp16 x fp16 -> fp32
+  return (1u << 4) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ float xb_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// (a, b) -> fp16 pair hi and the fp16 pair of the remainders
+__device__ __forceinline__ void xb_split(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 hh = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(hh);
+  const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&hh);
+  lo = *reinterpret_cast<const uint32_t*>(&ll);
+}
+
+// ----------------------------------------------------------------------------------------------- operand preparation
+// max |dO| over the valid rows, as the bit pattern of a non-negative float (ordered like an unsigned integer)
+__global__ void __launch_bounds__(256) xb_absmax_kernel(const float* __restrict__ dctx, int S, int Lp,
+                                                        const int32_t* __restrict__ lens, unsigned* __restrict__ slot) {
+  const size_t n4 = (size_t)S * Lp * (LG_D / 4);
+  float m = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i / (LG_D / 4);
+    const int s = (int)(row / Lp), l = (int)(row % Lp);
+    if (lens && l >= lens[s]) continue;
+    const float4 v = reinterpret_cast<const float4*>(dctx)[i];
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    if (v.x != v.x || v.y != v.y || v.z != v.z || v.w != v.w) m = INFINITY;  // (fmaxf drops NaN)
+  }
+  for (int ofs = 16; ofs; ofs >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, ofs));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(slot, __float_as_uint(m));
+}
+// g = the power of two that brings the maximum into [256, 512); 1 for an all-zero or non-finite gradient
+__global__ void xb_scale_kernel(const unsigned* __restrict__ slot, float* __restrict__ g) {
+  const float m = __uint_as_float(*slot);
+  float r = 1.f;
+  if (m > 0.f && m < INFINITY) {
+    int e;
+    frexpf(m, &e);  // m = f 2^e, f in [0.5, 1)
+    e = 9 - e;
+    e = e < -100 ? -100 : (e > 100 ? 100 : e);
+    r = ldexpf(1.f, e);
+  }
+  *g = r;
+}
+// fp32 -> head-major fp16 plane pair [2][S,4,Lp,64]; rows >= lens are zero.  token_major = 0: src is [S,4,Lp,64];
+// 1: src is [S,Lp,256] (ctx layout).  scale from *gptr if given, else LG_X3_EA.
+__global__ void __launch_bounds__(256) xb_split_kernel(const float* __restrict__ src, int token_major, int S, int Lp,
+                                                       const int32_t* __restrict__ lens, const float* __restrict__ gptr,
+                                                       __half* __restrict__ out, size_t plane) {
+  const size_t n8 = (size_t)S * LG_HEADS * Lp * (LG_DH / 8);
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const int d8 = (int)(i % (LG_DH / 8));
+  const size_t row = i / (LG_DH / 8);  // (s, h, l)
+  const int l = (int)(row % Lp), h = (int)((row / Lp) % LG_HEADS), s = (int)(row / ((size_t)Lp * LG_HEADS));
+  uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
+  if (!lens || l < lens[s]) {
+    const float sc = gptr ? *gptr : LG_X3_EA;
+    const size_t off = token_major ? ((size_t)s * Lp + l) * LG_D + h * LG_DH + d8 * 8 : row * LG_DH + d8 * 8;
+    const float4 a = *reinterpret_cast<const float4*>(src + off), b = *reinterpret_cast<const float4*>(src + off + 4);
+    xb_split(a.x * sc, a.y * sc, hi.x, lo.x);
+    xb_split(a.z * sc, a.w * sc, hi.y, lo.y);
+    xb_split(b.x * sc, b.y * sc, hi.z, lo.z);
+    xb_split(b.z * sc, b.w * sc, hi.w, lo.w);
+  }
+  *reinterpret_cast<uint4*>(out + row * LG_DH + d8 * 8) = hi;
+  *reinterpret_cast<uint4*>(out + plane + row * LG_DH + d8 * 8) = lo;
+}
+
+// ----------------------------------------------------------------------------------------------- the backward kernel
+template <bool DKV>
+__global__ void __launch_bounds__(320, 1)
+x3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmU,
+                   const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmW, int Lp,
+                   const int32_t* __restrict__ lens, int kv_xor, const float* __restrict__ ctx,
+                   const float* __restrict__ dctx, const float* __restrict__ gptr, float* __restrict__ lse2,
+                   float* __restrict__ dlt, float* __restrict__ out1, float* __restrict__ out2) {
+  const int h = blockIdx.y, r0 = blockIdx.x * 128, s = blockIdx.z;
+  const int so = s ^ kv_xor;
+  const int n_own = lens ? lens[s] : Lp, n_oth = lens ? lens[so] : Lp;
+  if (r0 >= n_own || n_oth <= 0) return;  // (outputs are zero-filled by the caller; no keys: every probability is 0)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (n_oth + XB_OT - 1) / XB_OT;
+  const int first_main = DKV ? 0 : n_tiles;  // DQ: iterations [0, n_tiles) are the statistics sweep
+  const int n_iter = first_main + n_tiles;
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((tc::smem_u32(smem) & 1023u) != 0) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + XB_BAR);
+  uint64_t* own_full = bars;
+  uint64_t* y_full = bars + 1;
+  uint64_t* y_empty = y_full + XB_NST;
+  uint64_t* sc_full = y_empty + XB_NST;  // [2]
+  uint64_t* sc_free = sc_full + 2;       // [2]
+  uint64_t* pd_ready = sc_free + 2;
+  uint64_t* out_done = pd_ready + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + XB_NBAR);
+  float4* xch = reinterpret_cast<float4*>(smem + XB_XCH);
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmX);
+    tc::prefetch_tmap(&tmU);
+    tc::prefetch_tmap(&tmY);
+    tc::prefetch_tmap(&tmW);
+    tc::mbar_init(own_full, 1);
+    for (int i = 0; i < XB_NST; ++i) { tc::mbar_init(&y_full[i], 1); tc::mbar_init(&y_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&sc_full[i], 1); tc::mbar_init(&sc_free[i], 8); }
+    tc::mbar_init(pd_ready, 8);
+    tc::mbar_init(out_done, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      const int own_row = (s * LG_HEADS + h) * Lp + r0;
+      const int oth_row = (so * LG_HEADS + h) * Lp;
+      tc::mbar_arrive_expect_tx(own_full, 4 * XB_TBO);
+#pragma unroll
+      for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          tc::tma_load_3d(smem + XB_X + pl * XB_TBO + hf * XB_TBY, &tmX, own_full, 0, own_row + hf * 64, pl);
+          tc::tma_load_3d(smem + XB_U + pl * XB_TBO + hf * XB_TBY, &tmU, own_full, 0, own_row + hf * 64, pl);
+        }
+      for (int it = 0; it < n_iter; ++it) {
+        const int j = it < first_main ? it : it - first_main, st = it % XB_NST;
+        tc::mbar_wait(&y_empty[st], ((it / XB_NST) & 1) ^ 1);
+        uint8_t* dst = smem + XB_Y + st * 4 * XB_TBY;
+        tc::mbar_arrive_expect_tx(&y_full[st], 4 * XB_TBY);
+        tc::tma_load_3d(dst, &tmY, &y_full[st], 0, oth_row + j * XB_OT, 0);
+        tc::tma_load_3d(dst + XB_TBY, &tmY, &y_full[st], 0, oth_row + j * XB_OT, 1);
+        tc::tma_load_3d(dst + 2 * XB_TBY, &tmW, &y_full[st], 0, oth_row + j * XB_OT, 0);
+        tc::tma_load_3d(dst + 3 * XB_TBY, &tmW, &y_full[st], 0, oth_row + j * XB_OT, 1);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------------------------------- MMA issuer
+    constexpr uint32_t idesc_sc = xb_idesc(128, XB_OT, 0);
+    constexpr uint32_t idesc_out = xb_idesc(128, 64, 1);
+    const uint64_t dXh = tc::smem_desc_sw128(tc::smem_u32(smem + XB_X), 0, 1024);
+    const uint64_t dXl = tc::smem_desc_sw128(tc::smem_u32(smem + XB_X + XB_TBO), 0, 1024);
+    const uint64_t dUh = tc::smem_desc_sw128(tc::smem_u32(smem + XB_U), 0, 1024);
+    const uint64_t dUl = tc::smem_desc_sw128(tc::smem_u32(smem + XB_U + XB_TBO), 0, 1024);
+    auto issue_sc = [&](int it) {  // sc[it & 1] = X . Y^T and (main sweep) dp[it & 1] = U . W^T
+      const int st = it % XB_NST, b = it & 1;
+      const bool main = it >= first_main;
+      tc::mbar_wait(&y_full[st], (it / XB_NST) & 1);
+      tc::mbar_wait(&sc_free[b], ((it >> 1) & 1) ^ 1);  // the warps have read iteration it-2 out of this buffer
+      tc::fence_after_sync();
+      const uint32_t ybase = tc::smem_u32(smem + XB_Y + st * 4 * XB_TBY);
+      const uint64_t dYh = tc::smem_desc_sw128(ybase, 0, 1024), dYl = tc::smem_desc_sw128(ybase + XB_TBY, 0, 1024);
+      const uint64_t dWh = tc::smem_desc_sw128(ybase + 2 * XB_TBY, 0, 1024), dWl = tc::smem_desc_sw128(ybase + 3 * XB_TBY, 0, 1024);
+      const uint32_t tS = tmem + XT_SC + b * XB_OT, tP = tmem + XT_DP + b * XB_OT;
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          tc::umma_ss(tS, dXl + 2 * k, dYh + 2 * k, idesc_sc, k != 0);
+          tc::umma_ss(tS, dXh + 2 * k, dYl + 2 * k, idesc_sc, 1);
+          tc::umma_ss(tS, dXh + 2 * k, dYh + 2 * k, idesc_sc, 1);
+        }
+        if (main) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            tc::umma_ss(tP, dUl + 2 * k, dWh + 2 * k, idesc_sc, k != 0);
+            tc::umma_ss(tP, dUh + 2 * k, dWl + 2 * k, idesc_sc, 1);
+            tc::umma_ss(tP, dUh + 2 * k, dWh + 2 * k, idesc_sc, 1);
+          }
+        }
+        tc::umma_commit(&sc_full[b]);
+        if (!main) tc::umma_commit(&y_empty[st]);  // the statistics sweep is done with the stage
+      }
+      __syncwarp();
+    };
+    tc::mbar_wait(own_full, 0);
+    issue_sc(0);
+    for (int it = 0; it < n_iter; ++it) {
+      if (it + 1 < n_iter) issue_sc(it + 1);
+      if (it < first_main) continue;
+      const int jm = it - first_main, st = it % XB_NST;
+      tc::mbar_wait(pd_ready, jm & 1);
+      tc::fence_after_sync();
+      const uint32_t ybase = tc::smem_u32(smem + XB_Y + st * 4 * XB_TBY);
+      // MN-major B operands: row = other row (the K index of these MMAs), 16 rows = 2048 B per K step
+      const uint64_t mYh = tc::smem_desc_sw128(ybase, XB_TBY, 1024), mYl = tc::smem_desc_sw128(ybase + XB_TBY, XB_TBY, 1024);
+      const uint64_t mWh = tc::smem_desc_sw128(ybase + 2 * XB_TBY, XB_TBY, 1024), mWl = tc::smem_desc_sw128(ybase + 3 * XB_TBY, XB_TBY, 1024);
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t acc = (jm | k) != 0;
+          tc::umma_ts(tmem + XT_O1, tmem + XT_DL + k * 8, mYh + k * (2048 >> 4), idesc_out, acc);
+          tc::umma_ts(tmem + XT_O1, tmem + XT_DH + k * 8, mYl + k * (2048 >> 4), idesc_out, 1);
+          tc::umma_ts(tmem + XT_O1, tmem + XT_DH + k * 8, mYh + k * (2048 >> 4), idesc_out, 1);
+          if (DKV) {
+            tc::umma_ts(tmem + XT_O2, tmem + XT_PL + k * 8, mWh + k * (2048 >> 4), idesc_out, acc);
+            tc::umma_ts(tmem + XT_O2, tmem + XT_PH + k * 8, mWl + k * (2048 >> 4), idesc_out, 1);
+            tc::umma_ts(tmem + XT_O2, tmem + XT_PH + k * 8, mWh + k * (2048 >> 4), idesc_out, 1);
+          }
+        }
+        tc::umma_commit(&y_empty[st]);
+        tc::umma_commit(out_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------- softmax warps
+    const int quarter = warp & 3;
+    const int part = (warp - 2) >> 2;  // column half of every score tile
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const bool row_ok = r0 + r < n_own;
+    constexpr float s_us = 1.f / (LG_X3_EA * LG_X3_EA);
+    const float g = *gptr;
+    const size_t own_stat = ((size_t)s * LG_HEADS + h) * Lp + r0 + r;
+    const size_t oth_stat = ((size_t)so * LG_HEADS + h) * Lp;
+    float lse_own = 0.f, dlt_own = 0.f;  // DQ: this row's log-sum-exp and g * delta
+
+    if (!DKV) {
+      // ---- statistics sweep: every thread keeps the online (max, sum) of ITS 32 columns; partial states merge
+      // associatively, so the two threads of a row are combined once, after the sweep
+      float m = -INFINITY, l = 0.f;
+      for (int it = 0; it < n_tiles; ++it) {
+        const int b = it & 1;
+        tc::mbar_wait(&sc_full[b], (it >> 1) & 1);
+        tc::fence_after_sync();
+        uint32_t sv[32];
+        tc::tmem_ld32(tmem + lane_base + XT_SC + b * XB_OT + part * 32, sv);
+        tc::tmem_ld_wait();
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&sc_free[b]);
+        const int valid = n_oth - it * XB_OT - part * 32;
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i >= valid) sv[i] = 0xff800000u;  // -inf
+          mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv[i]));
+        }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * s_us;
+        const float mnew = fmaxf(m, mx);
+        const float msafe = mnew == -INFINITY ? 0.f : mnew;
+        float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 32; ++i) rs4[i & 3] += xb_ex2(fmaf(__uint_as_float(sv[i]), s_us, -msafe));
+        l = l * xb_ex2(m - msafe) + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
+        m = mnew;
+      }
+      float dot = 0.f;
+      if (row_ok) {
+        const size_t off = ((size_t)s * Lp + r0 + r) * LG_D + h * LG_DH + part * 32;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 o = *reinterpret_cast<const float4*>(ctx + off + 4 * i);
+          const float4 gr = *reinterpret_cast<const float4*>(dctx + off + 4 * i);
+          dot += (o.x * gr.x + o.y * gr.y) + (o.z * gr.z + o.w * gr.w);
+        }
+      }
+      xch[r * 2 + part] = make_float4(m, l, dot, 0.f);
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+      const float4 a = xch[r * 2], bq = xch[r * 2 + 1];
+      const float mnew = fmaxf(a.x, bq.x);
+      const float msafe = mnew == -INFINITY ? 0.f : mnew;
+      const float lsum = a.y * xb_ex2(a.x - msafe) + bq.y * xb_ex2(bq.x - msafe);
+      lse_own = lsum > 0.f ? mnew + log2f(lsum) : INFINITY;
+      const float delta = a.z + bq.z;
+      dlt_own = delta * g;
+      if (part == 0 && row_ok) {
+        lse2[own_stat] = lse_own;
+        dlt[own_stat] = delta;
+      }
+    }
+
+    // ---- main sweep
+    for (int it = first_main; it < n_iter; ++it) {
+      const int jm = it - first_main, b = it & 1;
+      const int n0 = jm * XB_OT + part * 32;  // first other row of this thread's columns
+      tc::mbar_wait(&sc_full[b], (it >> 1) & 1);
+      tc::fence_after_sync();
+      uint32_t sv[32], dv[32];
+      tc::tmem_ld32(tmem + lane_base + XT_SC + b * XB_OT + part * 32, sv);
+      tc::tmem_ld32(tmem + lane_base + XT_DP + b * XB_OT + part * 32, dv);
+      tc::tmem_ld_wait();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&sc_free[b]);
+      uint32_t dh[16], dl[16], ph[16], pl[16];
+#pragma unroll
+      for (int i4 = 0; i4 < 8; ++i4) {
+        float lq[4], dq[4];
+        if (DKV) {  // per-column statistics of the queries (uniform over the warp: broadcast loads)
+          const float4 l4 = *reinterpret_cast<const float4*>(lse2 + oth_stat + n0 + 4 * i4);
+          const float4 d4 = *reinterpret_cast<const float4*>(dlt + oth_stat + n0 + 4 * i4);
+          lq[0] = l4.x; lq[1] = l4.y; lq[2] = l4.z; lq[3] = l4.w;
+          dq[0] = d4.x * g; dq[1] = d4.y * g; dq[2] = d4.z * g; dq[3] = d4.w * g;
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { lq[c] = lse_own; dq[c] = dlt_own; }
+        }
+        float p[4], d[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int i = 4 * i4 + c;
+          const bool ok = n0 + i < n_oth;
+          p[c] = ok ? xb_ex2(fmaf(__uint_as_float(sv[i]), s_us, -lq[c])) : 0.f;
+          // dp arrives as g * 64 * dP; D plane value = (g / 64) * P * (dP - delta), kept inside fp16
+          const float t = ok ? fmaf(__uint_as_float(dv[i]), 1.f / LG_X3_EA, -dq[c]) : 0.f;
+          d[c] = fminf(fmaxf(p[c] * t * XB_DC, -60000.f), 60000.f);
+        }
+        xb_split(d[0], d[1], dh[2 * i4], dl[2 * i4]);
+        xb_split(d[2], d[3], dh[2 * i4 + 1], dl[2 * i4 + 1]);
+        if (DKV) {
+          xb_split(p[0] * LG_X3_EP, p[1] * LG_X3_EP, ph[2 * i4], pl[2 * i4]);
+          xb_split(p[2] * LG_X3_EP, p[3] * LG_X3_EP, ph[2 * i4 + 1], pl[2 * i4 + 1]);
+        }
+      }
+      if (jm > 0) {
+        tc::mbar_wait(out_done, (jm - 1) & 1);  // the MMAs that read the previous planes have retired
+        tc::fence_after_sync();
+      }
+      tc::tmem_st16(tmem + lane_base + XT_DH + part * 16, dh);
+      tc::tmem_st16(tmem + lane_base + XT_DL + part * 16, dl);
+      if (DKV) {
+        tc::tmem_st16(tmem + lane_base + XT_PH + part * 16, ph);
+        tc::tmem_st16(tmem + lane_base + XT_PL + part * 16, pl);
+      }
+      tc::tmem_st_wait();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(pd_ready);
+    }
+    // ---- epilogue: this thread's 32 output columns of its row
+    tc::mbar_wait(out_done, (n_tiles - 1) & 1);
+    tc::fence_after_sync();
+    {
+      uint32_t o[32];
+      tc::tmem_ld32(tmem + lane_base + XT_O1 + part * 32, o);
+      tc::tmem_ld_wait();
+      // raw = ((g / 64) D) . (64 Y)
+      const float k1 = XB_LN2 / (g * XB_DC * LG_X3_EA);
+      if (row_ok) {
+        float4* dst = reinterpret_cast<float4*>(out1 + own_stat * LG_DH + part * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          dst[i] = make_float4(__uint_as_float(o[4 * i]) * k1, __uint_as_float(o[4 * i + 1]) * k1,
+                               __uint_as_float(o[4 * i + 2]) * k1, __uint_as_float(o[4 * i + 3]) * k1);
+      }
+      if (DKV) {
+        tc::tmem_ld32(tmem + lane_base + XT_O2 + part * 32, o);
+        tc::tmem_ld_wait();
+        const float k2 = 1.f / (g * LG_X3_EP);  // raw = (256 P) . (g dO)
+        if (row_ok) {
+          float4* dst = reinterpret_cast<float4*>(out2 + own_stat * LG_DH + part * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            dst[i] = make_float4(__uint_as_float(o[4 * i]) * k2, __uint_as_float(o[4 * i + 1]) * k2,
+                                 __uint_as_float(o[4 * i + 2]) * k2, __uint_as_float(o[4 * i + 3]) * k2);
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace
+
+size_t lg_x3_attention_bwd_ws_floats(int S, int Lp) {
+  return 2 * (size_t)S * LG_HEADS * Lp + 16 + 4 * (size_t)S * Lp * LG_D;
+}
+
+// Q, K, V fp32 [S,4,Lp,64]; ctx, dctx fp32 [S,Lp,256]; dQ, dK, dV fp32 [S,4,Lp,64] (zero-filled by the caller);
+// ws: lg_x3_attention_bwd_ws_floats(S, Lp) floats.
+int lg_x3_attention_bwd(const float* Q, const float* K, const float* V, const float* ctx, const float* dctx, int S,
+                        int Lp, const int32_t* lens, int kv_xor, float* dQ, float* dK, float* dV, float* ws,
+                        cudaStream_t st) {
+  const size_t n_stat = (size_t)S * LG_HEADS * Lp, n_el = (size_t)S * Lp * LG_D;
+  float* lse2 = ws;
+  float* dlt = ws + n_stat;
+  unsigned* slot = reinterpret_cast<unsigned*>(ws + 2 * n_stat);
+  float* g = ws + 2 * n_stat + 1;
+  __half* planes = reinterpret_cast<__half*>(ws + 2 * n_stat + 16);
+  __half* Qp = planes;
+  __half* Kp = K == Q ? Qp : planes + 2 * n_el;
+  __half* Vp = planes + 4 * n_el;
+  __half* Gp = planes + 6 * n_el;
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(slot, 0, sizeof(unsigned), st)) != cudaSuccess) return (int)e;
+  xb_absmax_kernel<<<592, 256, 0, st>>>(dctx, S, Lp, lens, slot);
+  LG_LAUNCH_CHECK();
+  xb_scale_kernel<<<1, 1, 0, st>>>(slot, g);
+  LG_LAUNCH_CHECK();
+  const unsigned nb = (unsigned)((n_el / 8 + 255) / 256);
+  xb_split_kernel<<<nb, 256, 0, st>>>(Q, 0, S, Lp, lens, nullptr, Qp, n_el);
+  LG_LAUNCH_CHECK();
+  if (Kp != Qp) {
+    xb_split_kernel<<<nb, 256, 0, st>>>(K, 0, S, Lp, lens, nullptr, Kp, n_el);
+    LG_LAUNCH_CHECK();
+  }
+  xb_split_kernel<<<nb, 256, 0, st>>>(V, 0, S, Lp, lens, nullptr, Vp, n_el);
+  LG_LAUNCH_CHECK();
+  xb_split_kernel<<<nb, 256, 0, st>>>(dctx, 1, S, Lp, lens, g, Gp, n_el);
+  LG_LAUNCH_CHECK();
+
+  CUtensorMap tq, tk, tv, tg;
+  const uint64_t rows = (uint64_t)S * LG_HEADS * Lp;
+  const uint64_t d[3] = {64, rows, 2}, sb[2] = {128, rows * 128};
+  const uint32_t box[3] = {64, 64, 1};
+  int rc;
+  if ((rc = lg_make_tmap_bf16(&tq, Qp, 3, d, sb, box))) return rc;
+  if ((rc = lg_make_tmap_bf16(&tk, Kp, 3, d, sb, box))) return rc;
+  if ((rc = lg_make_tmap_bf16(&tv, Vp, 3, d, sb, box))) return rc;
+  if ((rc = lg_make_tmap_bf16(&tg, Gp, 3, d, sb, box))) return rc;
+  if ((e = cudaFuncSetAttribute(x3_attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, XB_SMEM)) != cudaSuccess) return (int)e;
+  if ((e = cudaFuncSetAttribute(x3_attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, XB_SMEM)) != cudaSuccess) return (int)e;
+  const dim3 grid(Lp / 128, LG_HEADS, S);
+  x3_attn_bwd_kernel<false><<<grid, 320, XB_SMEM, st>>>(tq, tg, tk, tv, Lp, lens, kv_xor, ctx, dctx, g, lse2, dlt, dQ, nullptr);
+  LG_LAUNCH_CHECK();
+  x3_attn_bwd_kernel<true><<<grid, 320, XB_SMEM, st>>>(tk, tv, tq, tg, Lp, lens, kv_xor, ctx, dctx, g, lse2, dlt, dK, dV);
+  LG_LAUNCH_CHECK();
+  return LGB200_OK;
+}

@@ -24,6 +24,7 @@ raise as everywhere else in this package.
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 import os
 from typing import Dict, List, Tuple
@@ -121,7 +122,9 @@ class _Kern:
 
     def attention_bwd(self, q, k, v, ctx, dctx, kv_xor):
         dq, dk, dv = self.empty(self.T * 256), self.empty(self.T * 256), self.empty(self.T * 256)
-        ws = self.empty(2 * self.S * 4 * self.Lp)
+        n_ws = C.c_longlong(0)
+        check(self.lib.lgb200_attention_bwd_workspace(self.S, self.Lp, C.byref(n_ws)), "lgb200_attention_bwd_workspace")
+        ws = self.empty(n_ws.value)
         check(self.lib.lgb200_attention_bwd(ptr(q), ptr(k), ptr(v), ptr(ctx), ptr(dctx), self.S, self.Lp, ptr(self.lens),
                                             kv_xor, ptr(dq), ptr(dk), ptr(dv), ptr(ws), self.st), "lgb200_attention_bwd")
         return dq, dk, dv

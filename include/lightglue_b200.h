@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define LGB200_ABI_VERSION 5
+#define LGB200_ABI_VERSION 6
 
 enum { LGB200_F32 = 0, LGB200_BF16 = 1, LGB200_F32X3 = 2 };
 
@@ -287,7 +287,9 @@ int lgb200_x3_assign_scores(const float* sim, const float* z, const float* lse, 
  *   nothing N x M is stored).  Q, K, V [S,4,Lp,64] as given to the forward (Q pre-scaled, log2 domain), ctx / dctx
  *   [S,Lp,256] = forward output and its gradient.  dQ, dK, dV [S,4,Lp,64]: gradients w.r.t. the given (scaled) Q,
  *   K and V; with kv_xor = 1, dK / dV of sequence s collect the queries of sequence s ^ 1.  Rows >= lens are zero.
- *   workspace: 2 * S * 4 * Lp floats (row log-sum-exp and <dO, O>).
+ *   Runs on tcgen05 in the fp32-accurate split-fp16 mode (csrc/lg_x3_attn_bwd.cu).  workspace:
+ *   lgb200_attention_bwd_workspace(S, Lp) floats (row log-sum-exp, <dO, O>, and the fp16 plane pairs of Q, K, V, dO).
+ * lgb200_attention_bwd_workspace: *n_floats = the workspace size of lgb200_attention_bwd for (S, Lp).
  * lgb200_heads_bwd: backward of the HEADS epilogue of lgb200_linear (unflatten + rotary + scale, lightglue.py:43-50,
  *   157-161, 196-201).  n_parts = 3: out [T,768] = [scale0 R^T dQ | scale1 R^T dK | scale2 dV] in the packed column
  *   order part*256 + head*64 + d, R^T = inverse rotation by the angles in rot [T,64]; dtheta [T,32] (nullable) +=
@@ -304,6 +306,7 @@ int lgb200_x3_assign_scores(const float* sim, const float* z, const float* lse, 
 int lgb200_attention_bwd(const float* Q, const float* K, const float* V, const float* ctx, const float* dctx,
                          int S, int Lp, const int32_t* lens, int kv_xor, float* dQ, float* dK, float* dV,
                          float* workspace, void* stream);
+int lgb200_attention_bwd_workspace(int S, int Lp, long long* n_floats);
 int lgb200_heads_bwd(const float* dQ, const float* dK, const float* dV, const float* Q, const float* K,
                      const float* rot, int S, int Lp, const int32_t* lens, int n_parts, float scale0,
                      float scale1, float scale2, float* out, float* dtheta, void* stream);

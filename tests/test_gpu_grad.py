@@ -2,6 +2,7 @@
 torch autograd of the same op in float64, and a whole training step -- forward in training mode, LightGlue.loss,
 `losses["total"].mean().backward()` -- against (a) torch autograd through the CPU oracle, every entry of every
 gradient, and (b) gradient goldens of the unmodified reference (oracle/make_golden_grad.py)."""
+import ctypes
 import math
 
 import pytest
@@ -53,7 +54,9 @@ def test_attention_bwd_against_autograd(kv_xor, lens):
     ctx = torch.zeros(S, Lp, 256, device=DEV)
     assert lib.lgb200_attention(_abi.F32, ptr(q), ptr(k), ptr(v), S, Lp, ptr(lens_d), kv_xor, ptr(ctx), _st()) == 0
     dq, dk, dv = (torch.full((S, 4, Lp, 64), 7.0, device=DEV) for _ in range(3))
-    ws = torch.empty(2 * S * 4 * Lp, device=DEV)
+    n_ws = ctypes.c_longlong(0)
+    assert lib.lgb200_attention_bwd_workspace(S, Lp, ctypes.byref(n_ws)) == 0
+    ws = torch.empty(n_ws.value, device=DEV)
     rc = lib.lgb200_attention_bwd(ptr(q), ptr(k), ptr(v), ptr(ctx), ptr(dctx), S, Lp, ptr(lens_d), kv_xor, ptr(dq), ptr(dk),
                                   ptr(dv), ptr(ws), _st())
     assert rc == 0, lib.lgb200_error_string(rc)

@@ -1,6 +1,7 @@
 """Attention backward kernels alone (csrc/lg_bwd.cu through lgb200_attention_bwd): S sequences x 4 heads x Lp keypoints,
 fp32.  Prints ms per call and the useful fp32-equivalent TFLOP/s (8 tile products of 2.Lp^2.64 per head: 1 statistics +
 3 dQ + 4 dK/dV).  Usage: python tools/attn_bwd_bench.py [S] [Lp] [reps]   (LGB200_ATTN_BWD_SIMT=1: CUDA-core kernels)"""
+import ctypes
 import sys
 from pathlib import Path
 
@@ -23,7 +24,9 @@ ctx = torch.zeros(S, Lp, 256, device=dev)
 st = torch.cuda.current_stream(dev).cuda_stream
 assert lib.lgb200_attention(_abi.F32, ptr(q), ptr(k), ptr(v), S, Lp, None, 0, ptr(ctx), st) == 0
 dq, dk, dv = (torch.empty(S, 4, Lp, 64, device=dev) for _ in range(3))
-ws = torch.empty(2 * S * 4 * Lp, device=dev)
+n_ws = ctypes.c_longlong(0)
+assert lib.lgb200_attention_bwd_workspace(S, Lp, ctypes.byref(n_ws)) == 0
+ws = torch.empty(n_ws.value, device=dev)
 
 
 def call():
