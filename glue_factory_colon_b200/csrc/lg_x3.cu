@@ -499,6 +499,40 @@ __global__ void x3_split_kernel(const float* __restrict__ x, size_t n4, __half* 
   reinterpret_cast<uint2*>(xs + plane)[i] = make_uint2(l0, l1);
 }
 
+// Gradients have no fixed range: lgb200_split_dynamic scales by the power of two g that brings max |x| into [256, 512)
+// before splitting (a fixed scaling would leave small gradients in the fp16 subnormals).
+__global__ void __launch_bounds__(256) x3_absmax_kernel(const float* __restrict__ x, size_t n4, unsigned* __restrict__ slot) {
+  float m = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    if (v.x != v.x || v.y != v.y || v.z != v.z || v.w != v.w) m = INFINITY;  // (fmaxf drops NaN)
+  }
+  for (int ofs = 16; ofs; ofs >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, ofs));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(slot, __float_as_uint(m));
+}
+__device__ __forceinline__ float x3_dynamic_scale(unsigned bits) {  // 1 for an all-zero or non-finite tensor
+  const float m = __uint_as_float(bits);
+  if (!(m > 0.f && m < INFINITY)) return 1.f;
+  int e;
+  frexpf(m, &e);  // m = f 2^e, f in [0.5, 1)
+  e = 9 - e;
+  return ldexpf(1.f, e < -100 ? -100 : (e > 100 ? 100 : e));
+}
+__global__ void x3_split_dynamic_kernel(const float* __restrict__ x, size_t n4, const unsigned* __restrict__ slot,
+                                        __half* __restrict__ xs, size_t plane, float* __restrict__ inv_scale) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float g = x3_dynamic_scale(*slot);
+  if (i == 0) *inv_scale = 1.f / g;
+  const float4 v = reinterpret_cast<const float4*>(x)[i];
+  const __half2 h0 = __floats2half2_rn(v.x * g, v.y * g), h1 = __floats2half2_rn(v.z * g, v.w * g);
+  const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+  const __half2 l0 = __floats2half2_rn(v.x * g - f0.x, v.y * g - f0.y), l1 = __floats2half2_rn(v.z * g - f1.x, v.w * g - f1.y);
+  reinterpret_cast<uint2*>(xs)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+  reinterpret_cast<uint2*>(xs + plane)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+}
+
 // MatchAssignment normalisers from the similarity sim [B][Lp][Lp] (lightglue.py:262-263):
 // lse[2b, i] = logsumexp_j sim[b,i,j] (one warp per row) and lse[2b+1, j] = logsumexp_i sim[b,i,j] (one thread per
 // column, 8 warps striding the rows, combined through shared memory).
@@ -620,6 +654,22 @@ extern "C" int lgb200_split_rows(const float* x, long long n, void* xs, void* st
   if (n <= 0 || n % 4) return LGB200_ERR_SHAPE;
   const size_t n4 = (size_t)n / 4;
   x3_split_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, lg_stream(stream)>>>(x, n4, (__half*)xs, (size_t)n);
+  LG_LAUNCH_CHECK();
+  return LGB200_OK;
+}
+
+extern "C" int lgb200_split_dynamic(const float* x, long long n, void* xs, float* inv_scale, void* stream) {
+  if (!x || !xs || !inv_scale) return LGB200_ERR_NULL;
+  if (n <= 0 || n % 4) return LGB200_ERR_SHAPE;
+  const size_t n4 = (size_t)n / 4;
+  cudaStream_t st = lg_stream(stream);
+  unsigned* slot = reinterpret_cast<unsigned*>(inv_scale) + 1;  // inv_scale[1] holds the bit pattern of max |x|
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(slot, 0, sizeof(unsigned), st)) != cudaSuccess) return (int)e;
+  const unsigned nb = (unsigned)((n4 + 255) / 256);
+  x3_absmax_kernel<<<nb < 1184u ? nb : 1184u, 256, 0, st>>>(x, n4, slot);
+  LG_LAUNCH_CHECK();
+  x3_split_dynamic_kernel<<<nb, 256, 0, st>>>(x, n4, slot, (__half*)xs, (size_t)n, inv_scale);
   LG_LAUNCH_CHECK();
   return LGB200_OK;
 }

@@ -17,9 +17,10 @@ layer's descriptors in training mode, :588-637 turns them into the deep-supervis
     (losses.py:6-26: the sum of log_assignment over the ground-truth matches and the two dustbin vectors).  Forward =
     the library's assignment + reduction kernels; backward = lgb200_assign_dsim (d similarity of the double softmax).
 
-Plain GEMMs of the backward pass (dX = dY.W, dW = dY^T.X) go to cuBLAS through torch.matmul -- they are library
-GEMMs with nothing to fuse, and gradients span a range (1e-8 ... 1e-2) that the split-fp16 operand format does not
-cover.  Everything is fp32-accurate whatever conf.precision says (the bf16 kernels are inference kernels); CPU tensors
+Plain GEMMs of the backward pass (dX = dY.W, dW = dY^T.X) go to cuBLAS -- they are library GEMMs with nothing to fuse --
+as three fp16 tensor-core GEMMs on split planes with fp32 accumulation (_Kern.mm3; LGB200_TRAIN_SGEMM=1: one fp32
+sgemm on the CUDA cores).  Gradients span a range (1e-8 ... 1e-2) that a fixed plane scaling does not cover, so
+lgb200_split_dynamic scales every gradient tensor by its own power of two first.  Everything is fp32-accurate whatever conf.precision says (the bf16 kernels are inference kernels); CPU tensors
 raise as everywhere else in this package.
 """
 from __future__ import annotations
@@ -38,9 +39,13 @@ from ._abi import EPI_HEADS, EPI_LN_GELU, EPI_ROWMAJOR, F32, F32X3, check, ptr
 LOG2E = 1.4426950408889634
 Q_SCALE = LOG2E / math.sqrt(64.0)   # folded into q: the attention kernels work in the log2 domain
 C_SCALE = math.sqrt(Q_SCALE)        # cross block: to_qk feeds both sides (lightglue.py:208)
+AI, WI = 1.0 / 64.0, 1.0 / 256.0       # inverse plane scalings of activations / weights (LG_X3_EA, LG_X3_EW)
 N_PARTIALS = 296                    # CTAs of lgb200_ln_gelu_bwd (2 per SM)
 _SIMT_ATTN = os.environ.get("LGB200_TRAIN_SIMT_ATTN", "0") == "1"
 _SIMT_LINEAR = os.environ.get("LGB200_TRAIN_SIMT_LINEAR", "0") == "1"
+# plain GEMMs of the backward pass: 1 = cuBLAS fp32 (sgemm on the CUDA cores), default = three fp16 tensor-core GEMMs on
+# split planes with fp32 accumulation (the same hi.hi + hi.lo + lo.hi scheme as the forward's lg_x3.cu kernels)
+_SGEMM = os.environ.get("LGB200_TRAIN_SGEMM", "0") == "1" or _SIMT_LINEAR
 _X3_WEIGHTS = ("qkv_w", "so_w", "sf0_w", "sf3_w", "cqv_w", "co_w", "cf0_w", "cf3_w")
 # packed Wqkv row r holds reference row _PERM[r] (lightglue.py:158: head*192 + d*3 + part -> part*256 + head*64 + d)
 _PERM = torch.arange(768).view(4, 64, 3).permute(2, 0, 1).reshape(-1)
@@ -98,6 +103,30 @@ class _Kern:
         out = torch.empty(2, t.numel(), device=self.dev, dtype=torch.float16)
         check(self.lib.lgb200_split_rows(ptr(t), t.numel(), ptr(out), self.st), "lgb200_split_rows")
         return out
+
+    def asplit(self, t):
+        """activation [M, N] fp32 -> planes [2, M, N] (scale 64)"""
+        return self.split(t).view(2, *t.shape)
+
+    def gsplit(self, t):
+        """gradient [M, N] fp32 -> (planes [2, M, N] of g t, 1 / g on the device): lgb200_split_dynamic picks the power of
+        two g per tensor (gradients have no fixed range)."""
+        t = t.contiguous()
+        out = torch.empty(2, *t.shape, device=self.dev, dtype=torch.float16)
+        inv = torch.empty(2, device=self.dev, dtype=torch.float32)
+        check(self.lib.lgb200_split_dynamic(ptr(t), t.numel(), ptr(out), ptr(inv), self.st), "lgb200_split_dynamic")
+        return out, inv[0]
+
+    @staticmethod
+    def mm3(A, B, scale):
+        """fp32-accurate A.B from plane pairs A [2, M, K], B [2, K, N] (views may be transposed): lo.hi + hi.lo + hi.hi as
+        three fp16 tensor-core GEMMs with fp32 accumulation and fp32 output (cuBLAS: plain library GEMMs), times `scale`
+        (the product of the inverse plane scalings; float or 0-dim device tensor)."""
+        f32 = torch.float32
+        r = torch.mm(A[1], B[0], out_dtype=f32)
+        r += torch.mm(A[0], B[1], out_dtype=f32)
+        r += torch.mm(A[0], B[0], out_dtype=f32)
+        return r.mul_(scale)
 
     def attention(self, q, k, v, kv_xor, ctx):
         """Forward attention on the tensor cores in the fp32-accurate mode (lg_x3_attn.cu: split-fp16 operands, three
@@ -280,15 +309,35 @@ def _ffn_bwd(k: _Kern, w: Dict, pre: str, x, msg, dy):
     else:
         k.linear3(EPI_ROWMAJOR, k.split(x), w["x3"][pre + "f0_w"], w[pre + "f0_b"], 512, 512, A1=k.split(msg), K0=256,
                   out32=h)
-    da = dy @ w[pre + "f3_w"]
-    dh, act, gsum = k.ln_gelu_bwd(h, w[pre + "ln_g"], w[pre + "ln_b"], da)
+    if _SGEMM:
+        da = dy @ w[pre + "f3_w"]
+        dh, act, gsum = k.ln_gelu_bwd(h, w[pre + "ln_g"], w[pre + "ln_b"], da)
+        g3, g0 = dy.t() @ act, torch.cat([dh.t() @ x, dh.t() @ msg], 1)
+        dcat = dh @ w[pre + "f0_w"]
+    else:
+        wx = w["x3"]
+        dyp, dyi = k.gsplit(dy)
+        da = k.mm3(dyp, wx[pre + "f3_w"], dyi * WI)
+        dh, act, gsum = k.ln_gelu_bwd(h, w[pre + "ln_g"], w[pre + "ln_b"], da)
+        g3 = k.mm3(dyp.transpose(1, 2), k.asplit(act), dyi * AI)
+        dhp, dhi = k.gsplit(dh)
+        dht = dhp.transpose(1, 2)
+        g0 = torch.cat([k.mm3(dht, k.asplit(x), dhi * AI), k.mm3(dht, k.asplit(msg), dhi * AI)], 1)
+        dcat = k.mm3(dhp, wx[pre + "f0_w"], dhi * WI)
     g = {
-        pre + "f3_w": dy.t() @ act, pre + "f3_b": dy.sum(0),
+        pre + "f3_w": g3, pre + "f3_b": dy.sum(0),
         pre + "ln_g": gsum[:512], pre + "ln_b": gsum[512:],
-        pre + "f0_w": torch.cat([dh.t() @ x, dh.t() @ msg], 1), pre + "f0_b": dh.sum(0),
+        pre + "f0_w": g0, pre + "f0_b": dh.sum(0),
     }
-    dcat = dh @ w[pre + "f0_w"]
     return dcat[:, :256], dcat[:, 256:].contiguous(), g
+
+
+def _proj_bwd(k: _Kern, w: Dict, name: str, dy, x):
+    """Backward of y = x W^T (+ b) for the weight `name` ([N, K], planes in w["x3"]): (dy^T x, dy W)."""
+    if _SGEMM:
+        return dy.t() @ x, dy @ w[name]
+    dyp, dyi = k.gsplit(dy)
+    return k.mm3(dyp.transpose(1, 2), k.asplit(x), dyi * AI), k.mm3(dyp, w["x3"][name], dyi * WI)
 
 
 class TransformerFn(torch.autograd.Function):
@@ -357,30 +406,32 @@ class TransformerFn(torch.autograd.Function):
             dxa, dmsg, g = _ffn_bwd(k, w, "c", x_mid, msg, dx)
             for name, val in g.items():
                 grads[(i, name)] = val
-            grads[(i, "co_w")], grads[(i, "co_b")] = dmsg.t() @ c, dmsg.sum(0)
-            dq, dk, dv = k.attention_bwd(qk, qk, v, c, dmsg @ w["co_w"], 1)
+            grads[(i, "co_w")], dc = _proj_bwd(k, w, "co_w", dmsg, c)
+            grads[(i, "co_b")] = dmsg.sum(0)
+            dq, dk, dv = k.attention_bwd(qk, qk, v, c, dc, 1)
             dqv = k.heads_bwd(dq, dk, dv, None, None, None, 2, (C_SCALE, 1.0, 1.0), None)
-            gw = dqv.t() @ x_mid
+            gw, dxp = _proj_bwd(k, w, "cqv_w", dqv, x_mid)
             grads[(i, "cqk_w")], grads[(i, "cv_w")] = gw[:256], gw[256:]
             gb = dqv.sum(0)
             grads[(i, "cqk_b")], grads[(i, "cv_b")] = gb[:256], gb[256:]
-            dxm = dx + dxa + dqv @ w["cqv_w"]
+            dxm = dx + dxa + dxp
             # ---- self block (lightglue.py:151-164) ----
             q, kk, v, c, msg = ctx.kept[i][0] if ctx.kept[i] is not None else _self_attend(k, w, x_in, rot)
             ctx.kept[i] = None
             dxa, dmsg, g = _ffn_bwd(k, w, "s", x_in, msg, dxm)
             for name, val in g.items():
                 grads[(i, name)] = val
-            grads[(i, "so_w")], grads[(i, "so_b")] = dmsg.t() @ c, dmsg.sum(0)
-            dq, dk, dv = k.attention_bwd(q, kk, v, c, dmsg @ w["so_w"], 0)
+            grads[(i, "so_w")], dc = _proj_bwd(k, w, "so_w", dmsg, c)
+            grads[(i, "so_b")] = dmsg.sum(0)
+            dq, dk, dv = k.attention_bwd(q, kk, v, c, dc, 0)
             dqkv = k.heads_bwd(dq, dk, dv, q, kk, rot, 3, (Q_SCALE, 1.0, 1.0), dtheta)
             perm = _PERM.to(dqkv.device)
             gw = torch.empty(768, 256, device=dqkv.device, dtype=torch.float32)
-            gw[perm] = dqkv.t() @ x_in
+            gw[perm], dxp = _proj_bwd(k, w, "qkv_w", dqkv, x_in)
             gb = torch.empty(768, device=dqkv.device, dtype=torch.float32)
             gb[perm] = dqkv.sum(0)
             grads[(i, "qkv_w")], grads[(i, "qkv_b")] = gw, gb
-            dx = dxm + dxa + dqkv @ w["qkv_w"]
+            dx = dxm + dxa + dxp
         # positional encoding: theta = Wr . normalised keypoints (lightglue.py:61-66)
         kdim = geom["k0"].shape[-1]
         kn = k.zeros(k.T, kdim)

@@ -265,6 +265,10 @@ int lgb200_prune_compact(const float* match, const float* conf, float thr, float
  * lgb200_split_rows: x [n] fp32 -> xs [2][n] fp16 planes (hi = fp16(x), lo = fp16(x - hi)); n % 4 == 0.
  * Used for the staged descriptors (lightglue.py:456-465) and after point pruning (:506-521). */
 int lgb200_split_rows(const float* x, long long n, void* xs, void* stream);
+/* lgb200_split_dynamic: the same for tensors without a fixed range (gradients): xs [2][n] = planes of g x with g the
+ * power of two that brings max |x| into [256, 512) (1 for an all-zero tensor); inv_scale[0] = 1 / g on the device,
+ * inv_scale[1] is scratch (two floats).  Feeds the three-product tensor-core GEMMs of the backward pass (train.py). */
+int lgb200_split_dynamic(const float* x, long long n, void* xs, float* inv_scale, void* stream);
 /* Similarity of MatchAssignment (the einsum of lightglue.py:284) for all pairs: mds = split planes of
  * final_proj(desc)/4 [2][S*Lp][256]; sim [B][Lp][Lp] fp32 receives <md[2b,i], md[2b+1,j]> for i < lens[2b],
  * j < lens[2b+1] (tiles past the valid counts are not touched). Lp % 256 == 0. */
