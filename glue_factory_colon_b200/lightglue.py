@@ -279,7 +279,7 @@ class LightGlue(nn.Module):
             check(lib.lgb200_assign_lse(prec, ptr(md), S, Lp, ptr(lens), ptr(lse), st), "assign_lse")
         R, C = m + 1, n + 1
         if keep is not None:  # what the backward pass (train.AssignFn) and the training forward need
-            keep.update(z=z, lse=lse, Lp=Lp, lens=lens)
+            keep.update(z=z, lse=lse, Lp=Lp, lens=lens, md_planes=md if x3 else None)
         if bf:
             rows = torch.empty(3, B, m, **f32)
             row_arg = torch.empty(B, m, device=dev, dtype=torch.int32)

@@ -462,6 +462,9 @@ class AssignFn(torch.autograd.Function):
             lib, F32 if _SIMT_LINEAR else F32X3, d0, d1, layer, gt, keep=keep)
         ctx.save_for_backward(d0, d1, fp_w, fp_b, m_w, gt, keep["z"], keep["lse"])
         ctx.Lp = keep["Lp"]
+        # x3 mode: the split planes of final_proj(desc) / 4 (33 MB at 8 x 2048) -- the backward recomputes the similarity
+        # from them on tcgen05 instead of redoing final_proj and the N x M product in fp32 on the CUDA cores
+        ctx.md_planes, ctx.lens = (None, None) if _SGEMM else (keep["md_planes"], keep["lens"])
         ctx.mark_non_differentiable(pos_cnt, row_exp, row_arg, col_arg)
         return pos_sum, dust0.contiguous(), dust1.contiguous(), pos_cnt, row_exp, row_arg, col_arg
 
@@ -474,16 +477,39 @@ class AssignFn(torch.autograd.Function):
         Lp = ctx.Lp
         dev = d0.device
         x0, x1 = d0.to(torch.float32), d1.to(torch.float32)
-        md0 = torch.addmm(fp_b, x0.reshape(-1, 256), fp_w.t()).view(B, m, 256) * 0.25  # lightglue.py:281-283
-        md1 = torch.addmm(fp_b, x1.reshape(-1, 256), fp_w.t()).view(B, n, 256) * 0.25
-        sim = torch.bmm(md0, md1.transpose(1, 2)).contiguous()
+        st = torch.cuda.current_stream(dev).cuda_stream
+        mdp = ctx.md_planes
+        if mdp is None:
+            md0 = torch.addmm(fp_b, x0.reshape(-1, 256), fp_w.t()).view(B, m, 256) * 0.25  # lightglue.py:281-283
+            md1 = torch.addmm(fp_b, x1.reshape(-1, 256), fp_w.t()).view(B, n, 256) * 0.25
+            sim = torch.bmm(md0, md1.transpose(1, 2)).contiguous()
+        else:
+            sim = torch.empty(B, Lp, Lp, device=dev, dtype=torch.float32)
+            check(lib.lgb200_x3_similarity(ptr(mdp), B, Lp, ptr(ctx.lens), ptr(sim), st), "x3_similarity")
+            sim = sim[:, :m, :n].contiguous()
         g = (g_pos if g_pos is not None else torch.zeros(B, device=dev)).to(torch.float32).contiguous()
         r = (g[:, None] * gt.sum(2)).contiguous()
         c = (g[:, None] * gt.sum(1)).contiguous()
-        st = torch.cuda.current_stream(dev).cuda_stream
         check(lib.lgb200_assign_dsim(ptr(sim), B, m, n, ptr(lse), Lp, ptr(gt), ptr(g), ptr(r), ptr(c), st), "assign_dsim")
-        dmd0 = torch.bmm(sim, md1)
-        dmd1 = torch.bmm(sim.transpose(1, 2), md0)
+        if mdp is None:
+            dmd0 = torch.bmm(sim, md1)
+            dmd1 = torch.bmm(sim.transpose(1, 2), md0)
+        else:  # three fp16 tensor-core products per GEMM, as _Kern.mm3
+            sp = torch.empty(2, B, m, n, device=dev, dtype=torch.float16)
+            inv = torch.empty(2, device=dev, dtype=torch.float32)
+            check(lib.lgb200_split_dynamic(ptr(sim), sim.numel(), ptr(sp), ptr(inv), st), "lgb200_split_dynamic")
+            mv = mdp.view(2, B, 2, Lp, 256)
+            mp0, mp1 = mv[:, :, 0, :m], mv[:, :, 1, :n]
+            f32 = torch.float32
+
+            def bmm3(A, Bm):
+                o = torch.bmm(A[1], Bm[0], out_dtype=f32)
+                o += torch.bmm(A[0], Bm[1], out_dtype=f32)
+                o += torch.bmm(A[0], Bm[0], out_dtype=f32)
+                return o.mul_(inv[0] * AI)
+
+            dmd0 = bmm3(sp, mp1)
+            dmd1 = bmm3(sp.transpose(2, 3), mp0)
         zv = z.view(B, 2, Lp)
         z0, z1 = zv[:, 0, :m], zv[:, 1, :n]
         gd0 = g_d0 if g_d0 is not None else torch.zeros_like(z0)
