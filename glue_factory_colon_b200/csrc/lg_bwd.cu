@@ -1,10 +1,11 @@
 // Backward kernels of the training path ("training forward + loss", the part the reference
 // gets from autograd, lightglue.py:484-498, 588-637).  Everything is fp32-accurate; the training step is not the
 // benchmarked path, what counts here is that the fused forward ops have fused backward ops (nothing N x M is materialised
-// by the attention backward either) and that gradients agree with the reference's autograd.  The attention backward runs
-// on the tensor cores (3xTF32 warp MMAs, `*_tc_kernel` below; the CUDA-core versions are kept behind
-// LGB200_ATTN_BWD_SIMT=1); plain GEMMs of the backward (dX = dY.W, dW = dY^T.X) are left to cuBLAS through torch.matmul
-// on the host side (glue_factory_colon_b200/train.py).
+// by the attention backward either) and that gradients agree with the reference's autograd.  The attention backward that
+// ships is the tcgen05 kernel of lg_x3_attn_bwd.cu (lgb200_attention_bwd dispatches to it); the kernels in this file are
+// its predecessors, kept as cross-checks: 3xTF32 warp MMAs (`*_tc_kernel`, LGB200_ATTN_BWD_MMASYNC=1) and CUDA cores
+// (LGB200_ATTN_BWD_SIMT=1).  Plain GEMMs of the backward (dX = dY.W, dW = dY^T.X) are left to cuBLAS on the host side
+// (glue_factory_colon_b200/train.py: three fp16 tensor-core GEMMs on split planes).
 //
 //   attn_bwd_stats_kernel   per query row: lse (log2 domain) and delta = <dO, O>          (flash-attention backward,
 //   attn_bwd_kernel<false>  dQ for 64 queries, sweeping the keys                           recomputing S tile by tile)
