@@ -124,8 +124,8 @@ class _Kern:
         (the product of the inverse plane scalings; float or 0-dim device tensor)."""
         f32 = torch.float32
         r = torch.mm(A[1], B[0], out_dtype=f32)
-        r += torch.mm(A[0], B[1], out_dtype=f32)
-        r += torch.mm(A[0], B[0], out_dtype=f32)
+        r = torch.addmm(r, A[0], B[1], out_dtype=f32)  # (beta = 1: accumulated in the GEMM epilogue, no extra pass)
+        r = torch.addmm(r, A[0], B[0], out_dtype=f32)
         return r.mul_(scale)
 
     def attention(self, q, k, v, kv_xor, ctx):
@@ -504,8 +504,8 @@ class AssignFn(torch.autograd.Function):
 
             def bmm3(A, Bm):
                 o = torch.bmm(A[1], Bm[0], out_dtype=f32)
-                o += torch.bmm(A[0], Bm[1], out_dtype=f32)
-                o += torch.bmm(A[0], Bm[0], out_dtype=f32)
+                o = torch.baddbmm(o, A[0], Bm[1], out_dtype=f32)
+                o = torch.baddbmm(o, A[0], Bm[0], out_dtype=f32)
                 return o.mul_(inv[0] * AI)
 
             dmd0 = bmm3(sp, mp1)

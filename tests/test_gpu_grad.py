@@ -29,15 +29,19 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize("kv_xor", [0, 1], ids=["self", "cross"])
-@pytest.mark.parametrize("lens", [None, [200, 131, 64, 256], [70, 0, 129, 5]], ids=["full", "ragged", "empty_side"])
-def test_attention_bwd_against_autograd(kv_xor, lens):
+@pytest.mark.parametrize("lens,gscale", [(None, 1.0), ([200, 131, 64, 256], 1.0), ([70, 0, 129, 5], 1.0),
+                                         ([200, 131, 64, 256], 3e-9), (None, 7e3)],
+                         ids=["full", "ragged", "empty_side", "ragged_tiny_gradient", "full_large_gradient"])
+def test_attention_bwd_against_autograd(kv_xor, lens, gscale):
+    """gscale: gradients have no fixed range -- the tcgen05 kernel splits g dO into fp16 planes with a per-call power of
+    two g (lg_x3_attn_bwd.cu); 3e-9 would vanish in fp16 without it, 7e3 would overflow the D planes."""
     lib = _abi.load()
     S, Lp = 4, 256
     g = torch.Generator().manual_seed(11 + kv_xor)
     q = (torch.randn(S, 4, Lp, 64, generator=g) * 0.6).to(DEV)
     k = (torch.randn(S, 4, Lp, 64, generator=g) * 0.6).to(DEV)
     v = torch.randn(S, 4, Lp, 64, generator=g).to(DEV)
-    dctx = torch.randn(S, Lp, 256, generator=g).to(DEV)
+    dctx = (torch.randn(S, Lp, 256, generator=g) * torch.rand(S, Lp, 1, generator=g) ** 4 * gscale).to(DEV)
     ln = torch.tensor(lens if lens is not None else [Lp] * S)
     lens_d = None if lens is None else ln.to(DEV, torch.int32)
     # reference: float64 autograd; q is in the log2 domain (the kernels exponentiate with exp2)
@@ -67,6 +71,42 @@ def test_attention_bwd_against_autograd(kv_xor, lens):
             assert float(got[s, :, int(ln[s]):].abs().max() if int(ln[s]) < Lp else 0.0) == 0.0
     assert lib.lgb200_attention_bwd(ptr(q), ptr(k), ptr(v), ptr(ctx), ptr(dctx), S, Lp, None, kv_xor, None, ptr(dk), ptr(dv),
                                     ptr(ws), _st()) == -2
+
+
+def test_attention_bwd_shared_qk_tensor_and_split_gemm():
+    """Cross block: to_qk feeds both sides, K IS Q (one plane pair inside the kernel wrapper).  Also the backward's
+    three-product tensor-core GEMM (_Kern.mm3 on lgb200_split_dynamic planes) against float64."""
+    lib = _abi.load()
+    S, Lp = 2, 384
+    g = torch.Generator().manual_seed(5)
+    qk = (torch.randn(S, 4, Lp, 64, generator=g) * 0.5).to(DEV)
+    v = torch.randn(S, 4, Lp, 64, generator=g).to(DEV)
+    dctx = (torch.randn(S, Lp, 256, generator=g) * 1e-4).to(DEV)
+    qd, vd = qk.double().cpu().requires_grad_(True), v.double().cpu().requires_grad_(True)
+    ctx_ref = torch.stack([(torch.softmax(qd[s] @ qd[s ^ 1].transpose(-1, -2) * math.log(2.0), -1) @ vd[s ^ 1])
+                           .permute(1, 0, 2).reshape(Lp, 256) for s in range(S)])
+    (ctx_ref * dctx.double().cpu()).sum().backward()
+    ctx = torch.zeros(S, Lp, 256, device=DEV)
+    assert lib.lgb200_attention(_abi.F32, ptr(qk), ptr(qk), ptr(v), S, Lp, None, 1, ptr(ctx), _st()) == 0
+    dq, dk, dv = (torch.empty(S, 4, Lp, 64, device=DEV) for _ in range(3))
+    n_ws = ctypes.c_longlong(0)
+    assert lib.lgb200_attention_bwd_workspace(S, Lp, ctypes.byref(n_ws)) == 0
+    ws = torch.empty(n_ws.value, device=DEV)
+    assert lib.lgb200_attention_bwd(ptr(qk), ptr(qk), ptr(v), ptr(ctx), ptr(dctx), S, Lp, None, 1, ptr(dq), ptr(dk),
+                                    ptr(dv), ptr(ws), _st()) == 0
+    assert _rel(dq + dk, qd.grad) < 2e-5 and _rel(dv, vd.grad) < 2e-5
+
+    from glue_factory_colon_b200.train import _Kern
+
+    kern = _Kern(DEV, 1, 128, 128)
+    a = (torch.randn(1024, 512, generator=g) * torch.rand(1024, 1, generator=g) ** 6 * 2e-7).to(DEV)   # a "gradient"
+    b = torch.randn(1024, 256, generator=g).to(DEV)                                                     # an activation
+    ap, ai = kern.gsplit(a)
+    got = kern.mm3(ap.transpose(1, 2), kern.asplit(b), ai / 64.0)
+    assert _rel(got, a.double().t() @ b.double()) < 2e-6
+    z = torch.zeros(8, 64, device=DEV)
+    zp, zi = kern.gsplit(z)
+    assert float(zi) == 1.0 and float(zp.abs().max()) == 0.0
 
 
 def test_ln_gelu_bwd_against_autograd():

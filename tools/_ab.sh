@@ -1,3 +1,17 @@
 cd /root/repo
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:x3_attn_bwd --launch-count 2 -o gpurun_out/r2_attn_bwd_full python tools/attn_bwd_bench.py 16 2048 1 > gpurun_out/ncu_bwd.log 2>&1; tail -3 gpurun_out/ncu_bwd.log
-ls -la gpurun_out/r2_attn_bwd_full.ncu-rep
+timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/gputest_all.log 2>&1; tail -8 gpurun_out/gputest_all.log | cut -c1-300
+python - <<'PY' 2>&1 | tail -5
+import torch
+a = torch.randn(64, 128, device="cuda").half(); b = torch.randn(128, 32, device="cuda").half()
+r = torch.mm(a, b, out_dtype=torch.float32)
+try:
+    r2 = torch.addmm(r, a, b, out_dtype=torch.float32)
+    print("addmm out_dtype ok", float((r2 - 2 * r).abs().max()))
+except Exception as e:
+    print("addmm ERR", str(e)[:200])
+try:
+    r3 = torch.baddbmm(torch.zeros(2, 64, 32, device="cuda"), a[None].expand(2, -1, -1), b[None].expand(2, -1, -1), out_dtype=torch.float32)
+    print("baddbmm out_dtype ok")
+except Exception as e:
+    print("baddbmm ERR", str(e)[:200])
+PY
