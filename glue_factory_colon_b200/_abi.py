@@ -38,7 +38,8 @@ SIGNATURES = {
     "lgb200_assign_loss": [_i, _p, _p, _p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p],
     "lgb200_exit_check": [_p, _i, _i, _p, _p, _f, _f, _i, _p, _p, _p],
     "lgb200_split_rows": [_p, C.c_longlong, _p, _p],
-    "lgb200_split_dynamic": [_p, C.c_longlong, _p, _p, _p],
+    "lgb200_split_dynamic": [_p, C.c_longlong, _p, _p, _i, _p, _i, _p],
+    "lgb200_merge_rows": [_p, C.c_longlong, _f, _p, _p],
     "lgb200_x3_similarity": [_p, _i, _i, _p, _p, _p],
     "lgb200_x3_assign_lse": [_p, _i, _i, _p, _i, _i, _p, _p],
     "lgb200_x3_assign_scores": [_p, _p, _p, _i, _i, _p, _i, _i, _p, _p],

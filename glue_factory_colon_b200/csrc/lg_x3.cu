@@ -511,6 +511,33 @@ __global__ void __launch_bounds__(256) x3_absmax_kernel(const float* __restrict_
   for (int ofs = 16; ofs; ofs >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, ofs));
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(slot, __float_as_uint(m));
 }
+// the same pass with per-block column sums (bias gradients) on the side: x [rows][4 * blockDim.x], block b sums rows
+// b, b + gridDim.x, ... into partials[b][cols]; the caller adds the gridDim.x partial rows
+__global__ void x3_absmax_colsum_kernel(const float* __restrict__ x, int rows, unsigned* __restrict__ slot,
+                                        float* __restrict__ partials) {
+  const int c4 = threadIdx.x, n4 = blockDim.x;
+  float m = 0.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[(size_t)r * n4 + c4];
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    if (v.x != v.x || v.y != v.y || v.z != v.z || v.w != v.w) m = INFINITY;
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  reinterpret_cast<float4*>(partials)[(size_t)blockIdx.x * n4 + c4] = acc;
+  for (int ofs = 16; ofs; ofs >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, ofs));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(slot, __float_as_uint(m));
+}
+// split planes [2][n] (value * scale_in = hi + lo) -> fp32
+__global__ void x3_merge_kernel(const __half* __restrict__ xs, size_t plane, size_t n4, float inv_scale, float* __restrict__ x) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const uint2 h = reinterpret_cast<const uint2*>(xs)[i], l = reinterpret_cast<const uint2*>(xs + plane)[i];
+  const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), h1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+  const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&l.x)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
+  reinterpret_cast<float4*>(x)[i] = make_float4((h0.x + l0.x) * inv_scale, (h0.y + l0.y) * inv_scale,
+                                                (h1.x + l1.x) * inv_scale, (h1.y + l1.y) * inv_scale);
+}
 __device__ __forceinline__ float x3_dynamic_scale(unsigned bits) {  // 1 for an all-zero or non-finite tensor
   const float m = __uint_as_float(bits);
   if (!(m > 0.f && m < INFINITY)) return 1.f;
@@ -658,18 +685,32 @@ extern "C" int lgb200_split_rows(const float* x, long long n, void* xs, void* st
   return LGB200_OK;
 }
 
-extern "C" int lgb200_split_dynamic(const float* x, long long n, void* xs, float* inv_scale, void* stream) {
+extern "C" int lgb200_split_dynamic(const float* x, long long n, void* xs, float* inv_scale, int cols,
+                                    float* colsum_partials, int n_partials, void* stream) {
   if (!x || !xs || !inv_scale) return LGB200_ERR_NULL;
   if (n <= 0 || n % 4) return LGB200_ERR_SHAPE;
+  if (colsum_partials && (cols <= 0 || cols % 4 || cols > 4096 || n % cols || n_partials <= 0)) return LGB200_ERR_SHAPE;
   const size_t n4 = (size_t)n / 4;
   cudaStream_t st = lg_stream(stream);
   unsigned* slot = reinterpret_cast<unsigned*>(inv_scale) + 1;  // inv_scale[1] holds the bit pattern of max |x|
   cudaError_t e;
   if ((e = cudaMemsetAsync(slot, 0, sizeof(unsigned), st)) != cudaSuccess) return (int)e;
   const unsigned nb = (unsigned)((n4 + 255) / 256);
-  x3_absmax_kernel<<<nb < 1184u ? nb : 1184u, 256, 0, st>>>(x, n4, slot);
+  if (colsum_partials)
+    x3_absmax_colsum_kernel<<<n_partials, cols / 4, 0, st>>>(x, (int)(n / cols), slot, colsum_partials);
+  else
+    x3_absmax_kernel<<<nb < 1184u ? nb : 1184u, 256, 0, st>>>(x, n4, slot);
   LG_LAUNCH_CHECK();
   x3_split_dynamic_kernel<<<nb, 256, 0, st>>>(x, n4, slot, (__half*)xs, (size_t)n, inv_scale);
+  LG_LAUNCH_CHECK();
+  return LGB200_OK;
+}
+
+extern "C" int lgb200_merge_rows(const void* xs, long long n, float inv_scale, float* x, void* stream) {
+  if (!x || !xs) return LGB200_ERR_NULL;
+  if (n <= 0 || n % 4) return LGB200_ERR_SHAPE;
+  const size_t n4 = (size_t)n / 4;
+  x3_merge_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, lg_stream(stream)>>>((const __half*)xs, (size_t)n, n4, inv_scale, x);
   LG_LAUNCH_CHECK();
   return LGB200_OK;
 }

@@ -94,9 +94,12 @@ class _Kern:
     def planes(self, *shape):
         return torch.zeros(2, *shape, device=self.dev, dtype=torch.float16)
 
-    def unsplit(self, p, *shape):
+    def unsplit(self, p, *shape, out=None):
         """split planes (x * 64 = hi + lo) -> fp32"""
-        return torch.add(p[0].float(), p[1].float()).mul_(1.0 / 64.0).view(*shape)
+        n = p.numel() // 2
+        out = torch.empty(n, device=self.dev, dtype=torch.float32) if out is None else out
+        check(self.lib.lgb200_merge_rows(ptr(p), n, AI, ptr(out), self.st), "lgb200_merge_rows")
+        return out.view(*shape) if shape else out
 
     def split(self, t):
         """fp32 -> split-fp16 planes [2][n] (x * 64 = hi + lo), the operand format of the LGB200_F32X3 kernels."""
@@ -108,14 +111,17 @@ class _Kern:
         """activation [M, N] fp32 -> planes [2, M, N] (scale 64)"""
         return self.split(t).view(2, *t.shape)
 
-    def gsplit(self, t):
+    def gsplit(self, t, colsum: bool = False):
         """gradient [M, N] fp32 -> (planes [2, M, N] of g t, 1 / g on the device): lgb200_split_dynamic picks the power of
-        two g per tensor (gradients have no fixed range)."""
+        two g per tensor (gradients have no fixed range).  colsum: also t.sum(0) (the bias gradient), from per-CTA
+        partials of the same pass over t."""
         t = t.contiguous()
         out = torch.empty(2, *t.shape, device=self.dev, dtype=torch.float16)
         inv = torch.empty(2, device=self.dev, dtype=torch.float32)
-        check(self.lib.lgb200_split_dynamic(ptr(t), t.numel(), ptr(out), ptr(inv), self.st), "lgb200_split_dynamic")
-        return out, inv[0]
+        part = torch.empty(N_PARTIALS, t.shape[-1], device=self.dev, dtype=torch.float32) if colsum else None
+        check(self.lib.lgb200_split_dynamic(ptr(t), t.numel(), ptr(out), ptr(inv), t.shape[-1] if colsum else 0, ptr(part),
+                                            N_PARTIALS if colsum else 0, self.st), "lgb200_split_dynamic")
+        return (out, inv[0], part.sum(0)) if colsum else (out, inv[0])
 
     @staticmethod
     def mm3(A, B, scale):
@@ -145,8 +151,7 @@ class _Kern:
         cp = torch.zeros(2, self.T, 256, device=self.dev, dtype=torch.float16)
         check(self.lib.lgb200_attention(F32X3, ptr(qp), ptr(kp), ptr(vp), self.S, self.Lp, ptr(self.lens), kv_xor, ptr(cp),
                                         self.st), "lgb200_attention")
-        torch.add(cp[0].float(), cp[1].float(), out=ctx)
-        ctx.mul_(1.0 / 64.0)
+        self.unsplit(cp, out=ctx)
         return cp
 
     def attention_bwd(self, q, k, v, ctx, dctx, kv_xor):
@@ -314,30 +319,31 @@ def _ffn_bwd(k: _Kern, w: Dict, pre: str, x, msg, dy):
         dh, act, gsum = k.ln_gelu_bwd(h, w[pre + "ln_g"], w[pre + "ln_b"], da)
         g3, g0 = dy.t() @ act, torch.cat([dh.t() @ x, dh.t() @ msg], 1)
         dcat = dh @ w[pre + "f0_w"]
+        b3, b0 = dy.sum(0), dh.sum(0)
     else:
         wx = w["x3"]
-        dyp, dyi = k.gsplit(dy)
+        dyp, dyi, b3 = k.gsplit(dy, colsum=True)
         da = k.mm3(dyp, wx[pre + "f3_w"], dyi * WI)
         dh, act, gsum = k.ln_gelu_bwd(h, w[pre + "ln_g"], w[pre + "ln_b"], da)
         g3 = k.mm3(dyp.transpose(1, 2), k.asplit(act), dyi * AI)
-        dhp, dhi = k.gsplit(dh)
+        dhp, dhi, b0 = k.gsplit(dh, colsum=True)
         dht = dhp.transpose(1, 2)
         g0 = torch.cat([k.mm3(dht, k.asplit(x), dhi * AI), k.mm3(dht, k.asplit(msg), dhi * AI)], 1)
         dcat = k.mm3(dhp, wx[pre + "f0_w"], dhi * WI)
     g = {
-        pre + "f3_w": g3, pre + "f3_b": dy.sum(0),
+        pre + "f3_w": g3, pre + "f3_b": b3,
         pre + "ln_g": gsum[:512], pre + "ln_b": gsum[512:],
-        pre + "f0_w": g0, pre + "f0_b": dh.sum(0),
+        pre + "f0_w": g0, pre + "f0_b": b0,
     }
     return dcat[:, :256], dcat[:, 256:].contiguous(), g
 
 
 def _proj_bwd(k: _Kern, w: Dict, name: str, dy, x):
-    """Backward of y = x W^T (+ b) for the weight `name` ([N, K], planes in w["x3"]): (dy^T x, dy W)."""
+    """Backward of y = x W^T + b for the weight `name` ([N, K], planes in w["x3"]): (dy^T x, dy^T 1, dy W)."""
     if _SGEMM:
-        return dy.t() @ x, dy @ w[name]
-    dyp, dyi = k.gsplit(dy)
-    return k.mm3(dyp.transpose(1, 2), k.asplit(x), dyi * AI), k.mm3(dyp, w["x3"][name], dyi * WI)
+        return dy.t() @ x, dy.sum(0), dy @ w[name]
+    dyp, dyi, db = k.gsplit(dy, colsum=True)
+    return k.mm3(dyp.transpose(1, 2), k.asplit(x), dyi * AI), db, k.mm3(dyp, w["x3"][name], dyi * WI)
 
 
 class TransformerFn(torch.autograd.Function):
@@ -406,13 +412,11 @@ class TransformerFn(torch.autograd.Function):
             dxa, dmsg, g = _ffn_bwd(k, w, "c", x_mid, msg, dx)
             for name, val in g.items():
                 grads[(i, name)] = val
-            grads[(i, "co_w")], dc = _proj_bwd(k, w, "co_w", dmsg, c)
-            grads[(i, "co_b")] = dmsg.sum(0)
+            grads[(i, "co_w")], grads[(i, "co_b")], dc = _proj_bwd(k, w, "co_w", dmsg, c)
             dq, dk, dv = k.attention_bwd(qk, qk, v, c, dc, 1)
             dqv = k.heads_bwd(dq, dk, dv, None, None, None, 2, (C_SCALE, 1.0, 1.0), None)
-            gw, dxp = _proj_bwd(k, w, "cqv_w", dqv, x_mid)
+            gw, gb, dxp = _proj_bwd(k, w, "cqv_w", dqv, x_mid)
             grads[(i, "cqk_w")], grads[(i, "cv_w")] = gw[:256], gw[256:]
-            gb = dqv.sum(0)
             grads[(i, "cqk_b")], grads[(i, "cv_b")] = gb[:256], gb[256:]
             dxm = dx + dxa + dxp
             # ---- self block (lightglue.py:151-164) ----
@@ -421,15 +425,13 @@ class TransformerFn(torch.autograd.Function):
             dxa, dmsg, g = _ffn_bwd(k, w, "s", x_in, msg, dxm)
             for name, val in g.items():
                 grads[(i, name)] = val
-            grads[(i, "so_w")], dc = _proj_bwd(k, w, "so_w", dmsg, c)
-            grads[(i, "so_b")] = dmsg.sum(0)
+            grads[(i, "so_w")], grads[(i, "so_b")], dc = _proj_bwd(k, w, "so_w", dmsg, c)
             dq, dk, dv = k.attention_bwd(q, kk, v, c, dc, 0)
             dqkv = k.heads_bwd(dq, dk, dv, q, kk, rot, 3, (Q_SCALE, 1.0, 1.0), dtheta)
             perm = _PERM.to(dqkv.device)
             gw = torch.empty(768, 256, device=dqkv.device, dtype=torch.float32)
-            gw[perm], dxp = _proj_bwd(k, w, "qkv_w", dqkv, x_in)
             gb = torch.empty(768, device=dqkv.device, dtype=torch.float32)
-            gb[perm] = dqkv.sum(0)
+            gw[perm], gb[perm], dxp = _proj_bwd(k, w, "qkv_w", dqkv, x_in)
             grads[(i, "qkv_w")], grads[(i, "qkv_b")] = gw, gb
             dx = dxm + dxa + dxp
         # positional encoding: theta = Wr . normalised keypoints (lightglue.py:61-66)
@@ -497,7 +499,7 @@ class AssignFn(torch.autograd.Function):
         else:  # three fp16 tensor-core products per GEMM, as _Kern.mm3
             sp = torch.empty(2, B, m, n, device=dev, dtype=torch.float16)
             inv = torch.empty(2, device=dev, dtype=torch.float32)
-            check(lib.lgb200_split_dynamic(ptr(sim), sim.numel(), ptr(sp), ptr(inv), st), "lgb200_split_dynamic")
+            check(lib.lgb200_split_dynamic(ptr(sim), sim.numel(), ptr(sp), ptr(inv), 0, None, 0, st), "lgb200_split_dynamic")
             mv = mdp.view(2, B, 2, Lp, 256)
             mp0, mp1 = mv[:, :, 0, :m], mv[:, :, 1, :n]
             f32 = torch.float32

@@ -267,8 +267,13 @@ int lgb200_prune_compact(const float* match, const float* conf, float thr, float
 int lgb200_split_rows(const float* x, long long n, void* xs, void* stream);
 /* lgb200_split_dynamic: the same for tensors without a fixed range (gradients): xs [2][n] = planes of g x with g the
  * power of two that brings max |x| into [256, 512) (1 for an all-zero tensor); inv_scale[0] = 1 / g on the device,
- * inv_scale[1] is scratch (two floats).  Feeds the three-product tensor-core GEMMs of the backward pass (train.py). */
-int lgb200_split_dynamic(const float* x, long long n, void* xs, float* inv_scale, void* stream);
+ * inv_scale[1] is scratch (two floats).  Feeds the three-product tensor-core GEMMs of the backward pass (train.py).
+ * colsum_partials (nullable): x is read as [n / cols][cols] and colsum_partials [n_partials][cols] receives per-CTA
+ * column sums from the same pass (the caller adds the n_partials rows: the bias gradient dY^T 1); cols % 4 == 0.
+ * lgb200_merge_rows: planes [2][n] -> x [n] = (hi + lo) * inv_scale. */
+int lgb200_split_dynamic(const float* x, long long n, void* xs, float* inv_scale, int cols, float* colsum_partials,
+                         int n_partials, void* stream);
+int lgb200_merge_rows(const void* xs, long long n, float inv_scale, float* x, void* stream);
 /* Similarity of MatchAssignment (the einsum of lightglue.py:284) for all pairs: mds = split planes of
  * final_proj(desc)/4 [2][S*Lp][256]; sim [B][Lp][Lp] fp32 receives <md[2b,i], md[2b+1,j]> for i < lens[2b],
  * j < lens[2b+1] (tiles past the valid counts are not touched). Lp % 256 == 0. */
