@@ -19,6 +19,11 @@
 // warps work on tile j) | D hi, lo | P hi, lo | out1 | out2.  The DQ role first sweeps the other tiles once for the row
 // statistics (log-sum-exp in the log2 domain and delta; written to the workspace for the DKV role), then a second time
 // for dQ.
+// TWO-LEVEL ACCUMULATION (as in lg_x3_attn.cu): the tensor core rounds its fp32 accumulator toward zero after every MMA,
+// so one accumulator over 2048 other rows (384 MMAs) is ~1e-5 low on same-sign sums (measured against float64:
+// tools/attn_bwd_accuracy.py, profiles/r2_attn_bwd_tcgen05.txt).  out1 / out2 therefore collect XB_FLUSH tiles (48 MMAs)
+// and are then added, round-to-nearest, to fp32 running sums that every softmax thread keeps for its own row in shared
+// memory ([column][row]: conflict-free); the first MMA after a flush overwrites the accumulator.
 #include "lg_internal.cuh"
 #include "lg_tc_common.cuh"
 #include <cuda_fp16.h>
@@ -34,8 +39,11 @@ constexpr int XB_U = 2 * XB_TBO;                // Uh | Ul
 constexpr int XB_Y = 4 * XB_TBO;                // XB_NST x 32 KB
 constexpr int XB_BAR = XB_Y + XB_NST * 4 * XB_TBY;  // 160 KB of tiles
 constexpr int XB_NBAR = 1 + 2 * XB_NST + 2 + 2 + 1 + 1;
-constexpr int XB_XCH = XB_BAR + 256;            // [128 rows][2 parts] float4 (max, sum, partial delta)
-constexpr int XB_SMEM = XB_XCH + 128 * 2 * 16;
+constexpr int XB_ACC = XB_BAR + 256;            // [128 columns][128 rows] fp32 running sums of out1 | out2 (64 KB)
+constexpr int XB_XCH = XB_ACC;                  // [128 rows][2 parts] float4 (max, sum, partial delta): statistics sweep only
+constexpr int XB_SMEM = XB_ACC + 128 * 128 * 4;
+constexpr int XB_FLUSH = 4;                     // tiles per TMEM accumulator before it is folded into the running sums
+static_assert(XB_SMEM <= 227 * 1024, "attention backward: shared memory");
 constexpr uint32_t XT_SC = 0, XT_DP = 128, XT_DH = 256, XT_DL = 288, XT_PH = 320, XT_PL = 352, XT_O1 = 384, XT_O2 = 448;
 constexpr float XB_DC = 1.f / 64.f;             // D planes hold (g / 64) D
 constexpr float XB_LN2 = 0.69314718055994530942f;
@@ -237,7 +245,7 @@ x3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       if (tc::elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint32_t acc = (jm | k) != 0;
+          const uint32_t acc = ((jm % XB_FLUSH) | k) != 0;  // fresh accumulators after every flush
           tc::umma_ts(tmem + XT_O1, tmem + XT_DL + k * 8, mYh + k * (2048 >> 4), idesc_out, acc);
           tc::umma_ts(tmem + XT_O1, tmem + XT_DH + k * 8, mYl + k * (2048 >> 4), idesc_out, 1);
           tc::umma_ts(tmem + XT_O1, tmem + XT_DH + k * 8, mYh + k * (2048 >> 4), idesc_out, 1);
@@ -320,6 +328,28 @@ x3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       }
     }
 
+    // ---- running sums of this thread's 32 (+32) output columns, [column][row] in shared memory
+    float* racc = reinterpret_cast<float*>(smem + XB_ACC) + r;
+    if (!DKV) asm volatile("bar.sync 5, 256;" ::: "memory");  // every softmax thread has read xch (aliased with the sums)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      racc[(part * 32 + i) * 128] = 0.f;
+      if (DKV) racc[(64 + part * 32 + i) * 128] = 0.f;
+    }
+    auto flush = [&]() {  // TMEM accumulators (complete: out_done observed) -> running sums, round to nearest
+      uint32_t o[32];
+      tc::tmem_ld32(tmem + lane_base + XT_O1 + part * 32, o);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) racc[(part * 32 + i) * 128] += __uint_as_float(o[i]);
+      if (DKV) {
+        tc::tmem_ld32(tmem + lane_base + XT_O2 + part * 32, o);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) racc[(64 + part * 32 + i) * 128] += __uint_as_float(o[i]);
+      }
+    };
+
     // ---- main sweep
     for (int it = first_main; it < n_iter; ++it) {
       const int jm = it - first_main, b = it & 1;
@@ -366,6 +396,8 @@ x3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       if (jm > 0) {
         tc::mbar_wait(out_done, (jm - 1) & 1);  // the MMAs that read the previous planes have retired
         tc::fence_after_sync();
+        // the issuer starts fresh accumulators with tile jm only after this warp's pd_ready arrive below
+        if (jm % XB_FLUSH == 0) flush();
       }
       tc::tmem_st16(tmem + lane_base + XT_DH + part * 16, dh);
       tc::tmem_st16(tmem + lane_base + XT_DL + part * 16, dl);
@@ -381,30 +413,21 @@ x3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     // ---- epilogue: this thread's 32 output columns of its row
     tc::mbar_wait(out_done, (n_tiles - 1) & 1);
     tc::fence_after_sync();
-    {
-      uint32_t o[32];
-      tc::tmem_ld32(tmem + lane_base + XT_O1 + part * 32, o);
-      tc::tmem_ld_wait();
-      // raw = ((g / 64) D) . (64 Y)
-      const float k1 = XB_LN2 / (g * XB_DC * LG_X3_EA);
-      if (row_ok) {
-        float4* dst = reinterpret_cast<float4*>(out1 + own_stat * LG_DH + part * 32);
+    flush();
+    if (row_ok) {
+      const float k1 = XB_LN2 / (g * XB_DC * LG_X3_EA);  // raw = ((g / 64) D) . (64 Y)
+      float4* dst = reinterpret_cast<float4*>(out1 + own_stat * LG_DH + part * 32);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        dst[i] = make_float4(racc[(part * 32 + 4 * i) * 128] * k1, racc[(part * 32 + 4 * i + 1) * 128] * k1,
+                             racc[(part * 32 + 4 * i + 2) * 128] * k1, racc[(part * 32 + 4 * i + 3) * 128] * k1);
+      if (DKV) {
+        const float k2 = 1.f / (g * LG_X3_EP);  // raw = (256 P) . (g dO)
+        float4* dst2 = reinterpret_cast<float4*>(out2 + own_stat * LG_DH + part * 32);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          dst[i] = make_float4(__uint_as_float(o[4 * i]) * k1, __uint_as_float(o[4 * i + 1]) * k1,
-                               __uint_as_float(o[4 * i + 2]) * k1, __uint_as_float(o[4 * i + 3]) * k1);
-      }
-      if (DKV) {
-        tc::tmem_ld32(tmem + lane_base + XT_O2 + part * 32, o);
-        tc::tmem_ld_wait();
-        const float k2 = 1.f / (g * LG_X3_EP);  // raw = (256 P) . (g dO)
-        if (row_ok) {
-          float4* dst = reinterpret_cast<float4*>(out2 + own_stat * LG_DH + part * 32);
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            dst[i] = make_float4(__uint_as_float(o[4 * i]) * k2, __uint_as_float(o[4 * i + 1]) * k2,
-                                 __uint_as_float(o[4 * i + 2]) * k2, __uint_as_float(o[4 * i + 3]) * k2);
-        }
+          dst2[i] = make_float4(racc[(64 + part * 32 + 4 * i) * 128] * k2, racc[(64 + part * 32 + 4 * i + 1) * 128] * k2,
+                                racc[(64 + part * 32 + 4 * i + 2) * 128] * k2, racc[(64 + part * 32 + 4 * i + 3) * 128] * k2);
       }
     }
   }

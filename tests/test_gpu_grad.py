@@ -73,6 +73,34 @@ def test_attention_bwd_against_autograd(kv_xor, lens, gscale):
                                     ptr(ws), _st()) == -2
 
 
+def test_attention_bwd_long_sequence_accumulation():
+    """2048 keys = 384 MMAs per output element: a single tensor-core accumulator (rounded toward zero after every MMA) is
+    ~1e-5 low on same-sign sums; the kernel folds its TMEM accumulators into round-to-nearest running sums every 4 tiles
+    (lg_x3_attn_bwd.cu).  Reference: float64 autograd on the GPU; inputs with non-zero means so that the sums have a sign."""
+    lib = _abi.load()
+    S, Lp = 2, 2048
+    g = torch.Generator().manual_seed(1)
+    q = (torch.randn(S, 4, Lp, 64, generator=g) * 0.6).to(DEV)
+    k = (torch.randn(S, 4, Lp, 64, generator=g) * 0.6).to(DEV)
+    v = (torch.randn(S, 4, Lp, 64, generator=g) + 0.5).to(DEV)
+    dctx = (torch.randn(S, Lp, 256, generator=g) * 1e-3 + 5e-4).to(DEV)
+    qd, kd, vd = (t.double().requires_grad_(True) for t in (q, k, v))
+    a = torch.softmax(qd @ kd.transpose(-1, -2) * math.log(2.0), -1)
+    ((a @ vd).permute(0, 2, 1, 3).reshape(S, Lp, 256) * dctx.double()).sum().backward()
+    ctx = torch.zeros(S, Lp, 256, device=DEV)
+    assert lib.lgb200_attention(_abi.F32, ptr(q), ptr(k), ptr(v), S, Lp, None, 0, ptr(ctx), _st()) == 0
+    dq, dk, dv = (torch.empty(S, 4, Lp, 64, device=DEV) for _ in range(3))
+    n_ws = ctypes.c_longlong(0)
+    assert lib.lgb200_attention_bwd_workspace(S, Lp, ctypes.byref(n_ws)) == 0
+    ws = torch.empty(n_ws.value, device=DEV)
+    assert lib.lgb200_attention_bwd(ptr(q), ptr(k), ptr(v), ptr(ctx), ptr(dctx), S, Lp, None, 0, ptr(dq), ptr(dk), ptr(dv),
+                                    ptr(ws), _st()) == 0
+    for name, got, ref in (("dq", dq, qd.grad), ("dk", dk, kd.grad), ("dv", dv, vd.grad)):
+        d = got.double() - ref
+        assert float(d.norm() / ref.norm()) < 4e-6, f"{name}: {float(d.norm() / ref.norm()):.2e}"
+        assert abs(float(d.mean() / ref.abs().mean())) < 2e-6, f"{name}: one-sided error {float(d.mean() / ref.abs().mean()):+.2e}"
+
+
 def test_attention_bwd_shared_qk_tensor_and_split_gemm():
     """Cross block: to_qk feeds both sides, K IS Q (one plane pair inside the kernel wrapper).  Also the backward's
     three-product tensor-core GEMM (_Kern.mm3 on lgb200_split_dynamic planes) against float64."""
