@@ -27,6 +27,7 @@
 #include "lg_internal.cuh"
 #include "lg_tc_common.cuh"
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -121,8 +122,9 @@ __global__ void __launch_bounds__(256) xb_split_kernel(const float* __restrict__
 }
 
 // ----------------------------------------------------------------------------------------------- the backward kernel
-template <bool DKV>
-__global__ void __launch_bounds__(320, 1)
+// NP = softmax threads per own row: 2 (8 warps, 32 score columns each) or 4 (16 warps, 16 columns each)
+template <bool DKV, int NP>
+__global__ void __launch_bounds__(64 + 128 * NP, 1)
 x3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmU,
                    const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmW, int Lp,
                    const int32_t* __restrict__ lens, int kv_xor, const float* __restrict__ ctx,
@@ -157,8 +159,8 @@ x3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     tc::prefetch_tmap(&tmW);
     tc::mbar_init(own_full, 1);
     for (int i = 0; i < XB_NST; ++i) { tc::mbar_init(&y_full[i], 1); tc::mbar_init(&y_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&sc_full[i], 1); tc::mbar_init(&sc_free[i], 8); }
-    tc::mbar_init(pd_ready, 8);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&sc_full[i], 1); tc::mbar_init(&sc_free[i], 4 * NP); }
+    tc::mbar_init(pd_ready, 4 * NP);
     tc::mbar_init(out_done, 1);
     tc::fence_barrier_init();
   }
@@ -263,9 +265,18 @@ x3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   } else {
     // ------------------------------------------------------------------------------------------- softmax warps
     const int quarter = warp & 3;
-    const int part = (warp - 2) >> 2;  // column half of every score tile
-    const int r = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const int part = (warp - 2) >> 2;  // which COLS columns of every score tile / OC columns of the outputs
+    constexpr int COLS = XB_OT / NP, OC = 64 / NP;
+    auto ld_cols = [&](uint32_t col, uint32_t* dst) {  // COLS (= OC) consecutive TMEM columns of this thread's lane
+      if constexpr (COLS == 32) tc::tmem_ld32(tmem + lane_base + col, dst);
+      else tc::tmem_ld16(tmem + lane_base + col, dst);
+    };
+    auto st_plane = [&](uint32_t col, const uint32_t* src) {  // COLS / 2 packed fp16 pairs
+      if constexpr (COLS == 32) tc::tmem_st16(tmem + lane_base + col, src);
+      else tc::tmem_st8(tmem + lane_base + col, src);
+    };
+    const int r = quarter * 32 + lane;
     const bool row_ok = r0 + r < n_own;
     constexpr float s_us = 1.f / (LG_X3_EA * LG_X3_EA);
     const float g = *gptr;
@@ -274,23 +285,23 @@ x3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     float lse_own = 0.f, dlt_own = 0.f;  // DQ: this row's log-sum-exp and g * delta
 
     if (!DKV) {
-      // ---- statistics sweep: every thread keeps the online (max, sum) of ITS 32 columns; partial states merge
-      // associatively, so the two threads of a row are combined once, after the sweep
+      // ---- statistics sweep: every thread keeps the online (max, sum) of ITS columns; partial states merge
+      // associatively, so the NP threads of a row are combined once, after the sweep
       float m = -INFINITY, l = 0.f;
       for (int it = 0; it < n_tiles; ++it) {
         const int b = it & 1;
         tc::mbar_wait(&sc_full[b], (it >> 1) & 1);
         tc::fence_after_sync();
-        uint32_t sv[32];
-        tc::tmem_ld32(tmem + lane_base + XT_SC + b * XB_OT + part * 32, sv);
+        uint32_t sv[COLS];
+        ld_cols(XT_SC + b * XB_OT + part * COLS, sv);
         tc::tmem_ld_wait();
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&sc_free[b]);
-        const int valid = n_oth - it * XB_OT - part * 32;
+        const int valid = n_oth - it * XB_OT - part * COLS;
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < COLS; ++i) {
           if (i >= valid) sv[i] = 0xff800000u;  // -inf
           mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv[i]));
         }
@@ -299,28 +310,36 @@ x3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         const float msafe = mnew == -INFINITY ? 0.f : mnew;
         float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < 32; ++i) rs4[i & 3] += xb_ex2(fmaf(__uint_as_float(sv[i]), s_us, -msafe));
+        for (int i = 0; i < COLS; ++i) rs4[i & 3] += xb_ex2(fmaf(__uint_as_float(sv[i]), s_us, -msafe));
         l = l * xb_ex2(m - msafe) + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
         m = mnew;
       }
       float dot = 0.f;
       if (row_ok) {
-        const size_t off = ((size_t)s * Lp + r0 + r) * LG_D + h * LG_DH + part * 32;
+        const size_t off = ((size_t)s * Lp + r0 + r) * LG_D + h * LG_DH + part * OC;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < OC / 4; ++i) {
           const float4 o = *reinterpret_cast<const float4*>(ctx + off + 4 * i);
           const float4 gr = *reinterpret_cast<const float4*>(dctx + off + 4 * i);
           dot += (o.x * gr.x + o.y * gr.y) + (o.z * gr.z + o.w * gr.w);
         }
       }
-      xch[r * 2 + part] = make_float4(m, l, dot, 0.f);
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-      const float4 a = xch[r * 2], bq = xch[r * 2 + 1];
-      const float mnew = fmaxf(a.x, bq.x);
+      xch[r * NP + part] = make_float4(m, l, dot, 0.f);
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "n"(32 * NP) : "memory");
+      float4 pt[NP];
+#pragma unroll
+      for (int i = 0; i < NP; ++i) pt[i] = xch[r * NP + i];
+      float mnew = pt[0].x;
+#pragma unroll
+      for (int i = 1; i < NP; ++i) mnew = fmaxf(mnew, pt[i].x);
       const float msafe = mnew == -INFINITY ? 0.f : mnew;
-      const float lsum = a.y * xb_ex2(a.x - msafe) + bq.y * xb_ex2(bq.x - msafe);
+      float lsum = 0.f, delta = 0.f;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        lsum += pt[i].y * xb_ex2(pt[i].x - msafe);
+        delta += pt[i].z;
+      }
       lse_own = lsum > 0.f ? mnew + log2f(lsum) : INFINITY;
-      const float delta = a.z + bq.z;
       dlt_own = delta * g;
       if (part == 0 && row_ok) {
         lse2[own_stat] = lse_own;
@@ -328,44 +347,44 @@ x3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       }
     }
 
-    // ---- running sums of this thread's 32 (+32) output columns, [column][row] in shared memory
+    // ---- running sums of this thread's OC (+OC) output columns, [column][row] in shared memory
     float* racc = reinterpret_cast<float*>(smem + XB_ACC) + r;
-    if (!DKV) asm volatile("bar.sync 5, 256;" ::: "memory");  // every softmax thread has read xch (aliased with the sums)
+    if (!DKV) asm volatile("bar.sync 5, %0;" ::"n"(128 * NP) : "memory");  // every softmax thread has read xch (aliased with the sums)
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      racc[(part * 32 + i) * 128] = 0.f;
-      if (DKV) racc[(64 + part * 32 + i) * 128] = 0.f;
+    for (int i = 0; i < OC; ++i) {
+      racc[(part * OC + i) * 128] = 0.f;
+      if (DKV) racc[(64 + part * OC + i) * 128] = 0.f;
     }
     auto flush = [&]() {  // TMEM accumulators (complete: out_done observed) -> running sums, round to nearest
-      uint32_t o[32];
-      tc::tmem_ld32(tmem + lane_base + XT_O1 + part * 32, o);
+      uint32_t o[OC];
+      ld_cols(XT_O1 + part * OC, o);
       tc::tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) racc[(part * 32 + i) * 128] += __uint_as_float(o[i]);
+      for (int i = 0; i < OC; ++i) racc[(part * OC + i) * 128] += __uint_as_float(o[i]);
       if (DKV) {
-        tc::tmem_ld32(tmem + lane_base + XT_O2 + part * 32, o);
+        ld_cols(XT_O2 + part * OC, o);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) racc[(64 + part * 32 + i) * 128] += __uint_as_float(o[i]);
+        for (int i = 0; i < OC; ++i) racc[(64 + part * OC + i) * 128] += __uint_as_float(o[i]);
       }
     };
 
     // ---- main sweep
     for (int it = first_main; it < n_iter; ++it) {
       const int jm = it - first_main, b = it & 1;
-      const int n0 = jm * XB_OT + part * 32;  // first other row of this thread's columns
+      const int n0 = jm * XB_OT + part * COLS;  // first other row of this thread's columns
       tc::mbar_wait(&sc_full[b], (it >> 1) & 1);
       tc::fence_after_sync();
-      uint32_t sv[32], dv[32];
-      tc::tmem_ld32(tmem + lane_base + XT_SC + b * XB_OT + part * 32, sv);
-      tc::tmem_ld32(tmem + lane_base + XT_DP + b * XB_OT + part * 32, dv);
+      uint32_t sv[COLS], dv[COLS];
+      ld_cols(XT_SC + b * XB_OT + part * COLS, sv);
+      ld_cols(XT_DP + b * XB_OT + part * COLS, dv);
       tc::tmem_ld_wait();
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&sc_free[b]);
-      uint32_t dh[16], dl[16], ph[16], pl[16];
+      uint32_t dh[COLS / 2], dl[COLS / 2], ph[COLS / 2], pl[COLS / 2];
 #pragma unroll
-      for (int i4 = 0; i4 < 8; ++i4) {
+      for (int i4 = 0; i4 < COLS / 4; ++i4) {
         float lq[4], dq[4];
         if (DKV) {  // per-column statistics of the queries (uniform over the warp: broadcast loads)
           const float4 l4 = *reinterpret_cast<const float4*>(lse2 + oth_stat + n0 + 4 * i4);
@@ -399,11 +418,11 @@ x3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         // the issuer starts fresh accumulators with tile jm only after this warp's pd_ready arrive below
         if (jm % XB_FLUSH == 0) flush();
       }
-      tc::tmem_st16(tmem + lane_base + XT_DH + part * 16, dh);
-      tc::tmem_st16(tmem + lane_base + XT_DL + part * 16, dl);
+      st_plane(XT_DH + part * (COLS / 2), dh);
+      st_plane(XT_DL + part * (COLS / 2), dl);
       if (DKV) {
-        tc::tmem_st16(tmem + lane_base + XT_PH + part * 16, ph);
-        tc::tmem_st16(tmem + lane_base + XT_PL + part * 16, pl);
+        st_plane(XT_PH + part * (COLS / 2), ph);
+        st_plane(XT_PL + part * (COLS / 2), pl);
       }
       tc::tmem_st_wait();
       tc::fence_before_sync();
@@ -416,18 +435,18 @@ x3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     flush();
     if (row_ok) {
       const float k1 = XB_LN2 / (g * XB_DC * LG_X3_EA);  // raw = ((g / 64) D) . (64 Y)
-      float4* dst = reinterpret_cast<float4*>(out1 + own_stat * LG_DH + part * 32);
+      float4* dst = reinterpret_cast<float4*>(out1 + own_stat * LG_DH + part * OC);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        dst[i] = make_float4(racc[(part * 32 + 4 * i) * 128] * k1, racc[(part * 32 + 4 * i + 1) * 128] * k1,
-                             racc[(part * 32 + 4 * i + 2) * 128] * k1, racc[(part * 32 + 4 * i + 3) * 128] * k1);
+      for (int i = 0; i < OC / 4; ++i)
+        dst[i] = make_float4(racc[(part * OC + 4 * i) * 128] * k1, racc[(part * OC + 4 * i + 1) * 128] * k1,
+                             racc[(part * OC + 4 * i + 2) * 128] * k1, racc[(part * OC + 4 * i + 3) * 128] * k1);
       if (DKV) {
         const float k2 = 1.f / (g * LG_X3_EP);  // raw = (256 P) . (g dO)
-        float4* dst2 = reinterpret_cast<float4*>(out2 + own_stat * LG_DH + part * 32);
+        float4* dst2 = reinterpret_cast<float4*>(out2 + own_stat * LG_DH + part * OC);
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          dst2[i] = make_float4(racc[(64 + part * 32 + 4 * i) * 128] * k2, racc[(64 + part * 32 + 4 * i + 1) * 128] * k2,
-                                racc[(64 + part * 32 + 4 * i + 2) * 128] * k2, racc[(64 + part * 32 + 4 * i + 3) * 128] * k2);
+        for (int i = 0; i < OC / 4; ++i)
+          dst2[i] = make_float4(racc[(64 + part * OC + 4 * i) * 128] * k2, racc[(64 + part * OC + 4 * i + 1) * 128] * k2,
+                                racc[(64 + part * OC + 4 * i + 2) * 128] * k2, racc[(64 + part * OC + 4 * i + 3) * 128] * k2);
       }
     }
   }
@@ -487,12 +506,21 @@ int lg_x3_attention_bwd(const float* Q, const float* K, const float* V, const fl
   if ((rc = lg_make_tmap_bf16(&tk, Kp, 3, d, sb, box))) return rc;
   if ((rc = lg_make_tmap_bf16(&tv, Vp, 3, d, sb, box))) return rc;
   if ((rc = lg_make_tmap_bf16(&tg, Gp, 3, d, sb, box))) return rc;
-  if ((e = cudaFuncSetAttribute(x3_attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, XB_SMEM)) != cudaSuccess) return (int)e;
-  if ((e = cudaFuncSetAttribute(x3_attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, XB_SMEM)) != cudaSuccess) return (int)e;
+  // softmax threads per own row, per role (LGB200_X3_BWD_NP = "<dq><dkv>", e.g. 24)
+  static const int np_cfg = getenv("LGB200_X3_BWD_NP") ? atoi(getenv("LGB200_X3_BWD_NP")) : 44;
   const dim3 grid(Lp / 128, LG_HEADS, S);
-  x3_attn_bwd_kernel<false><<<grid, 320, XB_SMEM, st>>>(tq, tg, tk, tv, Lp, lens, kv_xor, ctx, dctx, g, lse2, dlt, dQ, nullptr);
-  LG_LAUNCH_CHECK();
-  x3_attn_bwd_kernel<true><<<grid, 320, XB_SMEM, st>>>(tk, tv, tq, tg, Lp, lens, kv_xor, ctx, dctx, g, lse2, dlt, dK, dV);
-  LG_LAUNCH_CHECK();
-  return LGB200_OK;
+  auto launch = [&](auto kern, int np, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const CUtensorMap& d,
+                    float* o1, float* o2) -> int {
+    cudaError_t le = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, XB_SMEM);
+    if (le != cudaSuccess) return (int)le;
+    kern<<<grid, 64 + 128 * np, XB_SMEM, st>>>(a, b, c, d, Lp, lens, kv_xor, ctx, dctx, g, lse2, dlt, o1, o2);
+    LG_LAUNCH_CHECK();
+    return LGB200_OK;
+  };
+  if (np_cfg / 10 == 2) rc = launch(x3_attn_bwd_kernel<false, 2>, 2, tq, tg, tk, tv, dQ, nullptr);
+  else rc = launch(x3_attn_bwd_kernel<false, 4>, 4, tq, tg, tk, tv, dQ, nullptr);
+  if (rc) return rc;
+  if (np_cfg % 10 == 2) rc = launch(x3_attn_bwd_kernel<true, 2>, 2, tk, tv, tq, tg, dK, dV);
+  else rc = launch(x3_attn_bwd_kernel<true, 4>, 4, tk, tv, tq, tg, dK, dV);
+  return rc;
 }
