@@ -14,11 +14,15 @@
 // operands Q, K, V carry the activation scaling LG_X3_EA, dO a per-call power of two g chosen so that max |g dO| lies in
 // [256, 512) (gradients have no fixed range: a fixed scaling would push small ones into the fp16 subnormals), P the
 // scaling LG_X3_EP and D the scaling g / 64; all are powers of two and are undone exactly in the epilogue.
-// CTA = warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 "softmax" warps (two threads per own row, 32 score columns
-// each).  TMEM (512 columns, one CTA per SM): sc x 2 | dp x 2 (double-buffered: the score MMAs of tile j+1 run while the
-// warps work on tile j) | D hi, lo | P hi, lo | out1 | out2.  The DQ role first sweeps the other tiles once for the row
-// statistics (log-sum-exp in the log2 domain and delta; written to the workspace for the DKV role), then a second time
-// for dQ.
+// CTA = warp 0 TMA producer, warp 1 MMA issuer, warps 2.. "softmax" warps (NP threads per own row).
+// ALL MMAs ARE OF THE TS FORM (A operand from TMEM): tools/micro/umma_rate.cu measures 75 cycles for an SS MMA of
+// 128 x 64 x 16 (the 4 KB A tile is fetched from shared memory in ~43 cycles that do not overlap the MMA) against 42 for
+// the TS form, so the own rows X, U are copied into TMEM once per CTA by the softmax threads (plain global loads +
+// tcgen05.st) and never pass through shared memory.  TMEM (512 columns, one CTA per SM): sc x 2 | dp x 2 (double-
+// buffered: the score MMAs of tile j+1 run while the warps work on tile j; a thread writes the D / P plane pairs of a
+// tile OVER ITS OWN score columns, so the planes are double-buffered too and no thread waits for another) | out1 | out2
+// | X hi, lo | U hi, lo.  The DQ role first sweeps the other tiles once for the row statistics (log-sum-exp in the log2
+// domain and delta; written to the workspace for the DKV role), then a second time for dQ.
 // TWO-LEVEL ACCUMULATION (as in lg_x3_attn.cu): the tensor core rounds its fp32 accumulator toward zero after every MMA,
 // so one accumulator over 2048 other rows (384 MMAs) is ~1e-5 low on same-sign sums (measured against float64:
 // tools/attn_bwd_accuracy.py, profiles/r2_attn_bwd_tcgen05.txt).  out1 / out2 therefore collect XB_FLUSH tiles (48 MMAs)
@@ -28,25 +32,29 @@
 #include "lg_tc_common.cuh"
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <type_traits>
 
 namespace {
 
 constexpr int XB_OT = 64;                       // other rows per tile
-constexpr int XB_TBO = 128 * 64 * 2;            // one plane of an own tile (128 x 64 fp16, 128-byte swizzle): 16 KB
-constexpr int XB_TBY = XB_OT * 64 * 2;          // one plane of an other tile: 8 KB
-constexpr int XB_NST = 3;                       // stages of (Yh | Yl | Wh | Wl)
-constexpr int XB_X = 0;                         // Xh | Xl
-constexpr int XB_U = 2 * XB_TBO;                // Uh | Ul
-constexpr int XB_Y = 4 * XB_TBO;                // XB_NST x 32 KB
-constexpr int XB_BAR = XB_Y + XB_NST * 4 * XB_TBY;  // 160 KB of tiles
+constexpr int XB_TBY = XB_OT * 64 * 2;          // one plane of an other tile (64 x 64 fp16, 128-byte swizzle): 8 KB
+constexpr int XB_NST = 4;                       // stages of (Yh | Yl | Wh | Wl)
+constexpr int XB_Y = 0;                         // XB_NST x 32 KB
+constexpr int XB_BAR = XB_Y + XB_NST * 4 * XB_TBY;  // 128 KB of tiles
 constexpr int XB_NBAR = 1 + 2 * XB_NST + 2 + 2 + 1 + 1;
 constexpr int XB_ACC = XB_BAR + 256;            // [128 columns][128 rows] fp32 running sums of out1 | out2 (64 KB)
-constexpr int XB_XCH = XB_ACC;                  // [128 rows][2 parts] float4 (max, sum, partial delta): statistics sweep only
+constexpr int XB_XCH = XB_ACC;                  // [128 rows][NP parts] float4 (max, sum, partial delta): statistics sweep only
 constexpr int XB_SMEM = XB_ACC + 128 * 128 * 4;
 constexpr int XB_FLUSH = 4;                     // tiles per TMEM accumulator before it is folded into the running sums
 static_assert(XB_SMEM <= 227 * 1024, "attention backward: shared memory");
-constexpr uint32_t XT_SC = 0, XT_DP = 128, XT_DH = 256, XT_DL = 288, XT_PH = 320, XT_PL = 352, XT_O1 = 384, XT_O2 = 448;
+// TMEM: sc x 2 | dp x 2 (the D / P plane pairs are written over the scores they were computed from) | out1 | out2 |
+// own rows as A operands: X hi, X lo, U hi, U lo
+constexpr uint32_t XT_SC = 0, XT_DP = 128, XT_O1 = 256, XT_O2 = 320, XT_XH = 384, XT_XL = 416, XT_UH = 448, XT_UL = 480;
 constexpr float XB_DC = 1.f / 64.f;             // D planes hold (g / 64) D
+// The exponentials are taken against lse - 8, i.e. they ARE the P plane values 256 P (LG_X3_EP); the workspace holds
+// lse2 - 8 and delta * g * XB_DT so that D = (256 P) * (dp * XB_DPS - delta') needs no further scaling (powers of two).
+constexpr float XB_DT = XB_DC / LG_X3_EP;       // delta' = delta * g * XB_DT
+constexpr float XB_DPS = XB_DT / LG_X3_EA;      // dp arrives as g * 64 * dP
 constexpr float XB_LN2 = 0.69314718055994530942f;
 
 __host__ __device__ constexpr uint32_t xb_idesc(int M, int N, int b_mn_major) {  // kind::f16, fp16 x fp16 -> fp32
@@ -56,6 +64,19 @@ __device__ __forceinline__ float xb_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// (a, b) -> fp16 pair (a in the low half), saturating at +-65504 instead of overflowing to inf
+__device__ __forceinline__ uint32_t xb_pack_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// the same split with saturating conversions: a value beyond the fp16 range (possible only for activations far outside
+// the |x| < 1023 contract of the x3 planes) yields finite garbage, not inf - inf = NaN
+__device__ __forceinline__ void xb_split_sat(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = xb_pack_sat(a, b);
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  lo = xb_pack_sat(a - hf.x, b - hf.y);
 }
 // (a, b) -> fp16 pair hi and the fp16 pair of the remainders
 __device__ __forceinline__ void xb_split(float a, float b, uint32_t& hi, uint32_t& lo) {
@@ -125,7 +146,7 @@ __global__ void __launch_bounds__(256) xb_split_kernel(const float* __restrict__
 // NP = softmax threads per own row: 2 (8 warps, 32 score columns each) or 4 (16 warps, 16 columns each)
 template <bool DKV, int NP>
 __global__ void __launch_bounds__(64 + 128 * NP, 1)
-x3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmU,
+x3_attn_bwd_kernel(const __half* __restrict__ Xp, const __half* __restrict__ Up, size_t plane,
                    const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmW, int Lp,
                    const int32_t* __restrict__ lens, int kv_xor, const float* __restrict__ ctx,
                    const float* __restrict__ dctx, const float* __restrict__ gptr, float* __restrict__ lse2,
@@ -138,26 +159,26 @@ x3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   const int n_tiles = (n_oth + XB_OT - 1) / XB_OT;
   const int first_main = DKV ? 0 : n_tiles;  // DQ: iterations [0, n_tiles) are the statistics sweep
   const int n_iter = first_main + n_tiles;
+  constexpr int COLS = XB_OT / NP, OC = 64 / NP;  // score / output columns per softmax thread
+  constexpr int KP = COLS / 16;                   // K steps (16 other rows) inside one thread's score columns
 
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((tc::smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + XB_BAR);
-  uint64_t* own_full = bars;
+  uint64_t* xu_ready = bars;
   uint64_t* y_full = bars + 1;
   uint64_t* y_empty = y_full + XB_NST;
   uint64_t* sc_full = y_empty + XB_NST;  // [2]
-  uint64_t* sc_free = sc_full + 2;       // [2]
+  uint64_t* sc_free = sc_full + 2;       // [2] statistics sweep only
   uint64_t* pd_ready = sc_free + 2;
-  uint64_t* out_done = pd_ready + 1;
+  uint64_t* out_done = pd_ready + 1;     // one phase per flush group
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + XB_NBAR);
   float4* xch = reinterpret_cast<float4*>(smem + XB_XCH);
 
   if (warp == 0 && lane == 0) {
-    tc::prefetch_tmap(&tmX);
-    tc::prefetch_tmap(&tmU);
     tc::prefetch_tmap(&tmY);
     tc::prefetch_tmap(&tmW);
-    tc::mbar_init(own_full, 1);
+    tc::mbar_init(xu_ready, 4 * NP);
     for (int i = 0; i < XB_NST; ++i) { tc::mbar_init(&y_full[i], 1); tc::mbar_init(&y_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&sc_full[i], 1); tc::mbar_init(&sc_free[i], 4 * NP); }
     tc::mbar_init(pd_ready, 4 * NP);
@@ -173,40 +194,38 @@ x3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   if (warp == 0) {
     // ------------------------------------------------------------------------------------------- TMA producer
     if (lane == 0) {
-      const int own_row = (s * LG_HEADS + h) * Lp + r0;
       const int oth_row = (so * LG_HEADS + h) * Lp;
-      tc::mbar_arrive_expect_tx(own_full, 4 * XB_TBO);
-#pragma unroll
-      for (int pl = 0; pl < 2; ++pl)
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          tc::tma_load_3d(smem + XB_X + pl * XB_TBO + hf * XB_TBY, &tmX, own_full, 0, own_row + hf * 64, pl);
-          tc::tma_load_3d(smem + XB_U + pl * XB_TBO + hf * XB_TBY, &tmU, own_full, 0, own_row + hf * 64, pl);
-        }
       for (int it = 0; it < n_iter; ++it) {
         const int j = it < first_main ? it : it - first_main, st = it % XB_NST;
-        tc::mbar_wait(&y_empty[st], ((it / XB_NST) & 1) ^ 1);
+        tc::mbar_wait_relaxed(&y_empty[st], ((it / XB_NST) & 1) ^ 1);  // (sleeping polls: the issue slots belong to the softmax warps)
         uint8_t* dst = smem + XB_Y + st * 4 * XB_TBY;
-        tc::mbar_arrive_expect_tx(&y_full[st], 4 * XB_TBY);
+        const bool main = it >= first_main;
+        tc::mbar_arrive_expect_tx(&y_full[st], (main ? 4 : 2) * XB_TBY);
         tc::tma_load_3d(dst, &tmY, &y_full[st], 0, oth_row + j * XB_OT, 0);
         tc::tma_load_3d(dst + XB_TBY, &tmY, &y_full[st], 0, oth_row + j * XB_OT, 1);
-        tc::tma_load_3d(dst + 2 * XB_TBY, &tmW, &y_full[st], 0, oth_row + j * XB_OT, 0);
-        tc::tma_load_3d(dst + 3 * XB_TBY, &tmW, &y_full[st], 0, oth_row + j * XB_OT, 1);
+        if (main) {
+          tc::tma_load_3d(dst + 2 * XB_TBY, &tmW, &y_full[st], 0, oth_row + j * XB_OT, 0);
+          tc::tma_load_3d(dst + 3 * XB_TBY, &tmW, &y_full[st], 0, oth_row + j * XB_OT, 1);
+        }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------------------- MMA issuer
     constexpr uint32_t idesc_sc = xb_idesc(128, XB_OT, 0);
     constexpr uint32_t idesc_out = xb_idesc(128, 64, 1);
-    const uint64_t dXh = tc::smem_desc_sw128(tc::smem_u32(smem + XB_X), 0, 1024);
-    const uint64_t dXl = tc::smem_desc_sw128(tc::smem_u32(smem + XB_X + XB_TBO), 0, 1024);
-    const uint64_t dUh = tc::smem_desc_sw128(tc::smem_u32(smem + XB_U), 0, 1024);
-    const uint64_t dUl = tc::smem_desc_sw128(tc::smem_u32(smem + XB_U + XB_TBO), 0, 1024);
-    auto issue_sc = [&](int it) {  // sc[it & 1] = X . Y^T and (main sweep) dp[it & 1] = U . W^T
+    const uint32_t tXh = tmem + XT_XH, tXl = tmem + XT_XL, tUh = tmem + XT_UH, tUl = tmem + XT_UL;
+    // TMEM address of the A operand of K step ks in a plane pair that a softmax thread wrote over ITS score columns:
+    // [part][hi: KP steps x 8 columns | lo: KP steps x 8 columns]
+    auto plane_col = [](int lo, int ks) -> uint32_t { return (uint32_t)((ks / KP) * COLS + lo * (COLS / 2) + (ks % KP) * 8); };
+    auto issue_sc = [&](int it) {  // sc[it & 1] = X . Y^T and (main sweep) dp[it & 1] = U . W^T, A operands from TMEM
       const int st = it % XB_NST, b = it & 1;
       const bool main = it >= first_main;
-      tc::mbar_wait(&y_full[st], (it / XB_NST) & 1);
-      tc::mbar_wait(&sc_free[b], ((it >> 1) & 1) ^ 1);  // the warps have read iteration it-2 out of this buffer
+      tc::mbar_wait_relaxed(&y_full[st], (it / XB_NST) & 1, 32);
+      // The buffer's previous user is iteration it - 2.  Statistics sweep: the warps arrive on sc_free once they hold
+      // the scores.  Main sweep: the warps were done with it before their pd_ready arrive, which this warp observed
+      // before it issued out(it - 2); those MMAs (reading the planes in the buffer) precede the ones below in this
+      // thread's MMA stream, which executes in order.
+      if (it - 2 < first_main) tc::mbar_wait_relaxed(&sc_free[b], ((it >> 1) & 1) ^ 1, 32);
       tc::fence_after_sync();
       const uint32_t ybase = tc::smem_u32(smem + XB_Y + st * 4 * XB_TBY);
       const uint64_t dYh = tc::smem_desc_sw128(ybase, 0, 1024), dYl = tc::smem_desc_sw128(ybase + XB_TBY, 0, 1024);
@@ -215,16 +234,16 @@ x3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       if (tc::elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          tc::umma_ss(tS, dXl + 2 * k, dYh + 2 * k, idesc_sc, k != 0);
-          tc::umma_ss(tS, dXh + 2 * k, dYl + 2 * k, idesc_sc, 1);
-          tc::umma_ss(tS, dXh + 2 * k, dYh + 2 * k, idesc_sc, 1);
+          tc::umma_ts(tS, tXl + k * 8, dYh + 2 * k, idesc_sc, k != 0);
+          tc::umma_ts(tS, tXh + k * 8, dYl + 2 * k, idesc_sc, 1);
+          tc::umma_ts(tS, tXh + k * 8, dYh + 2 * k, idesc_sc, 1);
         }
         if (main) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            tc::umma_ss(tP, dUl + 2 * k, dWh + 2 * k, idesc_sc, k != 0);
-            tc::umma_ss(tP, dUh + 2 * k, dWl + 2 * k, idesc_sc, 1);
-            tc::umma_ss(tP, dUh + 2 * k, dWh + 2 * k, idesc_sc, 1);
+            tc::umma_ts(tP, tUl + k * 8, dWh + 2 * k, idesc_sc, k != 0);
+            tc::umma_ts(tP, tUh + k * 8, dWl + 2 * k, idesc_sc, 1);
+            tc::umma_ts(tP, tUh + k * 8, dWh + 2 * k, idesc_sc, 1);
           }
         }
         tc::umma_commit(&sc_full[b]);
@@ -232,33 +251,35 @@ x3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       }
       __syncwarp();
     };
-    tc::mbar_wait(own_full, 0);
+    tc::mbar_wait(xu_ready, 0);
+    tc::fence_after_sync();
     issue_sc(0);
     for (int it = 0; it < n_iter; ++it) {
       if (it + 1 < n_iter) issue_sc(it + 1);
       if (it < first_main) continue;
-      const int jm = it - first_main, st = it % XB_NST;
-      tc::mbar_wait(pd_ready, jm & 1);
+      const int jm = it - first_main, st = it % XB_NST, b = it & 1;
+      tc::mbar_wait_relaxed(pd_ready, jm & 1, 32);
       tc::fence_after_sync();
       const uint32_t ybase = tc::smem_u32(smem + XB_Y + st * 4 * XB_TBY);
       // MN-major B operands: row = other row (the K index of these MMAs), 16 rows = 2048 B per K step
       const uint64_t mYh = tc::smem_desc_sw128(ybase, XB_TBY, 1024), mYl = tc::smem_desc_sw128(ybase + XB_TBY, XB_TBY, 1024);
       const uint64_t mWh = tc::smem_desc_sw128(ybase + 2 * XB_TBY, XB_TBY, 1024), mWl = tc::smem_desc_sw128(ybase + 3 * XB_TBY, XB_TBY, 1024);
+      const uint32_t tD = tmem + XT_DP + b * XB_OT, tPp = tmem + XT_SC + b * XB_OT;  // D planes over dp, P planes over sc
       if (tc::elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint32_t acc = ((jm % XB_FLUSH) | k) != 0;  // fresh accumulators after every flush
-          tc::umma_ts(tmem + XT_O1, tmem + XT_DL + k * 8, mYh + k * (2048 >> 4), idesc_out, acc);
-          tc::umma_ts(tmem + XT_O1, tmem + XT_DH + k * 8, mYl + k * (2048 >> 4), idesc_out, 1);
-          tc::umma_ts(tmem + XT_O1, tmem + XT_DH + k * 8, mYh + k * (2048 >> 4), idesc_out, 1);
+          tc::umma_ts(tmem + XT_O1, tD + plane_col(1, k), mYh + k * (2048 >> 4), idesc_out, acc);
+          tc::umma_ts(tmem + XT_O1, tD + plane_col(0, k), mYl + k * (2048 >> 4), idesc_out, 1);
+          tc::umma_ts(tmem + XT_O1, tD + plane_col(0, k), mYh + k * (2048 >> 4), idesc_out, 1);
           if (DKV) {
-            tc::umma_ts(tmem + XT_O2, tmem + XT_PL + k * 8, mWh + k * (2048 >> 4), idesc_out, acc);
-            tc::umma_ts(tmem + XT_O2, tmem + XT_PH + k * 8, mWl + k * (2048 >> 4), idesc_out, 1);
-            tc::umma_ts(tmem + XT_O2, tmem + XT_PH + k * 8, mWh + k * (2048 >> 4), idesc_out, 1);
+            tc::umma_ts(tmem + XT_O2, tPp + plane_col(1, k), mWh + k * (2048 >> 4), idesc_out, acc);
+            tc::umma_ts(tmem + XT_O2, tPp + plane_col(0, k), mWl + k * (2048 >> 4), idesc_out, 1);
+            tc::umma_ts(tmem + XT_O2, tPp + plane_col(0, k), mWh + k * (2048 >> 4), idesc_out, 1);
           }
         }
         tc::umma_commit(&y_empty[st]);
-        tc::umma_commit(out_done);
+        if (jm % XB_FLUSH == XB_FLUSH - 1 || jm == n_tiles - 1) tc::umma_commit(out_done);
       }
       __syncwarp();
     }
@@ -267,7 +288,6 @@ x3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     const int quarter = warp & 3;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const int part = (warp - 2) >> 2;  // which COLS columns of every score tile / OC columns of the outputs
-    constexpr int COLS = XB_OT / NP, OC = 64 / NP;
     auto ld_cols = [&](uint32_t col, uint32_t* dst) {  // COLS (= OC) consecutive TMEM columns of this thread's lane
       if constexpr (COLS == 32) tc::tmem_ld32(tmem + lane_base + col, dst);
       else tc::tmem_ld16(tmem + lane_base + col, dst);
@@ -283,6 +303,31 @@ x3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     const size_t own_stat = ((size_t)s * LG_HEADS + h) * Lp + r0 + r;
     const size_t oth_stat = ((size_t)so * LG_HEADS + h) * Lp;
     float lse_own = 0.f, dlt_own = 0.f;  // DQ: this row's log-sum-exp and g * delta
+
+    // ---- own rows into TMEM: the A operand of every score MMA (rows >= n_own are zero planes).  This thread copies
+    // words [part * 32 / NP, ...) of its row of X hi, X lo, U hi, U lo (a word = two fp16 = one TMEM column)
+    {
+      constexpr int NW = 32 / NP;
+      const __half* srcs[4] = {Xp + own_stat * LG_DH, Xp + plane + own_stat * LG_DH, Up + own_stat * LG_DH,
+                               Up + plane + own_stat * LG_DH};
+      const uint32_t cols[4] = {XT_XH, XT_XL, XT_UH, XT_UL};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t w[NW];
+        const uint4* src = reinterpret_cast<const uint4*>(srcs[q]) + part * (NW / 4);
+#pragma unroll
+        for (int i = 0; i < NW / 4; ++i) {
+          const uint4 v = src[i];
+          w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        }
+        if constexpr (NW == 16) tc::tmem_st16(tmem + lane_base + cols[q] + part * NW, w);
+        else tc::tmem_st8(tmem + lane_base + cols[q] + part * NW, w);
+      }
+      tc::tmem_st_wait();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(xu_ready);
+    }
 
     if (!DKV) {
       // ---- statistics sweep: every thread keeps the online (max, sum) of ITS columns; partial states merge
@@ -339,11 +384,11 @@ x3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         lsum += pt[i].y * xb_ex2(pt[i].x - msafe);
         delta += pt[i].z;
       }
-      lse_own = lsum > 0.f ? mnew + log2f(lsum) : INFINITY;
-      dlt_own = delta * g;
+      lse_own = lsum > 0.f ? mnew + log2f(lsum) - 8.f : INFINITY;  // (2^(s - lse_own) = 256 P)
+      dlt_own = delta * g * XB_DT;
       if (part == 0 && row_ok) {
         lse2[own_stat] = lse_own;
-        dlt[own_stat] = delta;
+        dlt[own_stat] = dlt_own;
       }
     }
 
@@ -373,64 +418,76 @@ x3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     for (int it = first_main; it < n_iter; ++it) {
       const int jm = it - first_main, b = it & 1;
       const int n0 = jm * XB_OT + part * COLS;  // first other row of this thread's columns
+      // DKV: per-column statistics of the queries (uniform over the warp: broadcast loads), fetched BEFORE the wait for
+      // the score MMAs -- issued at their first use, the ~700-cycle L2 round trip sat on the critical path of every tile
+      // (21 % of the role's stall samples, profiles/r2_attn_bwd_tcgen05.txt)
+      float4 lq4[DKV ? COLS / 4 : 1], dq4[DKV ? COLS / 4 : 1];
+      if (DKV) {
+#pragma unroll
+        for (int i4 = 0; i4 < COLS / 4; ++i4) {
+          lq4[i4] = *reinterpret_cast<const float4*>(lse2 + oth_stat + n0 + 4 * i4);
+          dq4[i4] = *reinterpret_cast<const float4*>(dlt + oth_stat + n0 + 4 * i4);
+        }
+      }
       tc::mbar_wait(&sc_full[b], (it >> 1) & 1);
       tc::fence_after_sync();
       uint32_t sv[COLS], dv[COLS];
       ld_cols(XT_SC + b * XB_OT + part * COLS, sv);
       ld_cols(XT_DP + b * XB_OT + part * COLS, dv);
       tc::tmem_ld_wait();
-      tc::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&sc_free[b]);
       uint32_t dh[COLS / 2], dl[COLS / 2], ph[COLS / 2], pl[COLS / 2];
+      auto planes = [&](auto full_tile) {  // full_tile: every column of this thread is a valid other row (no masks)
+        constexpr bool FULL = decltype(full_tile)::value;
 #pragma unroll
-      for (int i4 = 0; i4 < COLS / 4; ++i4) {
-        float lq[4], dq[4];
-        if (DKV) {  // per-column statistics of the queries (uniform over the warp: broadcast loads)
-          const float4 l4 = *reinterpret_cast<const float4*>(lse2 + oth_stat + n0 + 4 * i4);
-          const float4 d4 = *reinterpret_cast<const float4*>(dlt + oth_stat + n0 + 4 * i4);
-          lq[0] = l4.x; lq[1] = l4.y; lq[2] = l4.z; lq[3] = l4.w;
-          dq[0] = d4.x * g; dq[1] = d4.y * g; dq[2] = d4.z * g; dq[3] = d4.w * g;
-        } else {
+        for (int i4 = 0; i4 < COLS / 4; ++i4) {
+          float lq[4], dq[4];
+          if (DKV) {
+            const float4 l4 = lq4[i4], d4 = dq4[i4];
+            lq[0] = l4.x; lq[1] = l4.y; lq[2] = l4.z; lq[3] = l4.w;
+            dq[0] = d4.x; dq[1] = d4.y; dq[2] = d4.z; dq[3] = d4.w;
+          } else {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) { lq[c] = lse_own; dq[c] = dlt_own; }
-        }
-        float p[4], d[4];
+            for (int c = 0; c < 4; ++c) { lq[c] = lse_own; dq[c] = dlt_own; }
+          }
+          float p[4], d[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int i = 4 * i4 + c;
-          const bool ok = n0 + i < n_oth;
-          p[c] = ok ? xb_ex2(fmaf(__uint_as_float(sv[i]), s_us, -lq[c])) : 0.f;
-          // dp arrives as g * 64 * dP; D plane value = (g / 64) * P * (dP - delta), kept inside fp16
-          const float t = ok ? fmaf(__uint_as_float(dv[i]), 1.f / LG_X3_EA, -dq[c]) : 0.f;
-          d[c] = fminf(fmaxf(p[c] * t * XB_DC, -60000.f), 60000.f);
+          for (int c = 0; c < 4; ++c) {
+            const int i = 4 * i4 + c;
+            const bool ok = FULL || n0 + i < n_oth;  // (statistics of padding rows are undefined: select, not multiply)
+            p[c] = ok ? xb_ex2(fmaf(__uint_as_float(sv[i]), s_us, -lq[c])) : 0.f;            // 256 P
+            d[c] = ok ? p[c] * fmaf(__uint_as_float(dv[i]), XB_DPS, -dq[c]) : 0.f;           // (g / 64) P (dP - delta)
+          }
+          xb_split_sat(d[0], d[1], dh[2 * i4], dl[2 * i4]);
+          xb_split_sat(d[2], d[3], dh[2 * i4 + 1], dl[2 * i4 + 1]);
+          if (DKV) {
+            xb_split(p[0], p[1], ph[2 * i4], pl[2 * i4]);
+            xb_split(p[2], p[3], ph[2 * i4 + 1], pl[2 * i4 + 1]);
+          }
         }
-        xb_split(d[0], d[1], dh[2 * i4], dl[2 * i4]);
-        xb_split(d[2], d[3], dh[2 * i4 + 1], dl[2 * i4 + 1]);
-        if (DKV) {
-          xb_split(p[0] * LG_X3_EP, p[1] * LG_X3_EP, ph[2 * i4], pl[2 * i4]);
-          xb_split(p[2] * LG_X3_EP, p[3] * LG_X3_EP, ph[2 * i4 + 1], pl[2 * i4 + 1]);
-        }
-      }
-      if (jm > 0) {
-        tc::mbar_wait(out_done, (jm - 1) & 1);  // the MMAs that read the previous planes have retired
+      };
+      if (n0 + COLS <= n_oth) planes(std::true_type{});
+      else planes(std::false_type{});
+      if (jm > 0 && jm % XB_FLUSH == 0) {
+        // the group's MMAs have retired; the issuer starts fresh accumulators with tile jm only after this warp's
+        // pd_ready arrive below
+        tc::mbar_wait(out_done, (jm / XB_FLUSH - 1) & 1);
         tc::fence_after_sync();
-        // the issuer starts fresh accumulators with tile jm only after this warp's pd_ready arrive below
-        if (jm % XB_FLUSH == 0) flush();
+        flush();
       }
-      st_plane(XT_DH + part * (COLS / 2), dh);
-      st_plane(XT_DL + part * (COLS / 2), dl);
+      // the plane pairs go over this thread's OWN score columns (hi | lo), read above: no other thread touches them
+      st_plane(XT_DP + b * XB_OT + part * COLS, dh);
+      st_plane(XT_DP + b * XB_OT + part * COLS + COLS / 2, dl);
       if (DKV) {
-        st_plane(XT_PH + part * (COLS / 2), ph);
-        st_plane(XT_PL + part * (COLS / 2), pl);
+        st_plane(XT_SC + b * XB_OT + part * COLS, ph);
+        st_plane(XT_SC + b * XB_OT + part * COLS + COLS / 2, pl);
       }
       tc::tmem_st_wait();
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(pd_ready);
     }
-    // ---- epilogue: this thread's 32 output columns of its row
-    tc::mbar_wait(out_done, (n_tiles - 1) & 1);
+    // ---- epilogue: this thread's OC output columns of its row
+    tc::mbar_wait(out_done, ((n_tiles + XB_FLUSH - 1) / XB_FLUSH - 1) & 1);
     tc::fence_after_sync();
     flush();
     if (row_ok) {
@@ -509,18 +566,18 @@ int lg_x3_attention_bwd(const float* Q, const float* K, const float* V, const fl
   // softmax threads per own row, per role (LGB200_X3_BWD_NP = "<dq><dkv>", e.g. 24)
   static const int np_cfg = getenv("LGB200_X3_BWD_NP") ? atoi(getenv("LGB200_X3_BWD_NP")) : 44;
   const dim3 grid(Lp / 128, LG_HEADS, S);
-  auto launch = [&](auto kern, int np, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const CUtensorMap& d,
+  auto launch = [&](auto kern, int np, const __half* xp, const __half* up, const CUtensorMap& ty, const CUtensorMap& tw,
                     float* o1, float* o2) -> int {
     cudaError_t le = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, XB_SMEM);
     if (le != cudaSuccess) return (int)le;
-    kern<<<grid, 64 + 128 * np, XB_SMEM, st>>>(a, b, c, d, Lp, lens, kv_xor, ctx, dctx, g, lse2, dlt, o1, o2);
+    kern<<<grid, 64 + 128 * np, XB_SMEM, st>>>(xp, up, n_el, ty, tw, Lp, lens, kv_xor, ctx, dctx, g, lse2, dlt, o1, o2);
     LG_LAUNCH_CHECK();
     return LGB200_OK;
   };
-  if (np_cfg / 10 == 2) rc = launch(x3_attn_bwd_kernel<false, 2>, 2, tq, tg, tk, tv, dQ, nullptr);
-  else rc = launch(x3_attn_bwd_kernel<false, 4>, 4, tq, tg, tk, tv, dQ, nullptr);
+  if (np_cfg / 10 == 2) rc = launch(x3_attn_bwd_kernel<false, 2>, 2, Qp, Gp, tk, tv, dQ, nullptr);
+  else rc = launch(x3_attn_bwd_kernel<false, 4>, 4, Qp, Gp, tk, tv, dQ, nullptr);
   if (rc) return rc;
-  if (np_cfg % 10 == 2) rc = launch(x3_attn_bwd_kernel<true, 2>, 2, tk, tv, tq, tg, dK, dV);
-  else rc = launch(x3_attn_bwd_kernel<true, 4>, 4, tk, tv, tq, tg, dK, dV);
+  if (np_cfg % 10 == 2) rc = launch(x3_attn_bwd_kernel<true, 2>, 2, Kp, Vp, tq, tg, dK, dV);
+  else rc = launch(x3_attn_bwd_kernel<true, 4>, 4, Kp, Vp, tq, tg, dK, dV);
   return rc;
 }

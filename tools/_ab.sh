@@ -1,2 +1,3 @@
 cd /root/repo
-timeout 60 tools/micro/umma_rate 2>&1 | tee gpurun_out/umma_rate.log
+timeout 600 python -m pytest tests/test_gpu_grad.py -q -x -k "attention_bwd" > gpurun_out/gputest_bwd.log 2>&1; tail -3 gpurun_out/gputest_bwd.log | cut -c1-300
+for cfg in 22 44 24 42; do echo "np=$cfg"; LGB200_X3_BWD_NP=$cfg timeout 120 python tools/attn_bwd_bench.py 16 2048 10 2>&1 | grep -v Warn | tail -1; done | tee gpurun_out/attn_bwd_np_ab.log

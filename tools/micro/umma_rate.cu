@@ -11,7 +11,7 @@
 #include <cuda.h>
 #include "lg_tc_common.cuh"
 
-__global__ void __launch_bounds__(128) k(int N, int ts, int iters, int smem_bytes_dummy, long long* cyc) {
+__global__ void __launch_bounds__(128) k(int N, int ts, int iters, int bmn, long long* cyc) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t slot;
@@ -29,9 +29,10 @@ __global__ void __launch_bounds__(128) k(int N, int ts, int iters, int smem_byte
   tc::fence_after_sync();
   const uint32_t tmem = slot;
   if (warp == 0) {
-    const uint32_t idesc = tc::idesc_bf16(128, N, 0);
+    const uint32_t idesc = tc::idesc_bf16(128, N, bmn);
     const uint64_t dA = tc::smem_desc_sw128(tc::smem_u32(smem), 0, 1024);
-    const uint64_t dB = tc::smem_desc_sw128(tc::smem_u32(smem + 32768), 0, 1024);
+    // bmn: B is MN-major (row = K index, 64 N-elements per 128-byte row; N = 64 only): K step = 16 rows = 2048 B
+    const uint64_t dB = tc::smem_desc_sw128(tc::smem_u32(smem + 32768), bmn ? 8192 : 0, 1024);
     // accumulator at column 0 (N <= 256 columns would need 256: use N <= 128 for 2 CTAs/SM + TS), A planes at column 192
     const uint32_t tD = tmem, tA = tmem + 192;
     __syncwarp();
@@ -41,7 +42,7 @@ __global__ void __launch_bounds__(128) k(int N, int ts, int iters, int smem_byte
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
           const uint64_t a = dA + (uint64_t)((ks >> 2) * (16384 >> 4) + (ks & 3) * 2);
-          const uint64_t b = dB + (uint64_t)((ks >> 2) * ((N * 128) >> 4) + (ks & 3) * 2);
+          const uint64_t b = bmn ? dB + (uint64_t)(ks * (2048 >> 4)) : dB + (uint64_t)((ks >> 2) * ((N * 128) >> 4) + (ks & 3) * 2);
           if (ts) tc::umma_ts(tD, tA + ks * 8, b, idesc, (it | ks) != 0);
           else tc::umma_ss(tD, a, b, idesc, (it | ks) != 0);
         }
@@ -91,5 +92,14 @@ int main() {
         printf("%s M=128 N=%3d K=16, %d CTA/SM: %6.1f cycles per MMA per CTA (ideal at 8192 FLOP/clk/SM: %5.1f%s), operand bytes from smem per MMA %5d\n",
                ts ? "TS" : "SS", N, ctas, per, ideal, ctas == 2 ? " x2 when both CTAs issue" : "", (ts ? 0 : 128 * 32) + N * 32);
       }
+  for (int ts = 0; ts <= 1; ++ts) {  // MN-major B (the P.V / dS.K form), N = 64, one CTA per SM
+    for (int rep = 0; rep < 2; ++rep) k<<<148, 128, 32768 + 65536 + 65536 - 1024, 0>>>(64, ts, iters, 1, cyc);
+    if (cudaDeviceSynchronize() != cudaSuccess) { printf("error\n"); return 1; }
+    long long h[148];
+    cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    double avg = 0;
+    for (int i = 0; i < 148; ++i) avg += (double)h[i];
+    printf("%s M=128 N= 64 K=16, B MN-major, 1 CTA/SM: %6.1f cycles per MMA (ideal 32.0)\n", ts ? "TS" : "SS", avg / 148 / (iters * 8.0));
+  }
   return 0;
 }
