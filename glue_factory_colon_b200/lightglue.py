@@ -592,7 +592,8 @@ class LightGlue(nn.Module):
         L = conf.n_layers
         with torch.no_grad():
             keep: Dict = {}
-            self._log_assignment_of(lib, F32, r0[:, -1], r1[:, -1], L - 1, None, keep=keep)
+            # (fp32-accurate tensor-core kernels, as the rest of the training forward; CUDA cores with LGB200_TRAIN_SIMT_LINEAR=1)
+            self._log_assignment_of(lib, F32 if _train._SIMT_LINEAR else F32X3, r0[:, -1], r1[:, -1], L - 1, None, keep=keep)
             scores = keep["scores"]
             m0 = torch.empty(B, m, device=dev, dtype=torch.int64)
             m1 = torch.empty(B, n, device=dev, dtype=torch.int64)
