@@ -43,7 +43,10 @@ __global__ void __launch_bounds__(128) k(int N, int ts, int iters, int bmn, long
         for (int ks = 0; ks < 8; ++ks) {
           const uint64_t a = dA + (uint64_t)((ks >> 2) * (16384 >> 4) + (ks & 3) * 2);
           const uint64_t b = bmn ? dB + (uint64_t)(ks * (2048 >> 4)) : dB + (uint64_t)((ks >> 2) * ((N * 128) >> 4) + (ks & 3) * 2);
-          if (ts) tc::umma_ts(tD, tA + ks * 8, b, idesc, (it | ks) != 0);
+          if (ts == 2) {  // A slice copied smem -> TMEM by tcgen05.cp (128 rows x 32 bytes = one K step), then the TS MMA
+            asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tA + ks * 8), "l"(a) : "memory");
+            tc::umma_ts(tD, tA + ks * 8, b, idesc, (it | ks) != 0);
+          } else if (ts) tc::umma_ts(tD, tA + ks * 8, b, idesc, (it | ks) != 0);
           else tc::umma_ss(tD, a, b, idesc, (it | ks) != 0);
         }
       }
@@ -92,6 +95,15 @@ int main() {
         printf("%s M=128 N=%3d K=16, %d CTA/SM: %6.1f cycles per MMA per CTA (ideal at 8192 FLOP/clk/SM: %5.1f%s), operand bytes from smem per MMA %5d\n",
                ts ? "TS" : "SS", N, ctas, per, ideal, ctas == 2 ? " x2 when both CTAs issue" : "", (ts ? 0 : 128 * 32) + N * 32);
       }
+  for (int N : {64, 128}) {  // tcgen05.cp of the A slice + TS MMA: does the copy overlap the previous MMA?
+    for (int rep = 0; rep < 2; ++rep) k<<<148, 128, 32768 + 65536 + 65536 - 1024, 0>>>(N, 2, iters, 0, cyc);
+    if (cudaDeviceSynchronize() != cudaSuccess) { printf("error (cp)\n"); return 1; }
+    long long h[148];
+    cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    double avg = 0;
+    for (int i = 0; i < 148; ++i) avg += (double)h[i];
+    printf("cp+TS M=128 N=%3d K=16, 1 CTA/SM: %6.1f cycles per (tcgen05.cp 128x256b + MMA) (ideal %5.1f)\n", N, avg / 148 / (iters * 8.0), N / 2.0);
+  }
   for (int ts = 0; ts <= 1; ++ts) {  // MN-major B (the P.V / dS.K form), N = 64, one CTA per SM
     for (int rep = 0; rep < 2; ++rep) k<<<148, 128, 32768 + 65536 + 65536 - 1024, 0>>>(64, ts, iters, 1, cyc);
     if (cudaDeviceSynchronize() != cudaSuccess) { printf("error\n"); return 1; }
