@@ -10,7 +10,7 @@
 //
 //   P = 2^(sc - lse[query]),  D = P (dp - delta[query]),  delta = <dO, O>   (the query is the row in DQ, the column in DKV)
 //
-// Every product is three SS / TS MMAs on fp16 plane pairs (hi.hi + hi.lo + lo.hi, fp32 accumulation in TMEM): the
+// Every product is three MMAs on fp16 plane pairs (hi.hi + hi.lo + lo.hi, fp32 accumulation in TMEM): the
 // operands Q, K, V carry the activation scaling LG_X3_EA, dO a per-call power of two g chosen so that max |g dO| lies in
 // [256, 512) (gradients have no fixed range: a fixed scaling would push small ones into the fp16 subnormals), P the
 // scaling LG_X3_EP and D the scaling g / 64; all are powers of two and are undone exactly in the epilogue.
@@ -54,6 +54,7 @@ constexpr float XB_DC = 1.f / 64.f;             // D planes hold (g / 64) D
 // The exponentials are taken against lse - 8, i.e. they ARE the P plane values 256 P (LG_X3_EP); the workspace holds
 // lse2 - 8 and delta * g * XB_DT so that D = (256 P) * (dp * XB_DPS - delta') needs no further scaling (powers of two).
 constexpr float XB_DT = XB_DC / LG_X3_EP;       // delta' = delta * g * XB_DT
+static_assert(LG_X3_EP == 256.f, "the exponentials are taken against lse - 8 = lse - log2(LG_X3_EP)");
 constexpr float XB_DPS = XB_DT / LG_X3_EA;      // dp arrives as g * 64 * dP
 constexpr float XB_LN2 = 0.69314718055994530942f;
 
