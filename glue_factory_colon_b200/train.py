@@ -130,8 +130,9 @@ class _Kern:
         (the product of the inverse plane scalings; float or 0-dim device tensor)."""
         f32 = torch.float32
         r = torch.mm(A[1], B[0], out_dtype=f32)
-        r = torch.addmm(r, A[0], B[1], out_dtype=f32)  # (beta = 1: accumulated in the GEMM epilogue, no extra pass)
-        r = torch.addmm(r, A[0], B[0], out_dtype=f32)
+        # beta = 1: accumulated in the GEMM epilogue; out = r: in place (without it ATen copies r into a new output first)
+        torch.addmm(r, A[0], B[1], out_dtype=f32, out=r)
+        torch.addmm(r, A[0], B[0], out_dtype=f32, out=r)
         return r.mul_(scale)
 
     def attention(self, q, k, v, kv_xor, ctx):
@@ -506,8 +507,8 @@ class AssignFn(torch.autograd.Function):
 
             def bmm3(A, Bm):
                 o = torch.bmm(A[1], Bm[0], out_dtype=f32)
-                o = torch.baddbmm(o, A[0], Bm[1], out_dtype=f32)
-                o = torch.baddbmm(o, A[0], Bm[0], out_dtype=f32)
+                torch.baddbmm(o, A[0], Bm[1], out_dtype=f32, out=o)
+                torch.baddbmm(o, A[0], Bm[0], out_dtype=f32, out=o)
                 return o.mul_(inv[0] * AI)
 
             dmd0 = bmm3(sp, mp1)

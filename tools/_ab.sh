@@ -1,2 +1,3 @@
 cd /root/repo
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/bench_8gpu.json 2> gpurun_out/bench_8gpu.err; tail -c 900 gpurun_out/bench_8gpu.json
+timeout 900 python -m pytest tests/test_gpu_grad.py -q -x > gpurun_out/gputest_bwd.log 2>&1; tail -4 gpurun_out/gputest_bwd.log | cut -c1-400
+(timeout 600 python tools/train_bench.py 32 512 5; timeout 600 python tools/train_bench.py 8 2048 3) 2>&1 | grep -v Warn | grep '"impl"' | grep glue_factory | tee gpurun_out/train_tcbwd7.log | cut -c1-230
