@@ -1,6 +1,4 @@
 cd /root/repo
-timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/gputest_all.log 2>&1; tail -3 gpurun_out/gputest_all.log | cut -c1-300
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log | cut -c1-200
-timeout 600 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; python -c "
-import json; d = json.loads(open('gpurun_out/bench_final.json').read().strip().splitlines()[-1]); print(d['value'], d['e2e']['value'], d['roofline']['frac'], d['roofline']['whole_step']['frac'], d['gpu_launches'], d['clocks'])"
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; tail -c 300 gpurun_out/bench_reference.json
+timeout 600 python -m pytest tests/test_gpu_grad.py -q -x -k "attention_bwd" > gpurun_out/gputest_bwd.log 2>&1; tail -3 gpurun_out/gputest_bwd.log | cut -c1-300
+for cfg in 44 22 44; do echo "np=$cfg"; LGB200_X3_BWD_NP=$cfg timeout 120 python tools/attn_bwd_bench.py 16 2048 10 2>&1 | grep -v Warn | tail -1; done | tee gpurun_out/attn_bwd_np_ab.log
+timeout 200 python tools/attn_bwd_accuracy.py 1 8192 2>&1 | grep -v Warn
