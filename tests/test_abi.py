@@ -56,6 +56,14 @@ def test_argument_validation_without_gpu(libpath):
     assert lib.lgb200_attention(0, None, None, None, 2, 128, None, 0, None, None) == -2
     assert lib.lgb200_pack_rows(1, 1, 10, 255, 0, 128, 1, None, None) == -1
     assert lib.lgb200_filter_matches(None, 1, 5, 5, None, 0.0, None, None, 0, 4, 4, None, None, None, None, None, 0, None) == -2
+    # training-side helpers (ABI v6): workspace size of the attention backward, plane split / merge
+    n_ws = ctypes.c_longlong(0)
+    assert lib.lgb200_attention_bwd_workspace(4, 256, ctypes.byref(n_ws)) == 0
+    assert n_ws.value == 2 * 4 * 4 * 256 + 16 + 4 * 4 * 256 * 256  # statistics + scale slot + four fp16 plane pairs
+    assert lib.lgb200_attention_bwd_workspace(4, 200, ctypes.byref(n_ws)) == -1 and lib.lgb200_attention_bwd_workspace(4, 256, None) == -2
+    assert lib.lgb200_attention_bwd(None, None, None, None, None, 4, 256, None, 0, None, None, None, None, None) == -2
+    assert lib.lgb200_split_dynamic(None, 1024, None, None, 0, None, 0, None) == -2
+    assert lib.lgb200_merge_rows(None, 1024, 1.0, None, None) == -2
 
 
 def test_product_path_has_no_cpu_fallback():
