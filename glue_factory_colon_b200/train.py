@@ -45,7 +45,16 @@ _SIMT_ATTN = os.environ.get("LGB200_TRAIN_SIMT_ATTN", "0") == "1"
 _SIMT_LINEAR = os.environ.get("LGB200_TRAIN_SIMT_LINEAR", "0") == "1"
 # plain GEMMs of the backward pass: 1 = cuBLAS fp32 (sgemm on the CUDA cores), default = three fp16 tensor-core GEMMs on
 # split planes with fp32 accumulation (the same hi.hi + hi.lo + lo.hi scheme as the forward's lg_x3.cu kernels)
-_SGEMM = os.environ.get("LGB200_TRAIN_SGEMM", "0") == "1" or _SIMT_LINEAR
+def _has_mm_out_dtype() -> bool:
+    """torch.mm / addmm / bmm with out_dtype (fp16 operands, fp32 accumulation AND fp32 output) exist from PyTorch 2.8 on."""
+    try:
+        a = torch.empty(1, 1, device="meta", dtype=torch.float16)
+        return torch.mm(a, a, out_dtype=torch.float32).dtype == torch.float32
+    except (TypeError, RuntimeError, NotImplementedError):
+        return False
+
+
+_SGEMM = os.environ.get("LGB200_TRAIN_SGEMM", "0") == "1" or _SIMT_LINEAR or not _has_mm_out_dtype()
 _X3_WEIGHTS = ("qkv_w", "so_w", "sf0_w", "sf3_w", "cqv_w", "co_w", "cf0_w", "cf3_w")
 # packed Wqkv row r holds reference row _PERM[r] (lightglue.py:158: head*192 + d*3 + part -> part*256 + head*64 + d)
 _PERM = torch.arange(768).view(4, 64, 3).permute(2, 0, 1).reshape(-1)
