@@ -478,6 +478,28 @@ def test_assignment_fused_argmax_ties_and_nan():
 # ------------------------------------------------------------------ whole forward
 
 
+def assert_matches_equal_up_to_ties(got, ref, la_ref, thr, gap=2e-3):
+    """got / ref [B, m] match indices (-1 = unmatched), la_ref [B, m+1, n+1] the REFERENCE's log_assignment with the matched
+    side in the rows.  A row may differ only if the reference's decision was numerically open: two candidates within
+    `gap` of each other (arg-max ties, in the row or -- through the mutual check -- in the partner's column), or a
+    match score within `gap` of the filter threshold."""
+    B, m = ref.shape
+    inner = la_ref[:, :-1, :-1]
+    for b, i in (got != ref).nonzero().tolist():
+        g, r = int(got[b, i]), int(ref[b, i])
+        row = inner[b, i]
+        top2 = torch.topk(row, min(2, row.numel())).values
+        row_tie = top2.numel() == 2 and float(top2[0] - top2[1]) < gap
+        j = r if r >= 0 else g  # the candidate the two sides disagree about
+        col = inner[b, :, j]
+        ctop2 = torch.topk(col, min(2, col.numel())).values
+        col_tie = ctop2.numel() == 2 and float(ctop2[0] - ctop2[1]) < gap
+        at_thr = abs(float(inner[b, i, j].exp()) - thr) < gap
+        assert row_tie or col_tie or at_thr, (
+            f"pair {b} row {i}: got {g}, reference {r}; row gap {float(top2[0] - top2[-1]):.2e}, "
+            f"column gap {float(ctop2[0] - ctop2[-1]):.2e}, score {float(inner[b, i, j].exp()):.4f} vs threshold {thr}")
+
+
 @pytest.mark.parametrize("prec", ["fp32", "fp32_simt"])  # tensor-core fp32 mode (split fp16 x3) / CUDA-core fp32 kernels
 @pytest.mark.parametrize("name", ["basic", "nosize_sift", "prune"])
 def test_forward_fp32_against_reference_golden(name, prec, golden_dir):
@@ -489,9 +511,10 @@ def test_forward_fp32_against_reference_golden(name, prec, golden_dir):
     assert out["log_assignment"].shape == exp["log_assignment"].shape
     diff = (out["log_assignment"].cpu() - exp["log_assignment"]).abs().max()
     assert diff < 1e-3, f"max |dlog_assignment| vs reference = {diff:.2e}"
-    mism0 = (out["matches0"].cpu() != exp["matches0"]).sum()
-    mism1 = (out["matches1"].cpu() != exp["matches1"]).sum()
-    assert mism0 <= 2 and mism1 <= 2, (int(mism0), int(mism1))  # numerically tied rows only
+    # match indices: equal, except where the reference's own scores leave the decision numerically open (tie-gap rule)
+    thr = float(model.conf.filter_threshold)
+    assert_matches_equal_up_to_ties(out["matches0"].cpu(), exp["matches0"], exp["log_assignment"], thr)
+    assert_matches_equal_up_to_ties(out["matches1"].cpu(), exp["matches1"], exp["log_assignment"].transpose(1, 2), thr)
     assert out["matches0"].dtype == torch.int64 and out["prune0"].dtype == exp["prune0"].dtype
     assert torch.equal(out["prune0"].cpu(), exp["prune0"]) and torch.equal(out["prune1"].cpu(), exp["prune1"])
     torch.testing.assert_close(out["matching_scores0"].cpu(), exp["matching_scores0"], atol=2e-4, rtol=1e-2)
