@@ -6,8 +6,8 @@ Tolerances
               except where the oracle's own top-2 gap is < 1e-4 (numerically tied).
   bf16 mode : the reference's OWN bf16-autocast run deviates from its fp32 run by
               max 0.26 / mean 0.043 on log_assignment.  We
-              require mean |d| < 0.05 and max |d| < 0.5 on the valid block, and
-              row-argmax agreement > 85 %.
+              require mean |d| < 0.03 and max |d| < 0.2 on the valid block (the build's envelope), and
+              row-argmax agreement > 95 % (measured 97.7-100 %).
 """
 import math
 
@@ -66,7 +66,10 @@ def compare_to_oracle(out, res, m, n, fp32=True, la_tol=1e-3):
             tol = la_tol(la_o) if callable(la_tol) else la_tol
             assert diff.max() < tol, f"pair {b}: max |dlog_assignment| = {diff.max():.2e} (tolerance {tol:.1e})"
         else:
-            assert diff.mean() < 0.05 and diff.max() < 0.5, f"pair {b}: mean {diff.mean():.3f} max {diff.max():.3f}"
+            # the build's own envelope at random-init logit scale (measured on B200, pytest -s: mean 0.008-0.020, max
+            # 0.04-0.12 at 1-300 keypoints; DESIGN.md section 2 states the reference-level envelope 0.05 / 0.5)
+            print(f"[bf16 vs oracle] pair {b} ({n0}x{n1}): mean|d| {float(diff.mean()):.4f} max|d| {float(diff.max()):.4f}")
+            assert diff.mean() < 0.03 and diff.max() < 0.2, f"pair {b}: mean {diff.mean():.3f} max {diff.max():.3f}"
         m0, m1 = out["matches0"][b].cpu(), out["matches1"][b].cpu()
         s0, s1 = out["matching_scores0"][b].cpu(), out["matching_scores1"][b].cpu()
         if fp32 and "ind0" in r and n0 == r["matches0"].shape[0]:  # un-pruned: index spaces coincide
@@ -91,7 +94,8 @@ def compare_to_oracle(out, res, m, n, fp32=True, la_tol=1e-3):
         else:
             e0 = r["matches0"]
             agree = (la[:n0, :n1].argmax(1) == la_o[:n0, :n1].argmax(1)).float().mean()
-            assert agree > 0.85, f"pair {b}: row-argmax agreement {agree:.3f}"
+            print(f"[bf16 vs oracle] pair {b}: row-argmax agreement {float(agree):.4f}")  # measured 0.977-1.0
+            assert agree > 0.95, f"pair {b}: row-argmax agreement {agree:.3f}"
         # padded entries
         assert (m0[n0:] == -1).all() if n0 < m and "ind0" in r and n0 == r["matches0"].shape[0] else True
 
