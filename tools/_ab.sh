@@ -1,2 +1,2 @@
 cd /root/repo
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py -q -x 2>&1 | tail -3
+timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/gputest_all.log 2>&1; tail -4 gpurun_out/gputest_all.log | cut -c1-400
