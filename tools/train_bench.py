@@ -52,7 +52,7 @@ def timed(model, label, extra=None):
 for ckpt in (False, True):
     torch.manual_seed(0)
     ours = LightGlue({**conf, "checkpointed": ckpt}).to(dev).train()
-    timed(ours, f"glue_factory_colon_b200 (fp32 kernels forward, lg_bwd.cu + cuBLAS GEMMs backward), checkpointed={ckpt}")
+    timed(ours, f"glue_factory_colon_b200 (fp32-accurate tcgen05 kernels forward and backward, three-product tensor-core GEMMs), checkpointed={ckpt}")
     del ours
     torch.cuda.empty_cache()
 for ckpt in (False, True):
