@@ -15,9 +15,9 @@
 // [256, 512) (gradients have no fixed range: a fixed scaling would push small ones into the fp16 subnormals), P the
 // scaling LG_X3_EP and D the scaling g / 64; all are powers of two and are undone exactly in the epilogue.
 // CTA = warp 0 TMA producer, warp 1 MMA issuer, warps 2.. "softmax" warps (NP threads per own row).
-// ALL MMAs ARE OF THE TS FORM (A operand from TMEM): tools/micro/umma_rate.cu measures 75 cycles for an SS MMA of
-// 128 x 64 x 16 (the 4 KB A tile is fetched from shared memory in ~43 cycles that do not overlap the MMA) against 42 for
-// the TS form, so the own rows X, U are copied into TMEM once per CTA by the softmax threads (plain global loads +
+// ALL MMAs ARE OF THE TS FORM (A operand from TMEM): tools/micro/umma_rate.cu measures 48 cycles for an SS MMA of
+// 128 x 64 x 16 (6 KB of operands per MMA against the SM's 128 B/clk of shared memory) and the nominal 32 for the TS
+// form, so the own rows X, U are copied into TMEM once per CTA by the softmax threads (plain global loads +
 // tcgen05.st) and never pass through shared memory.  TMEM (512 columns, one CTA per SM): sc x 2 | dp x 2 (double-
 // buffered: the score MMAs of tile j+1 run while the warps work on tile j; a thread writes the D / P plane pairs of a
 // tile OVER ITS OWN score columns, so the planes are double-buffered too and no thread waits for another) | out1 | out2

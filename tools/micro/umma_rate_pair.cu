@@ -1,7 +1,7 @@
-// Microbenchmark: tcgen05.mma.cta_group::2 (kind::f16, bf16, M = 256 over a CTA pair, K = 16) cycles per MMA for N = 128 and
-// N = 256, SS form: each CTA supplies its 128 A rows (4 KB per K step) and its half of B (N/2 rows).  The leader CTA's
-// elected thread issues ITERS x 8 MMAs back to back, commits to a barrier in both CTAs, both wait.  Companion of
-// umma_rate.cu (cta_group::1): does the pair MMA pay the same ~43-cycle A fetch per K step?
+// Microbenchmark: tcgen05.mma.cta_group::2 (kind::f16, bf16, M = 256 over a CTA pair, K = 16) cycles per MMA for N = 64 /
+// 128 / 256 in the SS form (each CTA supplies its 128 A rows, 4 KB per K step, and its half of B) and the TS form (A from
+// each CTA's TMEM).  The leader CTA's elected thread issues ITERS x 8 MMAs back to back, commits to a barrier in both
+// CTAs, both wait.  Companion of umma_rate.cu (cta_group::1).  B200: nominal N/2 cycles everywhere except SS N = 64 (43).
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -I glue_factory_colon_b200/csrc tools/micro/umma_rate_pair.cu -o umma_rate_pair -lcuda
 #include <cstdio>
 #include <cstdint>
@@ -18,6 +18,8 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// TS is a compile-time switch: predicated-off MMAs left in the issue stream by a runtime switch are not free
+template <int TS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) k(int N, int iters, long long* cyc) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
@@ -55,12 +57,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) k(int N, int it
             const uint64_t a = dA + (uint64_t)((ks >> 2) * (16384 >> 4) + (ks & 3) * 2);
             const uint64_t b = dB + (uint64_t)((ks >> 2) * (((N / 2) * 128) >> 4) + (ks & 3) * 2);
             const uint32_t acc = (it | ks) != 0;
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "setp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem),
-                "l"(a), "l"(b), "r"(idesc), "r"(acc)
-                : "memory");
+            if constexpr (TS)  // A from TMEM (each CTA's own 128 rows at columns 192..), N <= 128
+              asm volatile(
+                  "{\n\t.reg .pred p;\n\t"
+                  "setp.ne.b32 p, %4, 0;\n\t"
+                  "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem),
+                  "r"(tmem + 192 + ks * 8), "l"(b), "r"(idesc), "r"(acc)
+                  : "memory");
+            else
+              asm volatile(
+                  "{\n\t.reg .pred p;\n\t"
+                  "setp.ne.b32 p, %4, 0;\n\t"
+                  "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem),
+                  "l"(a), "l"(b), "r"(idesc), "r"(acc)
+                  : "memory");
           }
         }
         asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -88,10 +98,16 @@ int main() {
   cudaMalloc(&cyc, 1024 * sizeof(long long));
   const int iters = 2000;
   const int smem = 163840 - 2048;  // one CTA per SM
-  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  for (int N : {128, 256}) {
+  for (int cfg = 0; cfg < 5; ++cfg) {
+    const int N = cfg == 0 ? 128 : cfg == 1 ? 256 : cfg == 2 ? 64 : cfg == 3 ? 64 : 128;
+    const int ts = cfg >= 3;
     const int grid = 148;
-    for (int rep = 0; rep < 2; ++rep) k<<<grid, 128, smem, 0>>>(N, iters, cyc);
+    cudaFuncSetAttribute(k<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    for (int rep = 0; rep < 2; ++rep) {
+      if (ts) k<1><<<grid, 128, smem, 0>>>(N, iters, cyc);
+      else k<0><<<grid, 128, smem, 0>>>(N, iters, cyc);
+    }
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
     long long h[148];
@@ -100,8 +116,8 @@ int main() {
     int n = 0;
     for (int i = 0; i < grid; i += 2) { avg += (double)h[i]; ++n; }  // leaders
     const double per = avg / n / (iters * 8.0);
-    printf("SS cta_group::2 M=256 N=%3d K=16: %6.1f cycles per MMA (ideal at 8192 FLOP/clk/SM: %5.1f), per CTA: A 4096 B + B %d B from shared memory\n",
-           N, per, N / 2.0, (N / 2) * 32);
+    printf("%s cta_group::2 M=256 N=%3d K=16: %6.1f cycles per MMA (ideal at 8192 FLOP/clk/SM: %5.1f), per CTA: A %d B + B %d B from shared memory\n",
+           ts ? "TS" : "SS", N, per, N / 2.0, ts ? 0 : 4096, (N / 2) * 32);
   }
   return 0;
 }
