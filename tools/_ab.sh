@@ -1,2 +1,3 @@
 cd /root/repo
-timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/gputest_all.log 2>&1; tail -4 gpurun_out/gputest_all.log | cut -c1-400
+timeout 600 python -m pytest tests/test_gpu_grad.py -q -x -k "attention_bwd" 2>&1 | tail -2
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | cut -c1-200
